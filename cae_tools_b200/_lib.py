@@ -1,0 +1,116 @@
+"""ctypes binding of libcae_b200.so (see include/cae_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or was built for the
+wrong architecture, importing :func:`lib` raises and every product path that needs
+arithmetic fails loudly.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcae_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class CaeView(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("N", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("ld", C.c_int), ("sC", C.c_longlong), ("sN", C.c_longlong)]
+
+
+class CaeSrc(C.Structure):
+    _fields_ = [("t0", CaeView), ("t1", C.c_void_p), ("k0", C.c_void_p), ("k1", C.c_void_p), ("k2", C.c_void_p),
+                ("relu", C.c_int), ("cursor", C.c_void_p), ("cursor_stride", C.c_longlong)]
+
+
+class CaeConvGeom(C.Structure):
+    _fields_ = [("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("pad", C.c_int)]
+
+
+class CaeBN(C.Structure):
+    _fields_ = [("C", C.c_int), ("eps", C.c_float), ("momentum", C.c_float),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dbias", C.c_void_p),
+                ("bwdA", C.c_void_p), ("bwdB", C.c_void_p), ("bwdC", C.c_void_p)]
+
+
+class CaeEpilogue(C.Structure):
+    _fields_ = [("mode", C.c_int), ("bias", C.c_void_p), ("partials", C.c_void_p), ("ticket", C.c_void_p),
+                ("bn", CaeBN), ("act", CaeView), ("target", CaeSrc), ("loss_out", C.c_void_p),
+                ("dbias", C.c_void_p), ("write_mode", C.c_int)]
+
+
+class CaeGemm(C.Structure):
+    _fields_ = [("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("A", C.c_void_p), ("sAm", C.c_longlong), ("sAk", C.c_longlong),
+                ("B", C.c_void_p), ("sBk", C.c_longlong), ("sBn", C.c_longlong),
+                ("C", C.c_void_p), ("sCm", C.c_longlong), ("sCn", C.c_longlong),
+                ("a_k0", C.c_void_p), ("a_k2", C.c_void_p), ("a_hw", C.c_int), ("a_relu", C.c_int),
+                ("b_k0", C.c_void_p), ("b_k2", C.c_void_p), ("b_hw", C.c_int), ("b_relu", C.c_int),
+                ("bias", C.c_void_p), ("relu_out", C.c_int), ("mask", C.c_void_p), ("rowsum_A", C.c_void_p)]
+
+
+EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE = 0, 1, 2, 3, 4
+
+# every symbol include/cae_b200.h declares
+EXPORTS = {
+    "cae_last_error": (C.c_char_p, []),
+    "cae_version": (C.c_int, []),
+    "cae_partials_len": (C.c_longlong, [C.c_int]),
+    "cae_conv_down": (C.c_int, [C.POINTER(CaeSrc), C.c_void_p, C.POINTER(CaeConvGeom), C.POINTER(CaeView),
+                                C.POINTER(CaeEpilogue), C.c_void_p]),
+    "cae_conv_up": (C.c_int, [C.POINTER(CaeSrc), C.c_void_p, C.POINTER(CaeConvGeom), C.POINTER(CaeView),
+                              C.POINTER(CaeEpilogue), C.c_void_p]),
+    "cae_conv_wgrad": (C.c_int, [C.POINTER(CaeSrc), C.POINTER(CaeSrc), C.POINTER(CaeConvGeom), C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cae_wgrad_partials_len": (C.c_longlong, [C.POINTER(CaeSrc), C.POINTER(CaeSrc), C.POINTER(CaeConvGeom)]),
+    "cae_ew_epilogue": (C.c_int, [C.POINTER(CaeSrc), C.POINTER(CaeView), C.POINTER(CaeEpilogue), C.c_void_p]),
+    "cae_gemm": (C.c_int, [C.POINTER(CaeGemm), C.c_void_p]),
+    "cae_bn_eval_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cae_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                          C.c_void_p]),
+    "cae_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float,
+                           C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "cae_step_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+class CaeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raise if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CaeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in EXPORTS.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is missing
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().cae_last_error().decode("utf-8", "replace")
+        raise CaeError(f"{what or 'libcae_b200'} failed (code {rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise CaeError("cae_tools_b200 needs a CUDA device (sm_100a); there is no CPU fallback for the hot path")
+    lib()

@@ -1,0 +1,342 @@
+// C ABI of libcae_b200.so: argument checking, kernel selection, launches.  See include/cae_b200.h.
+#include <stdarg.h>
+#include <string.h>
+#include "conv_family.cuh"
+#include "dense_misc.cuh"
+
+static thread_local char g_err[512] = "";
+
+void cae_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cae_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cae_set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return CAE_OK;
+}
+
+extern "C" const char* cae_last_error(void) { return g_err; }
+extern "C" int cae_version(void) { return 100; }
+extern "C" long long cae_partials_len(int C) { return (long long)CAE_MAX_GRID_X * C * 2; }
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static int check_view(const CaeView& v, const char* name) {
+    CAE_REQUIRE(v.p != nullptr, "%s: null pointer", name);
+    CAE_REQUIRE(v.N > 0 && v.C > 0 && v.H > 0 && v.W > 0, "%s: empty tensor %dx%dx%dx%d", name, v.N, v.C, v.H, v.W);
+    CAE_REQUIRE(v.ld >= v.W, "%s: ld %d < W %d", name, v.ld, v.W);
+    CAE_REQUIRE((long long)v.N * v.C * v.H * v.W < (1ll << 31), "%s: tensor too large for 32-bit positions", name);
+    return CAE_OK;
+}
+
+static int check_epilogue(const CaeEpilogue& e, const CaeView& out) {
+    CAE_REQUIRE(e.mode >= CAE_EPI_PLAIN && e.mode <= CAE_EPI_SIGMOID_MSE, "epilogue: bad mode %d", e.mode);
+    if (epi_reduces(e.mode)) {
+        CAE_REQUIRE(e.partials && e.ticket, "epilogue: reducing mode needs partials + ticket");
+    }
+    if (e.mode == CAE_EPI_STATS) {
+        CAE_REQUIRE(e.bn.C == out.C && e.bn.scale && e.bn.shift && e.bn.mean && e.bn.invstd,
+                    "epilogue STATS: BN block incomplete (C=%d vs out C=%d)", e.bn.C, out.C);
+    }
+    if (e.mode == CAE_EPI_MASKSTATS) {
+        CAE_REQUIRE(e.act.p, "epilogue MASKSTATS: act view missing");
+        CAE_REQUIRE(e.act.N == out.N && e.act.C == out.C && e.act.H == out.H && e.act.W == out.W,
+                    "epilogue MASKSTATS: act geometry differs from output");
+        CAE_REQUIRE(e.bn.C == out.C && e.bn.scale && e.bn.shift && e.bn.mean && e.bn.invstd && e.bn.bwdA &&
+                        e.bn.bwdB && e.bn.bwdC,
+                    "epilogue MASKSTATS: BN block incomplete");
+    }
+    if (e.mode == CAE_EPI_SIGMOID_MSE) {
+        const CaeView& t = e.target.t0;
+        CAE_REQUIRE(t.p && t.N == out.N && t.C == out.C && t.H == out.H && t.W == out.W,
+                    "epilogue MSE: target geometry differs from output");
+        CAE_REQUIRE(e.write_mode >= 0 && e.write_mode <= 2, "epilogue MSE: bad write_mode");
+    }
+    return CAE_OK;
+}
+
+// choose output channels per thread: largest of {8,4,2,1} that still yields >= 2 CTAs per SM,
+// otherwise the one that maximises the CTA count
+static int pick_cot(int Cout, int grid_x, int max_cot) {
+    const int opts[4] = {8, 4, 2, 1};
+    for (int i = 0; i < 4; ++i) {
+        int c = opts[i];
+        if (c > max_cot || c > Cout) continue;
+        long long ctas = (long long)grid_x * ((Cout + c - 1) / c);
+        if (ctas >= 2 * CAE_NUM_SMS) return c;
+    }
+    return 1;
+}
+
+static const int kSmemBudget = 40 * 1024;
+
+template <int KH, int KW, int S>
+static int launch_up_t(ConvArgs& a, cudaStream_t st) {
+    int gx = min(ceil_div(a.total, CAE_NT), CAE_MAX_GRID_X);
+    int cot = pick_cot(a.Cout, gx, S * S * 8 <= 32 ? 8 : 4);
+    int kk = KH * KW;
+    a.ci_chunk = min(a.Cin, max(1, kSmemBudget / (kk * cot * 4)));
+    size_t smem = (size_t)a.ci_chunk * kk * cot * 4;
+    dim3 grid(gx, ceil_div(a.Cout, cot));
+    switch (cot) {
+        case 8: k_conv_up<KH, KW, S, 8><<<grid, CAE_NT, smem, st>>>(a); break;
+        case 4: k_conv_up<KH, KW, S, 4><<<grid, CAE_NT, smem, st>>>(a); break;
+        case 2: k_conv_up<KH, KW, S, 2><<<grid, CAE_NT, smem, st>>>(a); break;
+        default: k_conv_up<KH, KW, S, 1><<<grid, CAE_NT, smem, st>>>(a); break;
+    }
+    return cae_check_launch("cae_conv_up");
+}
+
+template <int KH, int KW, int S>
+static int launch_down_t(ConvArgs& a, cudaStream_t st) {
+    int gx = min(ceil_div(a.total, CAE_NT), CAE_MAX_GRID_X);
+    int cot = pick_cot(a.Cout, gx, 8);
+    int kk = KH * KW;
+    a.ci_chunk = min(a.Cin, max(1, kSmemBudget / (kk * cot * 4)));
+    size_t smem = (size_t)a.ci_chunk * kk * cot * 4;
+    dim3 grid(gx, ceil_div(a.Cout, cot));
+    switch (cot) {
+        case 8: k_conv_down<KH, KW, S, 8><<<grid, CAE_NT, smem, st>>>(a); break;
+        case 4: k_conv_down<KH, KW, S, 4><<<grid, CAE_NT, smem, st>>>(a); break;
+        case 2: k_conv_down<KH, KW, S, 2><<<grid, CAE_NT, smem, st>>>(a); break;
+        default: k_conv_down<KH, KW, S, 1><<<grid, CAE_NT, smem, st>>>(a); break;
+    }
+    return cae_check_launch("cae_conv_down");
+}
+
+static int fill_conv_args(ConvArgs& a, const CaeSrc* in, const float* weight, const CaeConvGeom* g, const CaeView* out,
+                          const CaeEpilogue* epi) {
+    CAE_REQUIRE(in && weight && g && out && epi, "conv: null argument");
+    int rc;
+    if ((rc = check_view(in->t0, "conv input"))) return rc;
+    if ((rc = check_view(*out, "conv output"))) return rc;
+    CAE_REQUIRE(g->kh > 0 && g->kw > 0 && g->stride > 0 && g->pad >= 0, "conv: bad geometry k=%dx%d s=%d p=%d", g->kh,
+                g->kw, g->stride, g->pad);
+    CAE_REQUIRE(in->t0.N == out->N, "conv: batch mismatch %d vs %d", in->t0.N, out->N);
+    memset(&a, 0, sizeof(a));
+    a.in = *in;
+    a.w = weight;
+    a.kh = g->kh; a.kw = g->kw; a.s = g->stride; a.p = g->pad;
+    a.out = *out;
+    a.epi = *epi;
+    if (a.epi.mode == CAE_EPI_MASKSTATS && a.epi.act.p == nullptr) a.epi.mode = CAE_EPI_PLAIN;
+    if ((rc = check_epilogue(a.epi, *out))) return rc;
+    a.Cin = in->t0.C;
+    a.Cout = out->C;
+    a.inv_count = (float)(1.0 / ((double)out->N * out->C * out->H * out->W));
+    return CAE_OK;
+}
+
+extern "C" int cae_conv_up(const CaeSrc* in, const float* weight, const CaeConvGeom* g, const CaeView* out,
+                           const CaeEpilogue* epi, void* stream) {
+    ConvArgs a;
+    int rc = fill_conv_args(a, in, weight, g, out, epi);
+    if (rc) return rc;
+    const CaeView& iv = in->t0;
+    // Hout = (Hin-1)*s - 2p + kh + output_padding, 0 <= output_padding < s
+    int hmin = (iv.H - 1) * a.s - 2 * a.p + a.kh, wmin = (iv.W - 1) * a.s - 2 * a.p + a.kw;
+    CAE_REQUIRE(out->H >= hmin && out->H < hmin + max(a.s, 1) && out->W >= wmin && out->W < wmin + max(a.s, 1),
+                "conv_up: output %dx%d inconsistent with input %dx%d k=%dx%d s=%d p=%d", out->H, out->W, iv.H, iv.W,
+                a.kh, a.kw, a.s, a.p);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a.s == 2 && a.kh >= 3 && a.kh <= 4 && a.kw >= 3 && a.kw <= 4) {
+        a.QH = (out->H - 1 + a.p) / a.s + 1;
+        a.QW = (out->W - 1 + a.p) / a.s + 1;
+        a.total = out->N * a.QH * a.QW;
+        if (a.kh == 3 && a.kw == 3) return launch_up_t<3, 3, 2>(a, st);
+        if (a.kh == 4 && a.kw == 4) return launch_up_t<4, 4, 2>(a, st);
+        if (a.kh == 4 && a.kw == 3) return launch_up_t<4, 3, 2>(a, st);
+        return launch_up_t<3, 4, 2>(a, st);
+    }
+    a.QH = out->H; a.QW = out->W;
+    a.total = out->N * out->H * out->W;
+    dim3 grid(min(ceil_div(a.total, CAE_NT), CAE_MAX_GRID_X), a.Cout);
+    k_conv_up_generic<<<grid, CAE_NT, 0, st>>>(a);
+    return cae_check_launch("cae_conv_up(generic)");
+}
+
+extern "C" int cae_conv_down(const CaeSrc* in, const float* weight, const CaeConvGeom* g, const CaeView* out,
+                             const CaeEpilogue* epi, void* stream) {
+    ConvArgs a;
+    int rc = fill_conv_args(a, in, weight, g, out, epi);
+    if (rc) return rc;
+    const CaeView& iv = in->t0;
+    // Hout <= (Hin + 2p - kh)/s + 1  (a transposed conv with output_padding leaves unused input rows)
+    CAE_REQUIRE((out->H - 1) * a.s + a.kh <= iv.H + 2 * a.p && (out->W - 1) * a.s + a.kw <= iv.W + 2 * a.p,
+                "conv_down: output %dx%d too large for input %dx%d k=%dx%d s=%d p=%d", out->H, out->W, iv.H, iv.W, a.kh,
+                a.kw, a.s, a.p);
+    cudaStream_t st = (cudaStream_t)stream;
+    a.QH = out->H; a.QW = out->W;
+    a.total = out->N * out->H * out->W;
+    if (a.s == 2 && a.kh >= 3 && a.kh <= 4 && a.kw >= 3 && a.kw <= 4) {
+        if (a.kh == 3 && a.kw == 3) return launch_down_t<3, 3, 2>(a, st);
+        if (a.kh == 4 && a.kw == 4) return launch_down_t<4, 4, 2>(a, st);
+        if (a.kh == 4 && a.kw == 3) return launch_down_t<4, 3, 2>(a, st);
+        return launch_down_t<3, 4, 2>(a, st);
+    }
+    dim3 grid(min(ceil_div(a.total, CAE_NT), CAE_MAX_GRID_X), a.Cout);
+    k_conv_down_generic<<<grid, CAE_NT, 0, st>>>(a);
+    return cae_check_launch("cae_conv_down(generic)");
+}
+
+extern "C" int cae_ew_epilogue(const CaeSrc* in, const CaeView* out, const CaeEpilogue* epi, void* stream) {
+    CAE_REQUIRE(in && out && epi, "ew: null argument");
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc;
+    if ((rc = check_view(in->t0, "ew input"))) return rc;
+    if ((rc = check_view(*out, "ew output"))) return rc;
+    CAE_REQUIRE(in->t0.N == out->N && in->t0.C == out->C && in->t0.H == out->H && in->t0.W == out->W,
+                "ew: geometry mismatch");
+    a.in = *in;
+    a.out = *out;
+    a.epi = *epi;
+    if (a.epi.mode == CAE_EPI_MASKSTATS && a.epi.act.p == nullptr) a.epi.mode = CAE_EPI_PLAIN;
+    if ((rc = check_epilogue(a.epi, *out))) return rc;
+    a.Cin = a.Cout = out->C;
+    a.QH = out->H; a.QW = out->W;
+    a.total = out->N * out->H * out->W;
+    a.inv_count = (float)(1.0 / ((double)out->N * out->C * out->H * out->W));
+    dim3 grid(min(ceil_div(a.total, CAE_NT), CAE_MAX_GRID_X), out->C);
+    k_ew_epilogue<<<grid, CAE_NT, 0, (cudaStream_t)stream>>>(a);
+    return cae_check_launch("cae_ew_epilogue");
+}
+
+// ---- weight gradient -------------------------------------------------------------------
+#define CAE_WGRAD_MAX_CHUNKS 1024
+
+struct WgradPlan {
+    int cst, cbt, ntiles, tiles_b, nchunks, chunk;
+    bool generic;
+};
+
+static WgradPlan plan_wgrad(int Cs, int Cb, int kh, int kw, int s, int total) {
+    WgradPlan p;
+    p.generic = !(s == 2 && kh >= 3 && kh <= 4 && kw >= 3 && kw <= 4);
+    if (p.generic) {
+        p.cst = p.cbt = 1;
+        p.ntiles = Cs * Cb * kh * kw;
+        p.tiles_b = Cb;
+    } else {
+        int kk = kh * kw;
+        p.cst = Cs >= 4 ? 4 : (Cs >= 2 ? 2 : 1);
+        p.cbt = Cb >= 2 ? 2 : 1;
+        if (kk > 12 && p.cst == 4) p.cst = 2;                 // keep <= 64 accumulators
+        if (p.cst == 4 && p.cbt == 1) p.cst = 2;              // instantiated: (4,2) (2,2) (2,1) (1,2) (1,1)
+        p.tiles_b = (Cb + p.cbt - 1) / p.cbt;
+        p.ntiles = ((Cs + p.cst - 1) / p.cst) * p.tiles_b;
+    }
+    // enough warps to fill the machine (148 SMs x 8 warps x 2), at least 64 positions per warp
+    long long want = (2ll * CAE_NUM_SMS * CAE_NWARP + p.ntiles - 1) / p.ntiles;
+    long long cap = (total + 63) / 64;
+    long long n = want < cap ? want : cap;
+    if (n < 1) n = 1;
+    if (n > CAE_WGRAD_MAX_CHUNKS) n = CAE_WGRAD_MAX_CHUNKS;
+    p.nchunks = (int)n;
+    p.chunk = (total + p.nchunks - 1) / p.nchunks;
+    p.nchunks = (total + p.chunk - 1) / p.chunk;
+    return p;
+}
+
+static int check_wgrad(const CaeSrc* sm, const CaeSrc* bg, const CaeConvGeom* g) {
+    CAE_REQUIRE(sm && bg && g, "wgrad: null argument");
+    int rc;
+    if ((rc = check_view(sm->t0, "wgrad small operand"))) return rc;
+    if ((rc = check_view(bg->t0, "wgrad big operand"))) return rc;
+    CAE_REQUIRE(sm->t0.N == bg->t0.N, "wgrad: batch mismatch");
+    CAE_REQUIRE(g->kh > 0 && g->kw > 0 && g->stride > 0 && g->pad >= 0, "wgrad: bad geometry");
+    return CAE_OK;
+}
+
+extern "C" long long cae_wgrad_partials_len(const CaeSrc* sm, const CaeSrc* bg, const CaeConvGeom* g) {
+    if (check_wgrad(sm, bg, g)) return -1;
+    WgradPlan p = plan_wgrad(sm->t0.C, bg->t0.C, g->kh, g->kw, g->stride, sm->t0.N * sm->t0.H * sm->t0.W);
+    return (long long)p.nchunks * sm->t0.C * bg->t0.C * g->kh * g->kw;
+}
+
+template <int KH, int KW, int S>
+static int launch_wgrad_t(WgradArgs& a, const WgradPlan& p, cudaStream_t st) {
+    int grid = ceil_div((long long)p.ntiles * p.nchunks, CAE_NWARP);
+    constexpr bool big = KH * KW > 12;
+    if (p.cst == 4 && p.cbt == 2) {
+        if constexpr (!big) k_conv_wgrad<KH, KW, S, 4, 2><<<grid, CAE_NT, 0, st>>>(a);
+    } else if (p.cst == 2 && p.cbt == 2) k_conv_wgrad<KH, KW, S, 2, 2><<<grid, CAE_NT, 0, st>>>(a);
+    else if (p.cst == 2 && p.cbt == 1) k_conv_wgrad<KH, KW, S, 2, 1><<<grid, CAE_NT, 0, st>>>(a);
+    else if (p.cst == 1 && p.cbt == 2) k_conv_wgrad<KH, KW, S, 1, 2><<<grid, CAE_NT, 0, st>>>(a);
+    else k_conv_wgrad<KH, KW, S, 1, 1><<<grid, CAE_NT, 0, st>>>(a);
+    return cae_check_launch("cae_conv_wgrad");
+}
+
+extern "C" int cae_conv_wgrad(const CaeSrc* sm, const CaeSrc* bg, const CaeConvGeom* g, float* grad, float* partials,
+                              unsigned int* ticket, void* stream) {
+    int rc = check_wgrad(sm, bg, g);
+    if (rc) return rc;
+    CAE_REQUIRE(grad && partials && ticket, "wgrad: null output/workspace");
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sm = *sm; a.bg = *bg;
+    a.kh = g->kh; a.kw = g->kw; a.s = g->stride; a.p = g->pad;
+    a.grad = grad; a.partials = partials; a.ticket = ticket;
+    a.Cs = sm->t0.C; a.Cb = bg->t0.C;
+    a.total = sm->t0.N * sm->t0.H * sm->t0.W;
+    WgradPlan p = plan_wgrad(a.Cs, a.Cb, a.kh, a.kw, a.s, a.total);
+    a.chunk = p.chunk; a.tiles_b = p.tiles_b; a.ntiles = p.ntiles; a.nchunks = p.nchunks;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p.generic) {
+        if (a.kh == 3 && a.kw == 3) return launch_wgrad_t<3, 3, 2>(a, p, st);
+        if (a.kh == 4 && a.kw == 4) return launch_wgrad_t<4, 4, 2>(a, p, st);
+        if (a.kh == 4 && a.kw == 3) return launch_wgrad_t<4, 3, 2>(a, p, st);
+        return launch_wgrad_t<3, 4, 2>(a, p, st);
+    }
+    int grid = ceil_div((long long)p.ntiles * p.nchunks, CAE_NWARP);
+    k_conv_wgrad_generic<<<grid, CAE_NT, 0, st>>>(a);
+    return cae_check_launch("cae_conv_wgrad(generic)");
+}
+
+// ---- dense / misc ------------------------------------------------------------------------
+extern "C" int cae_gemm(const CaeGemm* g, void* stream) {
+    CAE_REQUIRE(g && g->A && g->B && g->C, "gemm: null argument");
+    CAE_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm: empty problem %dx%dx%d", g->M, g->N, g->K);
+    CAE_REQUIRE((!g->a_k0 || (g->a_k2 && g->a_hw > 0)) && (!g->b_k0 || (g->b_k2 && g->b_hw > 0)),
+                "gemm: on-load affine needs k0, k2 and hw");
+    dim3 grid(ceil_div(g->N, GT), ceil_div(g->M, GT));
+    k_gemm<<<grid, CAE_NT, 0, (cudaStream_t)stream>>>(*g);
+    return cae_check_launch("cae_gemm");
+}
+
+extern "C" int cae_bn_eval_prepare(const CaeBN* device_table, int count, void* stream) {
+    CAE_REQUIRE(device_table && count > 0, "bn_eval_prepare: bad argument");
+    k_bn_eval_prepare<<<count, 128, 0, (cudaStream_t)stream>>>(device_table, count);
+    return cae_check_launch("cae_bn_eval_prepare");
+}
+
+extern "C" int cae_mse(const float* a, const float* b, long long n, double* partials, unsigned int* ticket,
+                       float* loss_out, const int* cursor, void* stream) {
+    CAE_REQUIRE(a && b && partials && ticket && loss_out && n > 0, "mse: bad argument");
+    int grid = min(ceil_div(n, CAE_NT * 4), CAE_MAX_GRID_X);
+    k_mse<<<grid, CAE_NT, 0, (cudaStream_t)stream>>>(a, b, n, partials, ticket, loss_out, cursor);
+    return cae_check_launch("cae_mse");
+}
+
+extern "C" int cae_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int decoupled, float grad_scale, const int* step_count,
+                        void* stream) {
+    CAE_REQUIRE(p && g && m && v && step_count && n > 0, "adam: bad argument");
+    int grid = min(ceil_div(n, CAE_NT), CAE_NUM_SMS * 8);
+    k_adam<<<grid, CAE_NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled,
+                                                       grad_scale, step_count);
+    return cae_check_launch("cae_adam");
+}
+
+extern "C" int cae_step_advance(int* step_count, int* cursor, int n_batches, void* stream) {
+    CAE_REQUIRE(step_count || cursor, "step_advance: nothing to do");
+    k_step_advance<<<1, 32, 0, (cudaStream_t)stream>>>(step_count, cursor, n_batches);
+    return cae_check_launch("cae_step_advance");
+}

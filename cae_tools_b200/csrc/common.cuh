@@ -1,0 +1,166 @@
+// Shared device/host helpers for libcae_b200.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/cae_b200.h"
+
+#define CAE_NT 256            // threads per CTA for all family kernels
+#define CAE_NWARP (CAE_NT / 32)
+#define CAE_NUM_SMS 148       // B200
+#define CAE_MAX_GRID_X (CAE_NUM_SMS * 4)   // persistent-style cap: partial-sum rows per kernel
+
+void cae_set_error(const char* fmt, ...);
+int  cae_check_launch(const char* what);
+
+#define CAE_REQUIRE(cond, ...)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            cae_set_error(__VA_ARGS__);                \
+            return CAE_EINVAL;                         \
+        }                                              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// operand access
+// ---------------------------------------------------------------------------------------
+struct ChanCoef {
+    float k0, k1, k2;
+};
+
+__device__ __forceinline__ ChanCoef load_coef(const CaeSrc& s, int c) {
+    ChanCoef k;
+    k.k0 = s.k0 ? __ldg(s.k0 + c) : 1.f;
+    k.k1 = s.k1 ? __ldg(s.k1 + c) : 0.f;
+    k.k2 = s.k2 ? __ldg(s.k2 + c) : 0.f;
+    return k;
+}
+
+__device__ __forceinline__ long long src_cursor_offset(const CaeSrc& s) {
+    return s.cursor ? (long long)(__ldg(s.cursor)) * s.cursor_stride : 0ll;
+}
+
+// value of operand element at element offset `off` (cursor offset already included)
+__device__ __forceinline__ float src_value(const CaeSrc& s, long long off, const ChanCoef& k) {
+    float v = fmaf(__ldg(s.t0.p + off), k.k0, k.k2);
+    if (s.t1) v = fmaf(__ldg(s.t1 + off), k.k1, v);
+    if (s.relu) v = fmaxf(v, 0.f);
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// deterministic two-stage reduction: every CTA writes one row of partial sums, the CTA that
+// takes the last ticket reduces the rows in index order (result independent of scheduling).
+// ---------------------------------------------------------------------------------------
+// returns true (uniformly over the CTA) in exactly one CTA of the grid: the last to arrive
+__device__ __forceinline__ bool cae_last_block(unsigned int* ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == total - 1u);
+        if (s_last) *ticket = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// Reduce NV per-thread floats over the CTA and store them (as doubles) at dst[0..nvalid).
+// Must be called by all CTA_NT threads.
+template <int NV>
+__device__ __forceinline__ void cta_reduce_store(float (&v)[NV], double* dst, int nvalid) {
+    __shared__ double red[CAE_NWARP][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double d = warp_sum_d((double)v[i]);
+        if (lane == 0) red[warp][i] = d;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nvalid) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < CAE_NWARP; ++w) s += red[w][threadIdx.x];
+        dst[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// Sum column `col` (of `ncols`) over `rows` rows of a row-major double matrix, by one warp,
+// in a fixed order; result valid in all lanes.
+__device__ __forceinline__ double warp_colsum(const double* part, int rows, int ncols, int col) {
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int r = lane; r < rows; r += 32) s += __ldcg(part + (size_t)r * ncols + col);
+    return warp_sum_d(s);
+}
+
+// ---- finalizers (executed by the last CTA; `rows` = gridDim.x partial rows of C*2 doubles) ----
+// BatchNorm forward statistics (training): reference semantics of nn.BatchNorm2d
+// (biased variance for normalisation, unbiased for running_var, momentum update).
+__device__ __forceinline__ void finalize_bn_forward(const CaeBN& bn, const double* part, int rows, double count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < bn.C; c += CAE_NWARP) {
+        double S = warp_colsum(part, rows, bn.C * 2, c * 2 + 0);
+        double Q = warp_colsum(part, rows, bn.C * 2, c * 2 + 1);
+        if (lane == 0) {
+            double mean = S / count;
+            double var = Q / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            double invstd = rsqrt(var + (double)bn.eps);
+            float g = bn.gamma ? bn.gamma[c] : 1.f;
+            float b = bn.beta ? bn.beta[c] : 0.f;
+            float scale = (float)((double)g * invstd);
+            bn.scale[c] = scale;
+            bn.shift[c] = (float)((double)b - mean * (double)g * invstd);
+            bn.mean[c] = (float)mean;
+            bn.invstd[c] = (float)invstd;
+            if (bn.running_mean) {
+                double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                double m = (double)bn.momentum;
+                bn.running_mean[c] = (float)((1.0 - m) * (double)bn.running_mean[c] + m * mean);
+                bn.running_var[c] = (float)((1.0 - m) * (double)bn.running_var[c] + m * unbiased);
+            }
+        }
+    }
+    if (threadIdx.x == 0 && bn.num_batches_tracked) bn.num_batches_tracked[0] += 1;
+}
+
+// BatchNorm backward sums -> dgamma, dbeta and the coefficients of dL/dy = A*dz + B*y + C
+__device__ __forceinline__ void finalize_bn_backward(const CaeBN& bn, const double* part, int rows, double count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < bn.C; c += CAE_NWARP) {
+        double S1 = warp_colsum(part, rows, bn.C * 2, c * 2 + 0);  // sum dz
+        double S2 = warp_colsum(part, rows, bn.C * 2, c * 2 + 1);  // sum dz * xhat
+        if (lane == 0) {
+            double g = bn.gamma ? (double)bn.gamma[c] : 1.0;
+            double invstd = (double)bn.invstd[c], mean = (double)bn.mean[c];
+            double A = g * invstd;
+            double B = -A * invstd * S2 / count;
+            double Cc = -A * S1 / count - B * mean;
+            bn.bwdA[c] = (float)A;
+            bn.bwdB[c] = (float)B;
+            bn.bwdC[c] = (float)Cc;
+            if (bn.dgamma) bn.dgamma[c] = (float)S2;
+            if (bn.dbeta) bn.dbeta[c] = (float)S1;
+            // the bias of a conv that feeds a training-mode BN has an identically zero gradient
+            // (sum_y dL/dy = 0); autograd returns rounding noise here.
+            if (bn.dbias) bn.dbias[c] = 0.f;
+        }
+    }
+}

@@ -1,0 +1,459 @@
+"""Step program for the ConvAEModel hot path (reference: conv_ae_model.py:185-239 train/test/score loops,
+encoder.py:60-64, decoder.py:73-78, torch.nn.MSELoss :303, torch.optim.Adam :310).
+
+The engine owns
+  * one flat fp32 arena for all trainable parameters (+ grads, Adam m and v of the same layout); the
+    nn.Parameters of the Encoder/Decoder containers are re-pointed at views of it so state_dict(),
+    save() and load() keep working unchanged;
+  * per-layer activation / gradient buffers, BatchNorm scratch, reduction workspaces;
+  * an explicit forward + backward kernel schedule (no autograd) that is captured once per batch
+    geometry into a CUDA graph and replayed; the batch to use is selected on the device through a
+    cursor, so an epoch is `n_batches` graph launches with no host<->device traffic in between.
+
+Kernel schedule for one optimiser step (L_e encoder convs, L_d transposed convs):
+  forward   conv_down x L_e (bias + BN statistics in the epilogue; BN+ReLU applied by the *consumer* on load)
+            gemm x 4       (fc stack; first one applies BN+ReLU+Flatten on load)
+            conv_up x L_d  (same; the last one fuses sigmoid + MSE loss + dL/dz)
+  backward  per transposed conv: wgrad, then conv_down as dgrad with ReLU-mask + BN-backward sums in the epilogue
+            gemm x 7 (fc), ew_epilogue (mask + BN sums), per conv: wgrad (+ conv_up as dgrad)
+  update    one fused Adam launch over the arena, one bookkeeping launch (step counter, batch cursor)
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .._lib import require_cuda
+
+
+class DataBinding:
+    """A pre-batched, device-resident data set (reference keeps every batch on the device,
+    conv_ae_model.py:315-325): X [n,C,H,W], optional Y, a device cursor and a per-batch loss array."""
+
+    def __init__(self, X, Y, batch_size):
+        self.X = X.contiguous()
+        self.Y = Y.contiguous() if Y is not None else None
+        self.n = int(X.shape[0])
+        self.batch_size = int(batch_size)
+        self.n_batches = (self.n + self.batch_size - 1) // self.batch_size
+        self.tail = self.n - (self.n_batches - 1) * self.batch_size
+        dev = X.device
+        self.cursor = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.losses = torch.zeros(self.n_batches, dtype=torch.float32, device=dev)
+        self.graphs = {}
+
+    def batch_sizes(self):
+        """[(N, count)] in replay order: full batches then the ragged tail"""
+        if self.tail == self.batch_size:
+            return [(self.batch_size, self.n_batches)]
+        out = []
+        if self.n_batches > 1:
+            out.append((self.batch_size, self.n_batches - 1))
+        out.append((self.tail, 1))
+        return out
+
+
+def _align(n, a=4):
+    return (n + a - 1) // a * a
+
+
+class ConvAEEngine:
+
+    def __init__(self, encoder, decoder, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, decoupled=False,
+                 device="cuda", use_graphs=True, grad_hook=None, grad_scale=1.0):
+        require_cuda()
+        self.device = torch.device(device)
+        self.encoder = encoder.to(self.device)
+        self.decoder = decoder.to(self.device)
+        self.lr, self.weight_decay, self.betas, self.eps, self.decoupled = lr, weight_decay, betas, eps, decoupled
+        self.use_graphs = use_graphs
+        self.grad_hook = grad_hook      # callable(flat_grads) between backward and Adam (data-parallel all-reduce)
+        self.grad_scale = grad_scale
+        self._keep = []                 # descriptors' tensors must outlive the graphs
+        self._build_arena()
+        self.enc_layers = self.encoder.conv_layers()
+        self.dec_layers = self.decoder.conv_layers()
+        self.enc_specs = self.encoder.layer_specs
+        self.dec_specs = self.decoder.layer_specs
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._bufs = {}
+        self._bn_scratch = {}
+        self._progs = {}
+        self._tickets = torch.zeros(4096, dtype=torch.int32, device=self.device)
+        self._next_ticket = 0
+        self._bn_table = None
+
+    # ------------------------------------------------------------------ parameters
+    def _build_arena(self):
+        params = list(self.encoder.parameters()) + list(self.decoder.parameters())
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += _align(p.numel())
+        dev = self.device
+        self.arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._gview = {}
+        with torch.no_grad():
+            for p, off in zip(params, offs):
+                n = p.numel()
+                self.arena[off:off + n].copy_(p.detach().reshape(-1).to(dev, torch.float32))
+                p.data = self.arena[off:off + n].view(p.shape)
+                g = self.grads[off:off + n].view(p.shape)
+                p.grad = g
+                self._gview[id(p)] = g
+        self.n_params = total
+
+    def g(self, p):
+        """gradient view (inside the flat grad arena) of parameter p"""
+        return self._gview[id(p)]
+
+    # ------------------------------------------------------------------ buffers
+    def _f32(self, *shape):
+        t = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _ticket(self):
+        i = self._next_ticket
+        self._next_ticket += 1
+        assert i < self._tickets.numel()
+        return self._tickets[i:i + 1]
+
+    def _partials(self, C):
+        t = torch.zeros(ops.partials_len(C), dtype=torch.float64, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _bn(self, key, bn_mod, conv_bias_grad=None):
+        """CaeBN block for a BatchNorm2d module (scratch allocated once per module)"""
+        if key not in self._bn_scratch:
+            Cn = bn_mod.num_features
+            self._bn_scratch[key] = self._f32(7, Cn)
+        s = self._bn_scratch[key]
+        return ops.make_bn(bn_mod.num_features, bn_mod.eps, bn_mod.momentum, bn_mod.weight, bn_mod.bias,
+                           bn_mod.running_mean, bn_mod.running_var, bn_mod.num_batches_tracked,
+                           scale=s[0], shift=s[1], mean=s[2], invstd=s[3],
+                           dgamma=self.g(bn_mod.weight), dbeta=self.g(bn_mod.bias), dbias=conv_bias_grad,
+                           bwdA=s[4], bwdB=s[5], bwdC=s[6]), s
+
+    def _act_buffers(self, B):
+        """activation / gradient buffers for batch capacity B"""
+        if B in self._bufs:
+            return self._bufs[B]
+        b = {}
+        b["y_e"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.enc_specs]
+        b["dz_e"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.enc_specs]
+        lin = self.encoder.encoder_lin
+        dlin = self.decoder.decoder_lin
+        b["h1"] = self._f32(B, lin[0].out_features)
+        b["z"] = self._f32(B, lin[2].out_features)
+        b["h3"] = self._f32(B, dlin[0].out_features)
+        c0, h0, w0 = self.dec_specs[0].get_input_dimensions()
+        b["u"] = self._f32(B, c0, h0, w0)
+        b["du"] = self._f32(B, c0, h0, w0)
+        b["dh3"] = self._f32(B, dlin[0].out_features)
+        b["dzl"] = self._f32(B, lin[2].out_features)
+        b["dh1"] = self._f32(B, lin[0].out_features)
+        ce, he, we = self.enc_specs[-1].get_output_dimensions()
+        b["da"] = self._f32(B, ce, he, we)
+        b["y_d"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.dec_specs]   # last: dL/dz or yhat
+        b["dz_d"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.dec_specs[:-1]]
+        self._bufs[B] = b
+        return b
+
+    # ------------------------------------------------------------------ schedules
+    def _forward_ops(self, b, N, data, train, final):
+        """final: 'loss_grad' (train), 'loss' (test epoch), 'yhat' (score: writes sigmoid output into y_d[-1])"""
+        sched = []
+        X = data.X
+        src = ops.make_src(X[:data.batch_size] if X.shape[0] >= data.batch_size else X, cursor=data.cursor,
+                           cursor_stride=data.batch_size * X[0].numel(), n=N)
+        # the view above must describe one batch worth of samples starting at X[0]; N limits the count
+        for i, ((conv, bn), sp) in enumerate(zip(self.enc_layers, self.enc_specs)):
+            y = b["y_e"][i]
+            blk, s = self._bn(("e", i), bn, self.g(conv.bias))
+            if train:
+                epi = ops.make_epilogue(ops.EPI_STATS, bias=conv.bias, partials=self._partials(conv.out_channels),
+                                        ticket=self._ticket(), bn=blk)
+            else:
+                epi = ops.make_epilogue(ops.EPI_PLAIN, bias=conv.bias)
+            g = ops.geom(sp.get_kernel_size(), sp.get_stride(), 0)
+            sched.append(lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_down(src, w, g, o, e))
+            src = ops.make_src(y, k0=s[0], k2=s[1], relu=True, n=N)
+        # fc stack
+        lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
+        ylast = b["y_e"][-1]
+        ce, he, we = self.enc_specs[-1].get_output_dimensions()
+        flat = ce * he * we
+        s_last = self._bn_scratch[("e", len(self.enc_layers) - 1)]
+        fc, lat = lin[0].out_features, lin[2].out_features
+        fc2 = dlin[0].out_features
+        out4 = dlin[2].out_features
+        sched.append(lambda: ops.gemm(N, fc, flat, ylast, flat, 1, lin[0].weight, 1, flat, b["h1"], fc, 1,
+                                      a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True,
+                                      bias=lin[0].bias, relu_out=True))
+        sched.append(lambda: ops.gemm(N, lat, fc, b["h1"], fc, 1, lin[2].weight, 1, fc, b["z"], lat, 1,
+                                      bias=lin[2].bias))
+        sched.append(lambda: ops.gemm(N, fc2, lat, b["z"], lat, 1, dlin[0].weight, 1, lat, b["h3"], fc2, 1,
+                                      bias=dlin[0].bias, relu_out=True))
+        sched.append(lambda: ops.gemm(N, out4, fc2, b["h3"], fc2, 1, dlin[2].weight, 1, fc2, b["u"], out4, 1,
+                                      bias=dlin[2].bias))
+        src = ops.make_src(b["u"], n=N)
+        nd = len(self.dec_layers)
+        for j, ((conv, bn), sp) in enumerate(zip(self.dec_layers, self.dec_specs)):
+            y = b["y_d"][j]
+            g = ops.geom(sp.get_kernel_size(), sp.get_stride(), 0)
+            if j < nd - 1:
+                blk, s = self._bn(("d", j), bn, self.g(conv.bias))
+                if train:
+                    epi = ops.make_epilogue(ops.EPI_STATS, bias=conv.bias,
+                                            partials=self._partials(conv.out_channels), ticket=self._ticket(), bn=blk)
+                else:
+                    epi = ops.make_epilogue(ops.EPI_PLAIN, bias=conv.bias)
+                sched.append(lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_up(src, w, g, o, e))
+                src = ops.make_src(y, k0=s[0], k2=s[1], relu=True, n=N)
+            else:
+                if final == "yhat":
+                    epi = ops.make_epilogue(ops.EPI_SIGMOID, bias=conv.bias)
+                else:
+                    Y = data.Y
+                    tgt = ops.make_src(Y[:data.batch_size] if Y.shape[0] >= data.batch_size else Y, cursor=data.cursor,
+                                       cursor_stride=data.batch_size * Y[0].numel(), n=N)
+                    epi = ops.make_epilogue(ops.EPI_SIGMOID_MSE, bias=conv.bias,
+                                            partials=self._partials(conv.out_channels), ticket=self._ticket(),
+                                            target=tgt, loss_out=data.losses,
+                                            dbias=self.g(conv.bias) if train else None,
+                                            write_mode=0 if final == "loss_grad" else 2)
+                sched.append(lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_up(src, w, g, o, e))
+        return sched
+
+    def _wgrad_op(self, small, big, g, grad):
+        part = torch.zeros(ops.wgrad_partials_len(small, big, g), dtype=torch.float32, device=self.device)
+        self._keep.append(part)
+        t = self._ticket()
+        return lambda: ops.conv_wgrad(small, big, g, grad, part, t)
+
+    def _backward_ops(self, b, N, data):
+        sched = []
+        nd = len(self.dec_layers)
+        # ---- decoder
+        for j in range(nd - 1, -1, -1):
+            conv, bn = self.dec_layers[j]
+            sp = self.dec_specs[j]
+            g = ops.geom(sp.get_kernel_size(), sp.get_stride(), 0)
+            if j == nd - 1:
+                dy = ops.make_src(b["y_d"][j], n=N)            # holds dL/dz of the fused sigmoid+MSE epilogue
+            else:
+                s = self._bn_scratch[("d", j)]
+                dy = ops.make_src(b["dz_d"][j], t1=b["y_d"][j], k0=s[4], k1=s[5], k2=s[6], n=N)
+            if j > 0:
+                sp_prev = self._bn_scratch[("d", j - 1)]
+                x_in = ops.make_src(b["y_d"][j - 1], k0=sp_prev[0], k2=sp_prev[1], relu=True, n=N)
+            else:
+                x_in = ops.make_src(b["u"], n=N)
+            sched.append(self._wgrad_op(x_in, dy, g, self.g(conv.weight)))
+            if j > 0:
+                pconv, pbn = self.dec_layers[j - 1]
+                blk, _ = self._bn(("d", j - 1), pbn, self.g(pconv.bias))
+                epi = ops.make_epilogue(ops.EPI_MASKSTATS, partials=self._partials(pconv.out_channels),
+                                        ticket=self._ticket(), bn=blk, act=b["y_d"][j - 1], n=N)
+                out = ops.view4(b["dz_d"][j - 1], N)
+            else:
+                epi = ops.make_epilogue(ops.EPI_PLAIN)
+                out = ops.view4(b["du"], N)
+            sched.append(lambda dy=dy, w=conv.weight, g=g, o=out, e=epi: ops.conv_down(dy, w, g, o, e))
+        # ---- fc stack
+        lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
+        ce, he, we = self.enc_specs[-1].get_output_dimensions()
+        flat = ce * he * we
+        fc, lat = lin[0].out_features, lin[2].out_features
+        fc2, out4 = dlin[0].out_features, dlin[2].out_features
+        G = self.g
+        le = len(self.enc_layers) - 1
+        s_last = self._bn_scratch[("e", le)]
+        ylast = b["y_e"][-1]
+        # Linear 4: u = h3 W4^T + b4
+        sched.append(lambda: ops.gemm(out4, fc2, N, b["du"], 1, out4, b["h3"], fc2, 1, G(dlin[2].weight), fc2, 1,
+                                      rowsum_A=G(dlin[2].bias)))
+        sched.append(lambda: ops.gemm(N, fc2, out4, b["du"], out4, 1, dlin[2].weight, fc2, 1, b["dh3"], fc2, 1,
+                                      mask=b["h3"]))
+        # Linear 3: h3 = relu(z W3^T + b3)
+        sched.append(lambda: ops.gemm(fc2, lat, N, b["dh3"], 1, fc2, b["z"], lat, 1, G(dlin[0].weight), lat, 1,
+                                      rowsum_A=G(dlin[0].bias)))
+        sched.append(lambda: ops.gemm(N, lat, fc2, b["dh3"], fc2, 1, dlin[0].weight, lat, 1, b["dzl"], lat, 1))
+        # Linear 2: z = h1 W2^T + b2
+        sched.append(lambda: ops.gemm(lat, fc, N, b["dzl"], 1, lat, b["h1"], fc, 1, G(lin[2].weight), fc, 1,
+                                      rowsum_A=G(lin[2].bias)))
+        sched.append(lambda: ops.gemm(N, fc, lat, b["dzl"], lat, 1, lin[2].weight, fc, 1, b["dh1"], fc, 1,
+                                      mask=b["h1"]))
+        # Linear 1: h1 = relu(a W1^T + b1), a = relu(bn(y_last)) flattened
+        sched.append(lambda: ops.gemm(fc, flat, N, b["dh1"], 1, fc, ylast, flat, 1, G(lin[0].weight), flat, 1,
+                                      b_k0=s_last[0], b_k2=s_last[1], b_hw=he * we, b_relu=True,
+                                      rowsum_A=G(lin[0].bias)))
+        sched.append(lambda: ops.gemm(N, flat, fc, b["dh1"], fc, 1, lin[0].weight, flat, 1, b["da"], flat, 1))
+        # ReLU mask + BN-backward sums of the last encoder layer
+        conv, bn = self.enc_layers[le]
+        blk, _ = self._bn(("e", le), bn, self.g(conv.bias))
+        epi = ops.make_epilogue(ops.EPI_MASKSTATS, partials=self._partials(conv.out_channels), ticket=self._ticket(),
+                                bn=blk, act=ylast, n=N)
+        sched.append(lambda s=ops.make_src(b["da"], n=N), o=ops.view4(b["dz_e"][le], N), e=epi: ops.ew_epilogue(s, o, e))
+        # ---- encoder
+        X = data.X
+        for i in range(le, -1, -1):
+            conv, bn = self.enc_layers[i]
+            sp = self.enc_specs[i]
+            g = ops.geom(sp.get_kernel_size(), sp.get_stride(), 0)
+            s = self._bn_scratch[("e", i)]
+            dy = ops.make_src(b["dz_e"][i], t1=b["y_e"][i], k0=s[4], k1=s[5], k2=s[6], n=N)
+            if i > 0:
+                sp_prev = self._bn_scratch[("e", i - 1)]
+                x_in = ops.make_src(b["y_e"][i - 1], k0=sp_prev[0], k2=sp_prev[1], relu=True, n=N)
+            else:
+                x_in = ops.make_src(X[:data.batch_size] if X.shape[0] >= data.batch_size else X, cursor=data.cursor,
+                                    cursor_stride=data.batch_size * X[0].numel(), n=N)
+            sched.append(self._wgrad_op(dy, x_in, g, self.g(conv.weight)))
+            if i > 0:
+                pconv, pbn = self.enc_layers[i - 1]
+                blk, _ = self._bn(("e", i - 1), pbn, self.g(pconv.bias))
+                epi = ops.make_epilogue(ops.EPI_MASKSTATS, partials=self._partials(pconv.out_channels),
+                                        ticket=self._ticket(), bn=blk, act=b["y_e"][i - 1], n=N)
+                sched.append(lambda dy=dy, w=conv.weight, g=g, o=ops.view4(b["dz_e"][i - 1], N), e=epi:
+                             ops.conv_up(dy, w, g, o, e))
+        return sched
+
+    def _update_ops(self, data):
+        def upd():
+            if self.grad_hook is not None:
+                self.grad_hook(self.grads)
+            ops.adam(self.arena, self.grads, self.adam_m, self.adam_v, self.n_params, self.lr, self.betas[0],
+                     self.betas[1], self.eps, self.weight_decay, self.decoupled, self.grad_scale, self.step_count)
+            ops.step_advance(self.step_count, data.cursor, data.n_batches)
+        return [upd]
+
+    def _eval_prepare_op(self):
+        if self._bn_table is None:
+            blocks = []
+            for i, (conv, bn) in enumerate(self.enc_layers):
+                blocks.append(self._bn(("e", i), bn)[0])
+            for j, (conv, bn) in enumerate(self.dec_layers):
+                if bn is not None:
+                    blocks.append(self._bn(("d", j), bn)[0])
+            self._bn_count = len(blocks)
+            self._bn_table = ops.bn_table(blocks, self.device)
+        return lambda: ops.bn_eval_prepare(self._bn_table, self._bn_count)
+
+    # ------------------------------------------------------------------ execution
+    def _program(self, kind, data, N):
+        """build (and cache on the binding) the op list / CUDA graph for one batch geometry"""
+        key = (kind, N)
+        if key in data.graphs:
+            return data.graphs[key]
+        b = self._act_buffers(data.batch_size)
+        if kind == "train":
+            sched = self._forward_ops(b, N, data, True, "loss_grad") + self._backward_ops(b, N, data) + \
+                self._update_ops(data)
+        elif kind == "test":
+            sched = self._forward_ops(b, N, data, False, "loss") + \
+                [lambda: ops.step_advance(None, data.cursor, data.n_batches)]
+        elif kind == "score":
+            sched = self._forward_ops(b, N, data, False, "yhat") + \
+                [lambda: ops.step_advance(None, data.cursor, data.n_batches)]
+        else:
+            raise ValueError(kind)
+        state = [data.cursor, data.losses]
+        if kind == "train":
+            state += [self.arena, self.adam_m, self.adam_v, self.grads, self.step_count]
+            for mod in list(self.encoder.modules()) + list(self.decoder.modules()):
+                if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                    state += [mod.running_mean, mod.running_var, mod.num_batches_tracked]
+        prog = _Program(sched, self.use_graphs, state)
+        data.graphs[key] = prog
+        return prog
+
+    def bind(self, X, Y, batch_size):
+        X = X.to(self.device, torch.float32)
+        Y = Y.to(self.device, torch.float32) if Y is not None else None
+        return DataBinding(X, Y, batch_size)
+
+    def train_epoch(self, data):
+        """one pass over all batches; returns the per-batch losses (device tensor, no sync)"""
+        data.cursor.zero_()
+        for N, count in data.batch_sizes():
+            prog = self._program("train", data, N)
+            for _ in range(count):
+                prog.run()
+        return data.losses
+
+    def train_steps(self, data, steps):
+        """run `steps` optimiser steps cycling through the batches (bench helper; full batches only)"""
+        assert data.tail == data.batch_size, "train_steps needs n % batch_size == 0"
+        prog = self._program("train", data, data.batch_size)
+        for _ in range(steps):
+            prog.run()
+
+    def test_epoch(self, data):
+        self._eval_prepare_op()()
+        data.cursor.zero_()
+        for N, count in data.batch_sizes():
+            prog = self._program("test", data, N)
+            for _ in range(count):
+                prog.run()
+        return data.losses
+
+    def score_batches(self, data, sink):
+        """eval-mode forward of every batch; sink(batch_index, yhat[N,C,H,W] device view) consumes each output"""
+        self._eval_prepare_op()()
+        data.cursor.zero_()
+        b = self._act_buffers(data.batch_size)
+        idx = 0
+        for N, count in data.batch_sizes():
+            prog = self._program("score", data, N)
+            for _ in range(count):
+                prog.run()
+                sink(idx, b["y_d"][-1][:N])
+                idx += 1
+
+    def encode_decode(self, data):
+        """like score_batches but also exposes the latent z per batch: yields (yhat, z)"""
+        raise NotImplementedError
+
+
+class _Program:
+    """An op list; captured into a CUDA graph on first use when graphs are enabled."""
+
+    def __init__(self, sched, use_graph, state=()):
+        self.sched = sched
+        self.use_graph = use_graph
+        self.state = list(state)
+        self.graph = None
+
+    def run_eager(self):
+        for op in self.sched:
+            op()
+
+    def run(self):
+        if not self.use_graph:
+            self.run_eager()
+            return
+        if self.graph is None:
+            # one eager warm-up (loads every kernel outside of capture and surfaces launch errors with
+            # a readable message); the state it touches is snapshotted and restored so it is invisible.
+            saved = [t.clone() for t in self.state]
+            self.run_eager()
+            torch.cuda.current_stream().synchronize()
+            with torch.no_grad():
+                for t, c in zip(self.state, saved):
+                    t.copy_(c)
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(g, stream=s):
+                    self.run_eager()
+            torch.cuda.current_stream().wait_stream(s)
+            self.graph = g
+        self.graph.replay()

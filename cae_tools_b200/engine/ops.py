@@ -1,0 +1,150 @@
+"""Thin Python wrappers over the C ABI: build the POD descriptors from torch tensors and enqueue
+kernels on torch's current CUDA stream (so everything is capturable in a CUDA graph).
+
+Nothing here computes; if the library is missing, `lib()` raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeGemm, CaeSrc, CaeView, EPI_MASKSTATS, EPI_PLAIN,
+                    EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
+
+__all__ = ["view4", "make_src", "make_bn", "make_epilogue", "geom", "conv_up", "conv_down", "conv_wgrad",
+           "wgrad_partials_len", "ew_epilogue", "gemm", "bn_eval_prepare", "mse", "adam", "step_advance",
+           "partials_len", "EPI_PLAIN", "EPI_STATS", "EPI_MASKSTATS", "EPI_SIGMOID", "EPI_SIGMOID_MSE"]
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "device tensor expected"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def view4(t: torch.Tensor, n=None) -> CaeView:
+    """CaeView of a 4-D fp32 CUDA tensor (innermost stride must be 1); `n` restricts the batch."""
+    assert t.dim() == 4 and t.dtype == torch.float32 and t.is_cuda, (t.shape, t.dtype, t.device)
+    sn, sc, sh, sw = t.stride()
+    N, Cc, H, W = t.shape
+    assert sw == 1 or W == 1
+    if H == 1:
+        sh = max(W, 1)
+    return CaeView(t.data_ptr(), int(N if n is None else n), int(Cc), int(H), int(W), int(sh), int(sc), int(sn))
+
+
+def make_src(t0, t1=None, k0=None, k1=None, k2=None, relu=False, cursor=None, cursor_stride=0, n=None) -> CaeSrc:
+    if t1 is not None:
+        assert t1.shape == t0.shape and t1.stride() == t0.stride(), "t1 must share t0's geometry"
+    return CaeSrc(view4(t0, n), _ptr(t1), _ptr(k0), _ptr(k1), _ptr(k2), int(bool(relu)), _ptr(cursor),
+                  int(cursor_stride))
+
+
+def make_bn(Cn, eps=1e-5, momentum=0.1, gamma=None, beta=None, running_mean=None, running_var=None, nbt=None,
+            scale=None, shift=None, mean=None, invstd=None, dgamma=None, dbeta=None, dbias=None, bwdA=None,
+            bwdB=None, bwdC=None) -> CaeBN:
+    return CaeBN(int(Cn), float(eps), float(momentum), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                 _ptr(nbt), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(dgamma), _ptr(dbeta),
+                 _ptr(dbias), _ptr(bwdA), _ptr(bwdB), _ptr(bwdC))
+
+
+_NULL_VIEW = CaeView(None, 0, 0, 0, 0, 0, 0, 0)
+_NULL_BN = CaeBN()
+
+
+def make_epilogue(mode, bias=None, partials=None, ticket=None, bn=None, act=None, target=None, loss_out=None,
+                  dbias=None, write_mode=0, n=None) -> CaeEpilogue:
+    e = CaeEpilogue()
+    e.mode = int(mode)
+    e.bias = _ptr(bias)
+    e.partials = _ptr(partials)
+    e.ticket = _ptr(ticket)
+    if bn is not None:
+        e.bn = bn
+    if act is not None:
+        e.act = view4(act, n)
+    if target is not None:
+        e.target = target
+    e.loss_out = _ptr(loss_out)
+    e.dbias = _ptr(dbias)
+    e.write_mode = int(write_mode)
+    return e
+
+
+def geom(kernel, stride, pad=0) -> CaeConvGeom:
+    if isinstance(kernel, (tuple, list)):
+        kh, kw = int(kernel[0]), int(kernel[1])
+    else:
+        kh = kw = int(kernel)
+    return CaeConvGeom(kh, kw, int(stride), int(pad))
+
+
+def partials_len(Cn: int) -> int:
+    return int(lib().cae_partials_len(int(Cn)))
+
+
+def conv_up(src: CaeSrc, weight, g: CaeConvGeom, out: CaeView, epi: CaeEpilogue):
+    check(lib().cae_conv_up(C.byref(src), _ptr(weight), C.byref(g), C.byref(out), C.byref(epi), _stream()),
+          "cae_conv_up")
+
+
+def conv_down(src: CaeSrc, weight, g: CaeConvGeom, out: CaeView, epi: CaeEpilogue):
+    check(lib().cae_conv_down(C.byref(src), _ptr(weight), C.byref(g), C.byref(out), C.byref(epi), _stream()),
+          "cae_conv_down")
+
+
+def wgrad_partials_len(small: CaeSrc, big: CaeSrc, g: CaeConvGeom) -> int:
+    n = int(lib().cae_wgrad_partials_len(C.byref(small), C.byref(big), C.byref(g)))
+    if n < 0:
+        check(-1, "cae_wgrad_partials_len")
+    return n
+
+
+def conv_wgrad(small: CaeSrc, big: CaeSrc, g: CaeConvGeom, grad, partials, ticket):
+    check(lib().cae_conv_wgrad(C.byref(small), C.byref(big), C.byref(g), _ptr(grad), _ptr(partials), _ptr(ticket),
+                               _stream()), "cae_conv_wgrad")
+
+
+def ew_epilogue(src: CaeSrc, out: CaeView, epi: CaeEpilogue):
+    check(lib().cae_ew_epilogue(C.byref(src), C.byref(out), C.byref(epi), _stream()), "cae_ew_epilogue")
+
+
+def gemm(M, N, K, A, sAm, sAk, B, sBk, sBn, Cout, sCm, sCn, a_k0=None, a_k2=None, a_hw=1, a_relu=False, b_k0=None,
+         b_k2=None, b_hw=1, b_relu=False, bias=None, relu_out=False, mask=None, rowsum_A=None):
+    g = CaeGemm(int(M), int(N), int(K), _ptr(A), int(sAm), int(sAk), _ptr(B), int(sBk), int(sBn), _ptr(Cout),
+                int(sCm), int(sCn), _ptr(a_k0), _ptr(a_k2), int(a_hw), int(bool(a_relu)), _ptr(b_k0), _ptr(b_k2),
+                int(b_hw), int(bool(b_relu)), _ptr(bias), int(bool(relu_out)), _ptr(mask), _ptr(rowsum_A))
+    check(lib().cae_gemm(C.byref(g), _stream()), "cae_gemm")
+
+
+def bn_eval_prepare(device_table: torch.Tensor, count: int):
+    check(lib().cae_bn_eval_prepare(_ptr(device_table), int(count), _stream()), "cae_bn_eval_prepare")
+
+
+def bn_table(blocks, device) -> torch.Tensor:
+    """Pack CaeBN PODs into a device byte tensor for cae_bn_eval_prepare."""
+    raw = b"".join(bytes(b) for b in blocks)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+    return t
+
+
+def mse(a, b, n, partials, ticket, loss_out, cursor=None):
+    check(lib().cae_mse(_ptr(a), _ptr(b), int(n), _ptr(partials), _ptr(ticket), _ptr(loss_out), _ptr(cursor),
+                        _stream()), "cae_mse")
+
+
+def adam(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, grad_scale, step_count):
+    check(lib().cae_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), int(n), float(lr), float(beta1), float(beta2),
+                         float(eps), float(weight_decay), int(bool(decoupled)), float(grad_scale), _ptr(step_count),
+                         _stream()), "cae_adam")
+
+
+def step_advance(step_count, cursor, n_batches):
+    check(lib().cae_step_advance(_ptr(step_count), _ptr(cursor), int(n_batches), _stream()), "cae_step_advance")

@@ -1,0 +1,124 @@
+"""Behaviour shared by the model classes: ids, input/output specs on disk, ``apply`` and ``evaluate``.
+
+API and on-disk files follow the reference ``BaseModel`` (reference: src/cae_tools/models/base_model.py:28-203).
+``apply`` keeps the reference contract (normalise -> batches on device -> ``score`` -> denormalise ->
+new variable on the data set) but assembles the batches in one vectorised pass and lets the engine
+stream predictions back through pinned memory.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import uuid
+
+import numpy as np
+import torch
+
+from .ds_dataset import DSDataset
+from .model_metric import ModelMetric
+
+try:  # pragma: no cover - depends on the image
+    import xarray as _xr
+except ImportError:  # the build image has no xarray
+    from ..utils import xr_lite as _xr
+
+
+class BaseModel:
+
+    def __init__(self):
+        self.input_spec = None
+        self.output_spec = None
+        self.model_id = str(uuid.uuid4())
+
+    # ---- specs / ids
+    def set_input_spec(self, input_spec):
+        self.input_spec = input_spec
+
+    def get_input_spec(self):
+        return self.input_spec
+
+    def set_output_spec(self, output_spec):
+        self.output_spec = output_spec
+
+    def get_output_spec(self):
+        return self.output_spec
+
+    def get_input_variable_names(self):
+        return None if self.input_spec is None else [item["name"] for item in self.input_spec]
+
+    def get_output_variable_name(self):
+        return None if self.output_spec is None else self.output_spec["name"]
+
+    def set_model_id(self, model_id):
+        self.model_id = model_id
+
+    def get_model_id(self):
+        return self.model_id
+
+    def torch_load(self, from_path):
+        return torch.load(from_path, map_location=None if torch.cuda.is_available() else torch.device("cpu"))
+
+    # ---- inference over a data set
+    def predict_array(self, inputs: np.ndarray) -> np.ndarray:
+        """normalised fp32 inputs [n,C,y,x] -> model outputs [n,C',y',x'] (sub-classes implement)"""
+        raise NotImplementedError
+
+    def apply(self, score_ds, input_variables, prediction_variable="model_output",
+              channel_dimension="model_output_channel", y_dimension="model_output_y", x_dimension="model_output_x",
+              mask_variable_name=None):
+        """Add the model's (de-normalised) estimate to `score_ds` as `prediction_variable`."""
+        n_dimension = score_ds[input_variables[0]].dims[0]
+        ds = DSDataset(score_ds, input_variables, input_variables[0], normalise_in=self.normalise_input,
+                       mask_variable_name=mask_variable_name)
+        ds.set_normalisation_parameters(self.normalisation_parameters)
+        scores = self.predict_array(ds.input_array())
+        out = ds.denormalise_output(scores.astype(np.float64))
+        score_ds[prediction_variable] = _xr.DataArray(out, dims=(n_dimension, channel_dimension, y_dimension,
+                                                                  x_dimension))
+
+    def evaluate(self, dataset, device=None):
+        """mse / rmse / mae / mean Pearson of de-normalised predictions against the data set's output"""
+        dataset.set_normalise_output(False)
+        scores = dataset.denormalise_output(self.predict_array(dataset.input_array()).astype(np.float64), force=True)
+        actual = np.asarray(dataset.output_da.values)
+        mask = dataset.mask_array()
+        mm = ModelMetric()
+        for i in range(actual.shape[0]):
+            mm.accumulate(actual[i], scores[i], mask[i])
+        return mm.get_metrics()
+
+    def dump_metrics(self, title, metrics):
+        print("\n" + title)
+        for key in metrics:
+            print(f"\t{key:30s}:{metrics[key]}")
+
+    def score(self, batches, save_arr):
+        raise NotImplementedError
+
+    # ---- persistence of the input/output specs
+    def save(self, to_folder):
+        for name, spec in (("input_spec.json", self.input_spec), ("output_spec.json", self.output_spec)):
+            if spec is not None:
+                with open(os.path.join(to_folder, name), "w") as f:
+                    f.write(json.dumps(spec))
+
+    def load(self, from_folder):
+        path = os.path.join(from_folder, "input_spec.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                self.input_spec = json.loads(f.read())
+        path = os.path.join(from_folder, "output_spec.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                self.output_spec = json.loads(f.read())
+
+    def train(self, input_variables, output_variable, training_ds, testing_ds, model_path="", training_paths="",
+              testing_paths="", mask_variable_name=None):
+        raise NotImplementedError
+
+    def summary(self):
+        raise NotImplementedError
+
+    def get_parameters(self):
+        raise NotImplementedError

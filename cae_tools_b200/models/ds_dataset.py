@@ -1,0 +1,140 @@
+"""Data adaptor: named 4-D arrays (N,C,Y,X) -> normalised fp32 batches.
+
+Semantics follow the reference ``DSDataset`` (reference: src/cae_tools/models/ds_dataset.py:20-159):
+global min/max per input variable and for the output, NaNs rejected, inputs concatenated along the
+channel axis, items are ``(input, output, mask, label)``.  In addition to the per-item protocol this
+class assembles whole (optionally permuted) arrays in one vectorised pass - that is what feeds the
+device-resident batches of the engines (the reference collates item by item).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class DSDataset(torch.utils.data.Dataset):
+
+    def __init__(self, ds, input_variable_names, output_variable_name=None, normalise_in=True, normalise_out=True,
+                 mask_variable_name=None):
+        self.ds = ds
+        self.input_variable_names = input_variable_names
+        self.output_variable_name = output_variable_name
+        self.normalise_in = normalise_in
+        self.normalise_out = normalise_out
+        self.input_spec = []
+        self.output_spec = None
+        self.input_das = [ds[name] for name in input_variable_names]
+        first = self.input_das[0]
+        self.n = first.shape[0]
+        self.input_chan = sum(da.shape[1] for da in self.input_das)
+        self.input_y, self.input_x = first.shape[2], first.shape[3]
+        self.mask_da = ds[mask_variable_name] if mask_variable_name is not None else None
+
+        out_values = np.asarray(ds[output_variable_name].values)
+        bad = int(np.isnan(out_values).sum())
+        if bad > 0:
+            raise ValueError(f"output variable contains {bad} NaN values")
+
+        self.min_inputs, self.max_inputs = {}, {}
+        for name, da in zip(input_variable_names, self.input_das):
+            values = np.asarray(da.values)
+            self.min_inputs[name] = float(np.nanmin(values))
+            self.max_inputs[name] = float(np.nanmax(values))
+            bad = int(np.isnan(values).sum())
+            if bad > 0:
+                raise ValueError(f"input variable {name} contains {bad} NaN values")
+            self.input_spec.append({"name": name, "shape": list(da.shape[1:])})
+
+        if output_variable_name:
+            self.output_da = ds[output_variable_name]
+            self.output_chan, self.output_y, self.output_x = self.output_da.shape[1:4]
+            self.min_output = float(np.nanmin(out_values))
+            self.max_output = float(np.nanmax(out_values))
+            self.output_spec = {"name": output_variable_name, "shape": list(self.output_da.shape[1:])}
+        else:
+            self.output_da = None
+            self.output_chan = self.output_y = self.output_x = None
+            self.min_output = self.max_output = None
+
+    # ---- configuration
+    def set_normalise_output(self, normalise_out):
+        self.normalise_out = normalise_out
+
+    def get_normalisation_parameters(self):
+        return [self.min_inputs, self.max_inputs, self.min_output, self.max_output]
+
+    def set_normalisation_parameters(self, parameters):
+        (self.min_inputs, self.max_inputs, self.min_output, self.max_output) = tuple(parameters)
+
+    def get_input_shape(self):
+        return (self.input_chan, self.input_y, self.input_x)
+
+    def get_input_spec(self):
+        return self.input_spec
+
+    def get_output_shape(self):
+        return (self.output_chan, self.output_y, self.output_x)
+
+    def get_output_spec(self):
+        return self.output_spec
+
+    # ---- normalisation (min-max to [0,1])
+    def normalise_input(self, arr, input_name):
+        if not self.normalise_in:
+            return arr
+        lo, hi = self.min_inputs[input_name], self.max_inputs[input_name]
+        if hi - lo == 0:
+            return 0.0
+        return (arr - lo) / (hi - lo)
+
+    def normalise_output(self, arr):
+        if not self.normalise_out:
+            return arr
+        return (arr - self.min_output) / (self.max_output - self.min_output)
+
+    def denormalise_output(self, arr, force=False):
+        if force or self.normalise_out:
+            return self.min_output + (arr * (self.max_output - self.min_output))
+        return arr
+
+    # ---- whole-array assembly (vectorised equivalent of iterating __getitem__ + default collate)
+    def input_array(self, order=None):
+        out = np.zeros((self.n if order is None else len(order), self.input_chan, self.input_y, self.input_x),
+                       dtype=np.float32)
+        c = 0
+        for name, da in zip(self.input_variable_names, self.input_das):
+            vals = np.asarray(da.data)
+            if order is not None:
+                vals = vals[order]
+            nchan = da.shape[1]
+            out[:, c:c + nchan] = self.normalise_input(vals, name)
+            c += nchan
+        return out
+
+    def output_array(self, order=None):
+        vals = np.asarray(self.output_da.values)
+        if order is not None:
+            vals = vals[order]
+        return np.asarray(self.normalise_output(vals), dtype=np.float32)
+
+    def mask_array(self, order=None, like_output=True):
+        if self.mask_da is not None and self.mask_da.size > 0:
+            vals = np.asarray(self.mask_da.values)
+            if order is not None:
+                vals = vals[order]
+            return vals.astype(np.float32)
+        n = self.n if order is None else len(order)
+        if like_output and self.output_da is not None:
+            return np.ones((n, self.output_chan, self.output_y, self.output_x), dtype=np.float32)
+        return np.ones((n, self.input_chan, self.input_y, self.input_x), dtype=np.float32)
+
+    # ---- per-item protocol (kept for API compatibility)
+    def __getitem__(self, index):
+        in_arr = self.input_array(order=[index])[0]
+        out_arr = self.output_array(order=[index])[0] if self.output_da is not None else None
+        mask = self.mask_array(order=[index], like_output=False)[0]
+        return (in_arr, out_arr, mask, f"image{index}")
+
+    def __len__(self):
+        return self.n

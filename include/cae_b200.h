@@ -1,0 +1,182 @@
+/*
+ * cae_b200.h - C ABI of libcae_b200.so: the sm_100a kernels behind the cae_tools hot path.
+ *
+ * The reference (surftemp/cae_tools) has no FFI of its own: its hot path is a chain of
+ * PyTorch ATen calls made from nn.Module.forward / autograd / torch.optim.  Each entry
+ * point below names the reference call site (path:line under the reference tree) whose
+ * arithmetic it replaces.  Plain pointers, ints and PODs only - loadable with ctypes/cffi.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CAE_E* code for bad arguments or a
+ *     positive cudaError_t; cae_last_error() returns a thread-local message.
+ *   - all pointers are DEVICE pointers unless stated; the library never allocates
+ *     persistent device memory - callers (PyTorch's allocator) own every buffer.
+ *   - kernels are enqueued on the stream given (a cudaStream_t passed as void*); no call
+ *     synchronises, so everything is CUDA-graph capturable.
+ *   - tensors are fp32 NCHW with explicit strides (CaeView) so that internal buffers may
+ *     use padded rows and channel-offset views (skip concatenation writes in place).
+ */
+#ifndef CAE_B200_H
+#define CAE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAE_OK            0
+#define CAE_EINVAL       -1   /* bad argument */
+#define CAE_EUNSUPPORTED -2   /* geometry outside what the kernels implement */
+
+/* 4-D fp32 view: element (n,c,y,x) lives at p[n*sN + c*sC + y*ld + x] */
+typedef struct CaeView {
+    float*    p;
+    int       N, C, H, W;
+    int       ld;
+    long long sC, sN;
+} CaeView;
+
+/* Operand read through an on-load transform:
+ *     v = k0[c]*t0 + k1[c]*t1 + k2[c] ;  if (relu) v = max(v,0)
+ * NULL k0/k1/k2 mean 1/0/0; t1 (same geometry as t0) may be NULL.  Used to apply
+ * BatchNorm+ReLU of the producing layer while loading (forward) and to form
+ * dL/dy = A*dz + B*y + C of a BatchNorm backward while loading (backward), so neither
+ * is ever a standalone pass over HBM.
+ * cursor (device int*, may be NULL) selects the current batch of a pre-batched
+ * device-resident data set: the base address is advanced by cursor[0]*cursor_stride
+ * elements (reference keeps all batches on the device: conv_ae_model.py:315-325). */
+typedef struct CaeSrc {
+    CaeView       t0;
+    const float*  t1;
+    const float*  k0;
+    const float*  k1;
+    const float*  k2;
+    int           relu;
+    const int*    cursor;
+    long long     cursor_stride;
+} CaeSrc;
+
+typedef struct CaeConvGeom {
+    int kh, kw, stride, pad;
+} CaeConvGeom;
+
+/* Per-layer BatchNorm state; every pointer addresses C floats unless noted.
+ * (reference: nn.BatchNorm2d in encoder.py:45, decoder.py:47; eps 1e-5, momentum 0.1) */
+typedef struct CaeBN {
+    int          C;
+    float        eps, momentum;
+    const float* gamma;
+    const float* beta;
+    float*       running_mean;
+    float*       running_var;
+    long long*   num_batches_tracked;   /* 1 x int64 */
+    float*       scale;     /* y_hat = scale*y + shift   (written by fwd finalize / eval prepare) */
+    float*       shift;
+    float*       mean;      /* batch mean / 1/sqrt(var+eps) of the last training forward */
+    float*       invstd;
+    float*       dgamma;    /* gradients, written by bwd finalize (may point into the flat grad arena) */
+    float*       dbeta;
+    float*       dbias;     /* grad of the bias of the conv feeding this BN (may be NULL) */
+    float*       bwdA;      /* dL/dy = A*dz + B*y + C  (written by bwd finalize) */
+    float*       bwdB;
+    float*       bwdC;
+} CaeBN;
+
+/* Epilogue of the conv kernels (what happens to each accumulated output element) */
+#define CAE_EPI_PLAIN      0  /* out = acc + bias                                                  */
+#define CAE_EPI_STATS      1  /* out = acc + bias ; per-channel sum/sumsq -> BatchNorm (training)   */
+#define CAE_EPI_MASKSTATS  2  /* out = acc * [relu mask of `act`] ; sums for BatchNorm backward     */
+#define CAE_EPI_SIGMOID    3  /* out = sigmoid(acc + bias)                                          */
+#define CAE_EPI_SIGMOID_MSE 4 /* yhat = sigmoid(acc+bias); loss += (yhat-t)^2 ; out = dL/d(acc)     */
+
+typedef struct CaeEpilogue {
+    int            mode;
+    const float*   bias;          /* per output channel, may be NULL */
+    /* STATS / MASKSTATS / SIGMOID_MSE: deterministic two-stage reduction */
+    double*        partials;      /* workspace >= grid_x * C * 2 doubles (see cae_partials_len) */
+    unsigned int*  ticket;        /* 1 x u32, zero before first use; self-resetting */
+    CaeBN          bn;            /* STATS: BN that follows this conv. MASKSTATS: BN whose backward is reduced */
+    CaeView        act;           /* MASKSTATS: pre-BN output y of the layer whose ReLU/BN is differentiated
+                                     (same geometry as the kernel output). act.p NULL = no mask, plain write */
+    /* SIGMOID_MSE */
+    CaeSrc         target;        /* same geometry as the kernel output */
+    float*         loss_out;      /* loss_out[cursor ? *cursor : 0] = mean squared error of this batch */
+    float*         dbias;         /* gradient of `bias` (C floats) */
+    int            write_mode;    /* 0: write dL/d(acc) ; 1: write yhat ; 2: write nothing (loss only) */
+} CaeEpilogue;
+
+const char* cae_last_error(void);
+int  cae_version(void);
+/* number of doubles the `partials` workspace must hold for a kernel whose output has C channels */
+long long cae_partials_len(int C);
+
+/* ---- convolution family -------------------------------------------------------------
+ * cae_conv_down: strided convolution, weights [Cout][Cin][kh][kw]
+ *     out[n,co,oy,ox] = sum_{ci,ky,kx} in(n,ci,oy*s+ky-p,ox*s+kx-p) * W[co,ci,ky,kx]
+ *   forward of nn.Conv2d (reference encoder.py:43-44, unet.py:81-82) and, with the same weight
+ *   tensor, the input-gradient of nn.ConvTranspose2d (autograd of decoder.py:44-45).
+ * cae_conv_up: transposed convolution (gather form), weights [Cin][Cout][kh][kw]
+ *     out[n,co,oy,ox] = sum_{ci} sum_{ky,kx : (oy+p-ky)%s==0 ...} in(n,ci,(oy+p-ky)/s,(ox+p-kx)/s) * W[ci,co,ky,kx]
+ *   forward of nn.ConvTranspose2d (decoder.py:44-45, unet.py:138-140; followed by torch.sigmoid
+ *   decoder.py:77 and nn.MSELoss conv_ae_model.py:193 through the epilogue) and the
+ *   input-gradient of nn.Conv2d.
+ * cae_conv_wgrad: weight gradient of either, G[cs][cb][ky][kx] =
+ *     sum_{n,i,j} small(n,cs,i,j) * big(n,cb,i*s+ky-p,j*s+kx-p)
+ *   (convT: small = layer input, big = dL/dy; conv: small = dL/dy, big = layer input).
+ *   `partials` needs cae_wgrad_partials_len() floats. */
+int cae_conv_down(const CaeSrc* in, const float* weight, const CaeConvGeom* g, const CaeView* out,
+                  const CaeEpilogue* epi, void* stream);
+int cae_conv_up(const CaeSrc* in, const float* weight, const CaeConvGeom* g, const CaeView* out,
+                const CaeEpilogue* epi, void* stream);
+int cae_conv_wgrad(const CaeSrc* small_op, const CaeSrc* big_op, const CaeConvGeom* g, float* grad,
+                   float* partials, unsigned int* ticket, void* stream);
+long long cae_wgrad_partials_len(const CaeSrc* small_op, const CaeSrc* big_op, const CaeConvGeom* g);
+
+/* Elementwise member of the family: out = epilogue(in) - used where a gradient arrives from a
+ * non-conv producer (the fc stack) and still needs the ReLU mask + BatchNorm-backward sums. */
+int cae_ew_epilogue(const CaeSrc* in, const CaeView* out, const CaeEpilogue* epi, void* stream);
+
+/* ---- fully connected ------------------------------------------------------------------
+ * C[m,n] = epi( sum_k A(m,k) * B(k,n) ), A(m,k) = Ap[m*sAm + k*sAk], B(k,n) = Bp[k*sBk + n*sBn]
+ * replaces aten::addmm / mm of nn.Linear forward and backward (encoder.py:54-58, decoder.py:31-35).
+ *   a_k0/a_k2 (may be NULL): A is read as relu?(a_k0[k/a_hw]*A + a_k2[k/a_hw])  (BatchNorm+ReLU+Flatten on load)
+ *   b_k0/b_k2: same for B with channel = k... see cae_gemm fields.
+ *   bias (per n, may be NULL), relu_out, mask (same layout as C: C *= mask>0), bias_grad (per m: sum_k A(m,k))
+ */
+typedef struct CaeGemm {
+    int M, N, K;
+    const float* A; long long sAm, sAk;
+    const float* B; long long sBk, sBn;
+    float*       C; long long sCm, sCn;
+    /* on-load per-channel affine (+relu) for A indexed by k, or for B indexed by n */
+    const float* a_k0; const float* a_k2; int a_hw; int a_relu;   /* channel = k / a_hw */
+    const float* b_k0; const float* b_k2; int b_hw; int b_relu;   /* channel = n / b_hw */
+    const float* bias;        /* + bias[n] */
+    int          relu_out;    /* C = max(C,0) */
+    const float* mask;        /* C *= (mask[m*sCm+n*sCn] > 0) */
+    float*       rowsum_A;    /* if non-NULL: rowsum_A[m] = sum_k A(m,k)  (bias gradient when A = dy^T) */
+} CaeGemm;
+int cae_gemm(const CaeGemm* g, void* stream);
+
+/* ---- batch norm helpers ------------------------------------------------------------------ */
+/* eval mode: scale/shift from running statistics for `count` layers (table lives on the DEVICE) */
+int cae_bn_eval_prepare(const CaeBN* device_table, int count, void* stream);
+
+/* ---- loss (eval: no sigmoid fusion needed when yhat already exists) ---------------------- */
+/* loss_out[slot] = mean((a-b)^2) over n elements; deterministic two-stage reduction */
+int cae_mse(const float* a, const float* b, long long n, double* partials, unsigned int* ticket,
+            float* loss_out, const int* cursor, void* stream);
+
+/* ---- optimiser -----------------------------------------------------------------------------
+ * fused multi-tensor Adam/AdamW over one flat arena (reference: torch.optim.Adam
+ * conv_ae_model.py:310 (coupled L2) and torch.optim.AdamW unet.py:457 (decoupled)).
+ * step_count: device int holding the number of steps already taken (t = *step_count + 1).
+ * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
+int cae_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+             float eps, float weight_decay, int decoupled, float grad_scale, const int* step_count, void* stream);
+/* end-of-step bookkeeping: step_count[0] += 1 ; if cursor: cursor[0] = (cursor[0]+1) % n_batches */
+int cae_step_advance(int* step_count, int* cursor, int n_batches, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAE_B200_H */

@@ -1,0 +1,174 @@
+"""TEST INFRASTRUCTURE - writes tests/golden/* by running the UNMODIFIED reference in the build container.
+
+    python oracle/gen_golden.py            (needs /root/reference; not runnable on the GPU box)
+
+The reference's modules are imported from /root/reference/src (with the file-based xarray stand-in of
+oracle/_shims on sys.path because the image has no xarray).  Two run-time patches are applied to the
+*loaded module objects* - no reference source is copied or edited:
+  * DSDataset.__getitem__ is wrapped to return the 3-tuple (input, output, label) that
+    ConvAEModel.train unpacks (reference snapshot inconsistency: ds_dataset.py:159 returns 4 values,
+    conv_ae_model.py:316,322 unpack 3);
+  * BaseModel.evaluate / dump_metrics are stubbed (reference bug: default mask shaped like the INPUT,
+    base_model.py:93-98 - IndexError whenever input and output sizes differ).
+Everything written here is small (<1 MB per file) and committed.
+"""
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("CAE_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(0, os.path.join(REF, "src"))
+sys.path.insert(0, ROOT)
+
+from oracle import datagen  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_modules():
+    from cae_tools.models import encoder, decoder, model_sizer
+    return encoder, decoder, model_sizer
+
+
+def sd_np(sd, prefix):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
+
+
+def gen_specs():
+    _, _, sizer = ref_modules()
+    cases = {
+        "circle_16x16_256x256": dict(input_size=(16, 16), input_channels=1, output_size=(256, 256), output_channels=1),
+        "tidal_6x6_256x256": dict(input_size=(6, 6), input_channels=2, output_size=(256, 256), output_channels=1),
+        "circle2_24x20_280x256": dict(input_size=(24, 20), input_channels=1, output_size=(280, 256), output_channels=1),
+        "config4_64x64_1024x1024": dict(input_size=(64, 64), input_channels=4, output_size=(1024, 1024),
+                                        output_channels=4),
+        "mini_16x16_64x64": dict(input_size=(16, 16), input_channels=1, output_size=(64, 64), output_channels=1),
+        "nonsquare_12x10_40x36": dict(input_size=(12, 10), input_channels=1, output_size=(40, 36), output_channels=1),
+        "layers_2_3": dict(input_size=(32, 32), input_channels=3, output_size=(128, 128), output_channels=2,
+                           input_layer_count=2, output_layer_count=3),
+    }
+    out = {}
+    for name, kw in cases.items():
+        spec = sizer.create_model_spec(kernel_size=3, stride=2, **kw)
+        out[name] = {"args": {k: list(v) if isinstance(v, tuple) else v for k, v in kw.items()}, "spec": spec.save()}
+    with open(os.path.join(GOLD, "specs.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("specs.json", len(out))
+
+
+def gen_layers(name, in_size, out_size, in_ch, out_ch, batch, latent=4, fc=16, seed=1234, steps=3):
+    """reference Encoder/Decoder + MSELoss + Adam: per-layer activations, grads, 3 optimiser steps"""
+    enc_m, dec_m, sizer = ref_modules()
+    torch.manual_seed(seed)
+    spec = sizer.create_model_spec(input_size=in_size, input_channels=in_ch, output_size=out_size,
+                                   output_channels=out_ch, kernel_size=3, stride=2)
+    enc = enc_m.Encoder(spec.get_input_layers(), encoded_space_dim=latent, fc_size=fc)
+    dec = dec_m.Decoder(spec.get_output_layers(), encoded_space_dim=latent, fc_size=fc)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(batch, in_ch, *in_size, generator=g)
+    y = torch.rand(batch, out_ch, *out_size, generator=g)
+    out = {"x": x.numpy(), "y": y.numpy()}
+    out.update(sd_np(enc.state_dict(), "init.enc."))
+    out.update(sd_np(dec.state_dict(), "init.dec."))
+
+    # per-layer raw conv outputs (hooks on the conv modules; clone - the following ReLU is in-place)
+    acts = {}
+    hooks = []
+    for prefix, seq in (("enc", enc.encoder_cnn), ("dec", dec.decoder_conv)):
+        for idx, mod in enumerate(seq):
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                hooks.append(mod.register_forward_hook(
+                    lambda m, i, o, key=f"act.{prefix}.{idx}": acts.__setitem__(key, o.detach().clone().numpy())))
+    loss_fn = torch.nn.MSELoss()
+    optim = torch.optim.Adam([{'params': enc.parameters()}, {'params': dec.parameters()}], lr=1e-3, weight_decay=1e-5)
+    enc.train(); dec.train()
+    losses = []
+    for step in range(steps):
+        z = enc(x)
+        yhat = dec(z)
+        loss = loss_fn(yhat, y)
+        optim.zero_grad()
+        loss.backward()
+        if step == 0:
+            out.update(acts)
+            out["z"] = z.detach().numpy().copy()
+            out["yhat"] = yhat.detach().numpy().copy()
+            for k, p in enc.named_parameters():
+                out["grad.enc." + k] = p.grad.detach().numpy().copy()
+            for k, p in dec.named_parameters():
+                out["grad.dec." + k] = p.grad.detach().numpy().copy()
+        optim.step()
+        losses.append(float(loss.detach()))
+    for h in hooks:
+        h.remove()
+    out["losses"] = np.array(losses, dtype=np.float64)
+    out.update(sd_np(enc.state_dict(), f"after{steps}.enc."))
+    out.update(sd_np(dec.state_dict(), f"after{steps}.dec."))
+    enc.eval(); dec.eval()
+    with torch.no_grad():
+        out["eval_yhat"] = dec(enc(x)).numpy().copy()
+    out["spec_json"] = np.array(json.dumps(spec.save()))
+    path = os.path.join(GOLD, f"layers_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path) // 1024, "KB", "losses", losses)
+
+
+def gen_loss_curve(name, batch_size, nr_epochs, seed=1234, n=100):
+    """the reference ConvAEModel.train itself (patched as described in the module docstring)"""
+    from cae_tools.models import conv_ae_model as cam, ds_dataset, base_model
+    orig_getitem = ds_dataset.DSDataset.__getitem__
+    try:
+        def getitem3(self, index):
+            a, b, _m, lbl = orig_getitem(self, index)
+            return a, b, lbl
+        ds_dataset.DSDataset.__getitem__ = getitem3
+        ds_dataset.DSDataset.set_normalisation_parameters = \
+            lambda self, p: [setattr(self, k, v) for k, v in zip(("min_inputs", "max_inputs", "min_output", "max_output"), p)]
+        base_model.BaseModel.evaluate = lambda self, dataset, device: {}
+        base_model.BaseModel.dump_metrics = lambda self, title, metrics: None
+        train_ds, test_ds = datagen.circle_datasets(n, n)
+        torch.manual_seed(seed)
+        m = cam.ConvAEModel(batch_size=batch_size, nr_epochs=nr_epochs, test_interval=1, encoded_dim_size=4,
+                            fc_size=16, lr=1e-3, weight_decay=1e-5, use_gpu=False)
+        m.train(["lowres"], "hires", train_ds, test_ds)
+        # predictions of the trained reference on the first 4 test samples (eval mode)
+        lo = np.asarray(test_ds["lowres"].data[:4])
+        mn, mx = m.normalisation_parameters[0]["lowres"], m.normalisation_parameters[1]["lowres"]
+        xin = torch.from_numpy(((lo - mn) / (mx - mn)).astype(np.float32))
+        m.encoder.eval(); m.decoder.eval()
+        with torch.no_grad():
+            pred = m.decoder(m.encoder(xin)).numpy()
+        out = {
+            "train_loss": np.array(m.history["train_loss"], dtype=np.float64),
+            "test_loss": np.array(m.history["test_loss"], dtype=np.float64),
+            "pred_sub": pred[:, :, ::8, ::8].copy(),
+            "pred_mean": pred.mean(axis=(1, 2, 3)),
+            "norm": np.array(json.dumps(m.normalisation_parameters)),
+            "spec_json": np.array(json.dumps(m.spec.save())),
+            "params_json": np.array(json.dumps({k: v for k, v in m.get_parameters().items() if k != "model_id"})),
+        }
+        out.update(sd_np(m.encoder.state_dict(), "final.enc."))
+        out.update(sd_np(m.decoder.state_dict(), "final.dec."))
+        path = os.path.join(GOLD, f"curve_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(path, os.path.getsize(path) // 1024, "KB", out["train_loss"][[0, -1]], out["test_loss"][[0, -1]])
+    finally:
+        ds_dataset.DSDataset.__getitem__ = orig_getitem
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    gen_specs()
+    gen_layers("mini", (16, 16), (64, 64), 1, 1, batch=6)
+    gen_layers("nonsquare", (12, 10), (40, 36), 1, 1, batch=5)
+    gen_layers("multich", (16, 16), (64, 64), 2, 3, batch=4, latent=6, fc=24)
+    gen_loss_curve("conv_b10_e50", batch_size=10, nr_epochs=50)
+    gen_loss_curve("conv_b64_e5", batch_size=64, nr_epochs=5)

@@ -1,0 +1,126 @@
+"""TEST INFRASTRUCTURE - plain-PyTorch (CPU, fp32) restatement of the reference hot path.
+
+Written functionally (torch.nn.functional on explicit weight dictionaries) so that it shares no code
+with either the reference's nn.Module classes or the product's containers/kernels.  Each function names
+the reference lines it follows.  Checked against the live reference by tests/test_oracle_golden.py via
+the fixtures that oracle/gen_golden.py wrote.
+
+State-dict key layout (reference, probed - SURVEY section 8b):
+  encoder: encoder_cnn.{3i}.{weight,bias}  encoder_cnn.{3i+1}.{weight,bias,running_mean,running_var,num_batches_tracked}
+           encoder_lin.{0,2}.{weight,bias}
+  decoder: decoder_lin.{0,2}.{weight,bias} decoder_conv.{3j}.{weight,bias} decoder_conv.{3j+1}.{...BN...} (none after the last)
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _bn(x, sd, prefix, training):
+    """nn.BatchNorm2d forward (encoder.py:45, decoder.py:47): batch stats in training (and running-stat
+    update, unbiased variance, momentum 0.1), running stats in eval."""
+    rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+    out = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training, BN_MOMENTUM, BN_EPS)
+    if training:
+        sd[prefix + ".num_batches_tracked"] += 1
+    return out
+
+
+def encoder_forward(sd, specs, x, training, trace=None):
+    """Encoder.forward (encoder.py:60-64): [Conv2d -> BN -> ReLU] per layer, flatten, Linear-ReLU-Linear"""
+    for i, sp in enumerate(specs):
+        x = F.conv2d(x, sd[f"encoder_cnn.{3 * i}.weight"], sd[f"encoder_cnn.{3 * i}.bias"], stride=sp["stride"])
+        if trace is not None:
+            trace.append(x)
+        x = F.relu(_bn(x, sd, f"encoder_cnn.{3 * i + 1}", training))
+    x = x.flatten(1)
+    x = F.relu(F.linear(x, sd["encoder_lin.0.weight"], sd["encoder_lin.0.bias"]))
+    return F.linear(x, sd["encoder_lin.2.weight"], sd["encoder_lin.2.bias"])
+
+
+def decoder_forward(sd, specs, z, training, trace=None):
+    """Decoder.forward (decoder.py:73-78): Linear-ReLU-Linear, unflatten, [ConvT -> BN -> ReLU]..., ConvT, sigmoid"""
+    x = F.relu(F.linear(z, sd["decoder_lin.0.weight"], sd["decoder_lin.0.bias"]))
+    x = F.linear(x, sd["decoder_lin.2.weight"], sd["decoder_lin.2.bias"])
+    c, h, w = specs[0]["input_dimensions"]
+    x = x.view(-1, c, h, w)
+    last = len(specs) - 1
+    for j, sp in enumerate(specs):
+        x = F.conv_transpose2d(x, sd[f"decoder_conv.{3 * j}.weight"], sd[f"decoder_conv.{3 * j}.bias"],
+                               stride=sp["stride"], output_padding=sp["output_padding"])
+        if trace is not None:
+            trace.append(x)
+        if j != last:
+            x = F.relu(_bn(x, sd, f"decoder_conv.{3 * j + 1}", training))
+    return torch.sigmoid(x)
+
+
+def trainable_keys(sd):
+    return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var")
+                                  or k.endswith("num_batches_tracked"))]
+
+
+class OracleModel:
+    """weights + Adam state + the train/test/score loops of ConvAEModel (conv_ae_model.py:185-239,303-334)"""
+
+    def __init__(self, enc_sd, dec_sd, spec, lr=1e-3, weight_decay=1e-5, decoupled=False):
+        self.enc = {k: v.detach().clone().float() if v.is_floating_point() else v.detach().clone()
+                    for k, v in enc_sd.items()}
+        self.dec = {k: v.detach().clone().float() if v.is_floating_point() else v.detach().clone()
+                    for k, v in dec_sd.items()}
+        self.spec = spec  # dict as written to spec.json
+        self.params = []
+        for sd in (self.enc, self.dec):
+            for k in trainable_keys(sd):
+                sd[k].requires_grad_(True)
+                self.params.append(sd[k])
+        opt = torch.optim.AdamW if decoupled else torch.optim.Adam
+        self.optim = opt(self.params, lr=lr, weight_decay=weight_decay)  # conv_ae_model.py:310 / unet.py:457
+
+    def forward(self, x, training, trace=None):
+        z = encoder_forward(self.enc, self.spec["input_layers"], x, training, trace)
+        return decoder_forward(self.dec, self.spec["output_layers"], z, training, trace)
+
+    def train_step(self, x, y):
+        """conv_ae_model.py:191-197"""
+        loss = F.mse_loss(self.forward(x, True), y)
+        self.optim.zero_grad()
+        loss.backward()
+        self.optim.step()
+        return loss.detach()
+
+    def train_epoch(self, batches):
+        """conv_ae_model.py:185-203: mean of the per-batch mean losses"""
+        return float(np.mean([self.train_step(x, y).numpy() for x, y in batches]))
+
+    def test_epoch(self, batches):
+        """conv_ae_model.py:205-221 (eval mode: running statistics, no grad)"""
+        with torch.no_grad():
+            return float(np.mean([F.mse_loss(self.forward(x, False), y).numpy() for x, y in batches]))
+
+    def score(self, x):
+        with torch.no_grad():
+            return self.forward(x, False)
+
+
+def make_batches(X, Y, order, batch_size):
+    """the frozen, once-shuffled batch list of conv_ae_model.py:291-325 (last ragged batch kept)"""
+    X, Y = torch.as_tensor(X)[order], torch.as_tensor(Y)[order]
+    return [(X[i:i + batch_size], Y[i:i + batch_size]) for i in range(0, X.shape[0], batch_size)]
+
+
+def minmax(arr, lo, hi):
+    """DSDataset.normalise_* (ds_dataset.py:99-113)"""
+    return (arr - lo) / (hi - lo)
+
+
+def shuffled_order(n, batch_size):
+    """sample order of one pass over DataLoader(ds, batch_size, shuffle=True) drawing from torch's global RNG
+    (conv_ae_model.py:291-292; consumed at :316 and :322)"""
+    loader = torch.utils.data.DataLoader(range(n), batch_size=batch_size, shuffle=True)
+    return [int(i) for idx in loader for i in idx]

@@ -1,0 +1,121 @@
+"""Pin the oracle: the torch restatement (oracle/torch_port.py) and the numpy definitions
+(oracle/numpy_ops.py) must reproduce what the LIVE reference produced (tests/golden/*, written by
+oracle/gen_golden.py in the build container)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import load_npz, rel_err, spec_of, split_sd
+from oracle import datagen, numpy_ops
+from oracle.torch_port import OracleModel, make_batches, shuffled_order
+
+torch.set_num_threads(min(8, torch.get_num_threads()))
+
+
+@pytest.mark.parametrize("name", ["mini", "nonsquare", "multich"])
+def test_port_matches_reference_layers(name):
+    g = load_npz(f"layers_{name}.npz")
+    spec = spec_of(g)
+    m = OracleModel(split_sd(g, "init.enc."), split_sd(g, "init.dec."), spec)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    trace = []
+    yhat = m.forward(x, True, trace)
+    loss = F.mse_loss(yhat, y)
+    loss.backward()
+    acts = sorted((k for k in g if k.startswith("act.enc.")), key=lambda s: int(s.split(".")[-1])) + \
+        sorted((k for k in g if k.startswith("act.dec.")), key=lambda s: int(s.split(".")[-1]))
+    assert len(acts) == len(trace)
+    for k, t in zip(acts, trace):
+        assert rel_err(t.detach().numpy(), g[k]) < 1e-5, k
+    assert rel_err(yhat.detach().numpy(), g["yhat"]) < 1e-5
+    assert abs(float(loss) - g["losses"][0]) < 1e-6 * g["losses"][0]
+    for prefix, sd in (("enc.", m.enc), ("dec.", m.dec)):
+        for k, v in sd.items():
+            gk = "grad." + prefix + k
+            if gk in g:
+                scale = max(np.abs(g[gk]).max(), 1e-6)
+                assert np.abs(v.grad.numpy() - g[gk]).max() <= 2e-4 * scale + 1e-8, gk
+
+
+@pytest.mark.parametrize("name", ["mini", "nonsquare"])
+def test_port_matches_reference_adam_steps(name):
+    g = load_npz(f"layers_{name}.npz")
+    m = OracleModel(split_sd(g, "init.enc."), split_sd(g, "init.dec."), spec_of(g))
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    losses = [float(m.train_step(x, y)) for _ in range(3)]
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-5)
+    for prefix, sd in (("enc.", m.enc), ("dec.", m.dec)):
+        for k, v in sd.items():
+            ref = g["after3." + prefix + k]
+            if ref.dtype.kind == "f":
+                assert np.abs(v.detach().numpy() - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-3), k
+            else:
+                assert int(v) == int(ref)
+    assert rel_err(m.score(x).numpy(), g["eval_yhat"]) < 1e-4
+
+
+def test_port_matches_reference_training_loop_ragged():
+    """reference ConvAEModel.train, batch 64 on 100 samples (64 + ragged 36), 5 epochs"""
+    g = load_npz("curve_conv_b64_e5.npz")
+    tr, te = datagen.circle_datasets(100, 100)
+    norm = lambda a, lo, hi: ((a - lo) / (hi - lo)).astype(np.float32)
+    lo_min, lo_max = float(tr["lowres"].data.min()), float(tr["lowres"].data.max())
+    hi_min, hi_max = float(tr["hires"].data.min()), float(tr["hires"].data.max())
+    torch.manual_seed(1234)
+    from cae_tools_b200.models.model_sizer import create_model_spec
+    from cae_tools_b200.models.encoder import Encoder
+    from cae_tools_b200.models.decoder import Decoder
+    spec = create_model_spec(input_size=(16, 16), input_channels=1, output_size=(256, 256), output_channels=1)
+    assert spec.save() == spec_of(g)
+    enc = Encoder(spec.get_input_layers(), 4, 16)      # containers only supply the reference's init stream
+    dec = Decoder(spec.get_output_layers(), 4, 16)
+    order_tr = shuffled_order(100, 64)
+    order_te = shuffled_order(100, 64)
+    m = OracleModel(enc.state_dict(), dec.state_dict(), spec.save())
+    btr = make_batches(norm(tr["lowres"].data, lo_min, lo_max), norm(tr["hires"].data, hi_min, hi_max), order_tr, 64)
+    bte = make_batches(norm(te["lowres"].data, lo_min, lo_max), norm(te["hires"].data, hi_min, hi_max), order_te, 64)
+    assert [b[0].shape[0] for b in btr] == [64, 36]
+    train, test = [], []
+    for _ in range(5):
+        train.append(m.train_epoch(btr))
+        test.append(m.test_epoch(bte))
+    np.testing.assert_allclose(train, g["train_loss"], rtol=2e-4)
+    np.testing.assert_allclose(test, g["test_loss"], rtol=2e-4)
+
+
+def test_numpy_definitions_match_torch():
+    rng = np.random.RandomState(0)
+    for (ci, co, k, s, p, op, h, w) in [(3, 4, 3, 2, 0, 0, 7, 9), (2, 5, (4, 3), 2, 1, 1, 6, 5), (1, 2, 5, 3, 2, 0, 8, 8)]:
+        kh, kw = (k, k) if isinstance(k, int) else k
+        x = rng.randn(2, ci, h, w)
+        wc = rng.randn(co, ci, kh, kw)
+        b = rng.randn(co)
+        ref = F.conv2d(torch.tensor(x), torch.tensor(wc), torch.tensor(b), stride=s, padding=p).numpy()
+        np.testing.assert_allclose(numpy_ops.conv2d(x, wc, b, s, p), ref, atol=1e-10)
+        wt = rng.randn(ci, co, kh, kw)
+        ref = F.conv_transpose2d(torch.tensor(x), torch.tensor(wt), torch.tensor(b), stride=s, padding=p,
+                                 output_padding=op).numpy()
+        np.testing.assert_allclose(numpy_ops.conv_transpose2d(x, wt, b, s, p, op), ref, atol=1e-10)
+    x = rng.randn(4, 3, 5, 6) * 2 + 1
+    gam, bet, rm, rv = rng.rand(3) + 0.5, rng.randn(3), rng.randn(3), rng.rand(3) + 0.5
+    trm, trv = torch.tensor(rm.copy()), torch.tensor(rv.copy())
+    ref = F.batch_norm(torch.tensor(x), trm, trv, torch.tensor(gam), torch.tensor(bet), True, 0.1, 1e-5).numpy()
+    y, nrm, nrv = numpy_ops.batch_norm_train(x, gam, bet, rm, rv)
+    np.testing.assert_allclose(y, ref, atol=1e-10)
+    np.testing.assert_allclose(nrm, trm.numpy(), atol=1e-12)
+    np.testing.assert_allclose(nrv, trv.numpy(), atol=1e-12)
+    ref = F.batch_norm(torch.tensor(x), trm, trv, torch.tensor(gam), torch.tensor(bet), False, 0.1, 1e-5).numpy()
+    np.testing.assert_allclose(numpy_ops.batch_norm_eval(x, gam, bet, trm.numpy(), trv.numpy()), ref, atol=1e-10)
+    # Adam / AdamW, three steps
+    for decoupled in (False, True):
+        p0 = rng.randn(50)
+        tp = torch.tensor(p0.copy(), requires_grad=True)
+        opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([tp], lr=1e-2, weight_decay=0.1)
+        p, m, v = p0.copy(), np.zeros(50), np.zeros(50)
+        for t in range(1, 4):
+            gnp = rng.randn(50)
+            tp.grad = torch.tensor(gnp.copy())
+            opt.step()
+            p, m, v = numpy_ops.adam_step(p, gnp, m, v, t, lr=1e-2, wd=0.1, decoupled=decoupled)
+            np.testing.assert_allclose(p, tp.detach().numpy(), atol=1e-12)

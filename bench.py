@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Benchmark of the cae_tools hot path on B200 (BASELINE.json metric: train samples/s and apply images/s,
+16x16 -> 256x256 CAE).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one optimiser step (forward + MSE + backward + Adam) on one batch of synthetic data of the named
+shape.  N>1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N` (if it is
+not, this script re-executes itself that way): one rank per GPU, batch-sharded data parallel, the flat
+gradient arena all-reduced by NCCL inside the captured step, weak scaling (per-GPU batch fixed).
+
+Rank 0 prints ONE JSON line.  `value` is device-timed with inputs resident in HBM; `e2e` is the same metric with
+every step's inputs copied from pinned host memory and its loss read back inside the timed region.
+`--impl reference` times the CPU oracle port of the reference's PyTorch path (the reference itself is
+pure Python over PyTorch; see oracle/) on the host cores for the same config.
+"""
+
+import argparse
+import json
+import os
+import socket
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 64                 # per-GPU batch (BASELINE config 2 names batch 64)
+IN_SHAPE = (1, 16, 16)
+OUT_SHAPE = (1, 256, 256)
+LATENT, FC = 4, 16
+N_BATCHES = 64             # device-resident batches that the steps cycle through (1.1 GB > 126 MB L2)
+APPLY_BATCH = 1024
+APPLY_BATCHES = 16
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
+    return ap.parse_args()
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+# ----------------------------------------------------------------------------------------------------
+# geometry / algorithmic bytes (SURVEY section 8(d) convention; stated in DESIGN.md)
+# ----------------------------------------------------------------------------------------------------
+def layer_table(spec):
+    enc = [(l.get_input_dimensions(), l.get_output_dimensions()) for l in spec.get_input_layers()]
+    dec = [(l.get_input_dimensions(), l.get_output_dimensions()) for l in spec.get_output_layers()]
+    return enc, dec
+
+
+def numel(d):
+    return d[0] * d[1] * d[2]
+
+
+def bytes_per_sample(spec, fc, latent):
+    """B_train = 2*in + 5*inter + 5*out ; B_apply = in + 2*inter + out   (fp32)"""
+    enc, dec = layer_table(spec)
+    inp = numel(enc[0][0]) * 4
+    out = numel(dec[-1][1]) * 4
+    inter = sum(numel(o) for _, o in enc) + sum(numel(o) for _, o in dec[:-1])
+    inter += fc + latent + fc + numel(dec[0][0])
+    inter *= 4
+    return 2 * inp + 5 * inter + 5 * out, inp + 2 * inter + out
+
+
+def op_bytes(name, spec, B):
+    """algorithmic (compulsory) HBM bytes of one launch of a conv-family op: tensors read once + written once"""
+    enc, dec = layer_table(spec)
+    nd = len(dec)
+    f = 4 * B
+    if name.startswith("fwd.convT"):
+        j = int(name[len("fwd.convT"):].split("+")[0])
+        b = f * (numel(dec[j][0]) + numel(dec[j][1]))
+        if "mse" in name:
+            b += f * numel(dec[j][1])          # target
+        return b
+    if name.startswith("fwd.conv"):
+        i = int(name[len("fwd.conv"):])
+        return f * (numel(enc[i][0]) + numel(enc[i][1]))
+    if name.startswith("bwd.convT"):
+        j = int(name[len("bwd.convT"):].split(".")[0])
+        dy = numel(dec[j][1]) * (1 if j == nd - 1 else 2)      # dz (+ y for the BatchNorm-backward affine)
+        if name.endswith("wgrad"):
+            return f * (numel(dec[j][0]) + dy)
+        return f * (dy + (2 * numel(dec[j][0]) if j > 0 else numel(dec[j][0])))   # + mask read + dz write
+    if name.startswith("bwd.conv"):
+        i = int(name[len("bwd.conv"):].split(".")[0])
+        dy = 2 * numel(enc[i][1])
+        if name.endswith("wgrad"):
+            return f * (numel(enc[i][0]) + dy)
+        return f * (dy + 2 * numel(enc[i][0]))
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port of the reference's PyTorch path on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_train_rate(batch, steps, warmup):
+    import torch
+    from cae_tools_b200.models.decoder import Decoder
+    from cae_tools_b200.models.encoder import Encoder
+    from cae_tools_b200.models.model_sizer import create_model_spec
+    from oracle.torch_port import OracleModel
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    spec = create_model_spec(input_size=IN_SHAPE[1:], input_channels=IN_SHAPE[0], output_size=OUT_SHAPE[1:],
+                             output_channels=OUT_SHAPE[0])
+    enc, dec = Encoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
+    m = OracleModel(enc.state_dict(), dec.state_dict(), spec.save())
+    x, y = torch.rand(batch, *IN_SHAPE), torch.rand(batch, *OUT_SHAPE)
+    for _ in range(warmup):
+        m.train_step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.train_step(x, y)
+    dt = time.perf_counter() - t0
+    ta = time.perf_counter()
+    reps = max(1, steps // 4)
+    for _ in range(reps):
+        m.score(x)
+    apply_rate = batch * reps / (time.perf_counter() - ta)
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads(), apply_rate
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only; the CPU restatement of the reference path with all host threads"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 60))      # bounded sample: ~0.15 s per step on 8 cores
+    rate, ms, cores, apply_rate = cpu_train_rate(args.batch, steps, max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": "train_samples_per_sec", "value": rate, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.batch, 1),
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} optimiser steps at batch {args.batch} (oracle/torch_port.py, torch CPU)"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "apply": {"value": apply_rate, "unit": "images/s"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, world):
+    return {"workload": "ConvAEModel method=conv 1x16x16->1x256x256, latent 4, fc 16, k3 s2 (BASELINE config 1 "
+                        "geometry at config 2's batch 64); unet variant not built yet",
+            "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
+            "l2": f"steps cycle through {N_BATCHES} device-resident batches "
+                  f"({N_BATCHES * batch * (numel(IN_SHAPE) + numel(OUT_SHAPE)) * 4 / 1e6:.0f} MB > 126 MB L2); "
+                  "no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 leg
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from cae_tools_b200.engine.convae import ConvAEEngine
+    from cae_tools_b200.models.decoder import Decoder
+    from cae_tools_b200.models.encoder import Encoder
+    from cae_tools_b200.models.model_sizer import create_model_spec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(0)            # identical initial weights on every rank
+    spec = create_model_spec(input_size=IN_SHAPE[1:], input_channels=IN_SHAPE[0], output_size=OUT_SHAPE[1:],
+                             output_channels=OUT_SHAPE[0])
+    enc, dec = Encoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
+    hook = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=dev, grad_hook=hook, grad_scale=1.0 / world)
+
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    X = torch.rand(N_BATCHES * B, *IN_SHAPE, device=dev, generator=gen)
+    Y = torch.rand(N_BATCHES * B, *OUT_SHAPE, device=dev, generator=gen)
+    data = eng.bind(X, Y, B)
+    prog = eng._program("train", data, B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    # ---- train, inputs resident
+    for _ in range(W):
+        prog.run()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms = timed(prog.run, K)
+    clocks.stop()
+    value = world * B * K / (ms / 1e3)
+    final_loss = float(data.losses.mean().item())
+
+    # ---- train end to end: pinned host -> device staging -> step -> loss back
+    nh = 8
+    xh = torch.rand(nh, B, *IN_SHAPE).pin_memory()
+    yh = torch.rand(nh, B, *OUT_SHAPE).pin_memory()
+    xs, ys = torch.empty(B, *IN_SHAPE, device=dev), torch.empty(B, *OUT_SHAPE, device=dev)
+    sdata = eng.bind(xs, ys, B)
+    sprog = eng._program("train", sdata, B)
+    state = {"i": 0}
+
+    def e2e_step():
+        i = state["i"] % nh
+        state["i"] += 1
+        sdata.X.copy_(xh[i], non_blocking=True)
+        sdata.Y.copy_(yh[i], non_blocking=True)
+        sprog.run()
+        return float(sdata.losses.cpu()[0])
+
+    for _ in range(W):
+        e2e_step()
+    Ke = max(10, K // 4)
+    ms_e2e = timed(e2e_step, Ke)
+    e2e_value = world * B * Ke / (ms_e2e / 1e3)
+    h2d = B * (numel(IN_SHAPE) + numel(OUT_SHAPE)) * 4
+
+    # ---- apply (eval forward), inputs resident / end to end
+    AB = APPLY_BATCH
+    XA = torch.rand(APPLY_BATCHES * AB, *IN_SHAPE, device=dev, generator=gen)
+    adata = eng.bind(XA, None, AB)
+    eng._eval_prepare_op()()
+    aprog = eng._program("score", adata, AB)
+    for _ in range(W):
+        aprog.run()
+    Ka = max(10, K // 4)
+    ms_apply = timed(aprog.run, Ka)
+    apply_value = world * AB * Ka / (ms_apply / 1e3)
+    xah = torch.rand(4, AB, *IN_SHAPE).pin_memory()
+    yah = torch.empty(AB, *OUT_SHAPE).pin_memory()
+    xas = torch.empty(AB, *IN_SHAPE, device=dev)
+    sadata = eng.bind(xas, None, AB)
+    saprog = eng._program("score", sadata, AB)
+    yout = eng._act_buffers(AB)["y_d"][-1]
+
+    def apply_e2e():
+        sadata.X.copy_(xah[state["i"] % 4], non_blocking=True)
+        state["i"] += 1
+        saprog.run()
+        yah.copy_(yout, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        apply_e2e()
+    Kae = max(5, K // 10)
+    ms_apply_e2e = timed(apply_e2e, Kae)
+    apply_e2e_value = world * AB * Kae / (ms_apply_e2e / 1e3)
+
+    # ---- per-kernel table (eager, CUDA events around every launch) -> dominant kernel roofline
+    table = prog.profile(reps=5)
+    if args.profile_ops and rank == 0:
+        tot = sum(t for _, t in table)
+        for name, t in sorted(table, key=lambda r: -r[1]):
+            ob = op_bytes(name, spec, B)
+            gbs = f"{ob / t / 1e6:8.0f} GB/s" if ob else ""
+            print(f"  {name:28s} {t * 1e3:8.1f} us {100 * t / tot:5.1f}%  {gbs}", file=sys.stderr)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    conv_rows = [(n, t, op_bytes(n, spec, B)) for n, t in table if op_bytes(n, spec, B)]
+    top = max(conv_rows, key=lambda r: r[1])
+    achieved = top[2] / (top[1] / 1e3) / 1e9
+    b_train, b_apply = bytes_per_sample(spec, FC, LATENT)
+    roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel_us": top[1] * 1e3, "kernel_share_of_step": top[1] / sum(t for _, t in table),
+                "algorithmic_bytes_per_launch": top[2],
+                "step": {"bytes_per_sample": b_train, "achieved": b_train * B / (ms / K / 1e3) / 1e9,
+                         "frac": b_train * B / (ms / K / 1e3) / 1e9 / hbm_peak},
+                "apply_step": {"bytes_per_image": b_apply, "achieved": b_apply * AB / (ms_apply / Ka / 1e3) / 1e9,
+                               "frac": b_apply * AB / (ms_apply / Ka / 1e3) / 1e9 / hbm_peak}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cms, cores, arate = cpu_train_rate(B, 40, 3)
+        cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "apply_images_per_sec": arate,
+               "sample": f"40 optimiser steps at batch {B} (+10 eval batches) of the same workload, oracle port on torch CPU"}
+
+    if rank == 0:
+        line = {
+            "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / Ke},
+            "gpu_launches": prog.n_launches * K,
+            "launches_per_step": prog.n_launches,
+            "apply": {"value": apply_value, "unit": "images/s", "batch": AB, "ms_per_batch": ms_apply / Ka,
+                      "e2e": {"value": apply_e2e_value, "unit": "images/s",
+                              "h2d_bytes_per_step": AB * numel(IN_SHAPE) * 4,
+                              "d2h_bytes_per_step": AB * numel(OUT_SHAPE) * 4}},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "final_loss": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -182,7 +182,7 @@ class ConvAEEngine:
             else:
                 epi = ops.make_epilogue(ops.EPI_PLAIN, bias=conv.bias)
             g = ops.geom(sp.get_kernel_size(), sp.get_stride(), 0)
-            sched.append(lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_down(src, w, g, o, e))
+            sched.append((f"fwd.conv{i}", lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_down(src, w, g, o, e)))
             src = ops.make_src(y, k0=s[0], k2=s[1], relu=True, n=N)
         # fc stack
         lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
@@ -193,15 +193,15 @@ class ConvAEEngine:
         fc, lat = lin[0].out_features, lin[2].out_features
         fc2 = dlin[0].out_features
         out4 = dlin[2].out_features
-        sched.append(lambda: ops.gemm(N, fc, flat, ylast, flat, 1, lin[0].weight, 1, flat, b["h1"], fc, 1,
-                                      a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True,
-                                      bias=lin[0].bias, relu_out=True))
-        sched.append(lambda: ops.gemm(N, lat, fc, b["h1"], fc, 1, lin[2].weight, 1, fc, b["z"], lat, 1,
-                                      bias=lin[2].bias))
-        sched.append(lambda: ops.gemm(N, fc2, lat, b["z"], lat, 1, dlin[0].weight, 1, lat, b["h3"], fc2, 1,
-                                      bias=dlin[0].bias, relu_out=True))
-        sched.append(lambda: ops.gemm(N, out4, fc2, b["h3"], fc2, 1, dlin[2].weight, 1, fc2, b["u"], out4, 1,
-                                      bias=dlin[2].bias))
+        sched.append(("fwd.fc1", lambda: ops.gemm(N, fc, flat, ylast, flat, 1, lin[0].weight, 1, flat, b["h1"], fc, 1,
+                                                  a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True,
+                                                  bias=lin[0].bias, relu_out=True)))
+        sched.append(("fwd.fc2", lambda: ops.gemm(N, lat, fc, b["h1"], fc, 1, lin[2].weight, 1, fc, b["z"], lat, 1,
+                                                  bias=lin[2].bias)))
+        sched.append(("fwd.fc3", lambda: ops.gemm(N, fc2, lat, b["z"], lat, 1, dlin[0].weight, 1, lat, b["h3"], fc2, 1,
+                                                  bias=dlin[0].bias, relu_out=True)))
+        sched.append(("fwd.fc4", lambda: ops.gemm(N, out4, fc2, b["h3"], fc2, 1, dlin[2].weight, 1, fc2, b["u"], out4,
+                                                  1, bias=dlin[2].bias)))
         src = ops.make_src(b["u"], n=N)
         nd = len(self.dec_layers)
         for j, ((conv, bn), sp) in enumerate(zip(self.dec_layers, self.dec_specs)):
@@ -214,7 +214,8 @@ class ConvAEEngine:
                                             partials=self._partials(conv.out_channels), ticket=self._ticket(), bn=blk)
                 else:
                     epi = ops.make_epilogue(ops.EPI_PLAIN, bias=conv.bias)
-                sched.append(lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_up(src, w, g, o, e))
+                sched.append((f"fwd.convT{j}", lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi:
+                              ops.conv_up(src, w, g, o, e)))
                 src = ops.make_src(y, k0=s[0], k2=s[1], relu=True, n=N)
             else:
                 if final == "yhat":
@@ -228,7 +229,8 @@ class ConvAEEngine:
                                             target=tgt, loss_out=data.losses,
                                             dbias=self.g(conv.bias) if train else None,
                                             write_mode=0 if final == "loss_grad" else 2)
-                sched.append(lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_up(src, w, g, o, e))
+                sched.append((f"fwd.convT{j}+sigmoid" + ("" if final == "yhat" else "+mse"),
+                              lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_up(src, w, g, o, e)))
         return sched
 
     def _wgrad_op(self, small, big, g, grad):
@@ -255,7 +257,7 @@ class ConvAEEngine:
                 x_in = ops.make_src(b["y_d"][j - 1], k0=sp_prev[0], k2=sp_prev[1], relu=True, n=N)
             else:
                 x_in = ops.make_src(b["u"], n=N)
-            sched.append(self._wgrad_op(x_in, dy, g, self.g(conv.weight)))
+            sched.append((f"bwd.convT{j}.wgrad", self._wgrad_op(x_in, dy, g, self.g(conv.weight))))
             if j > 0:
                 pconv, pbn = self.dec_layers[j - 1]
                 blk, _ = self._bn(("d", j - 1), pbn, self.g(pconv.bias))
@@ -265,7 +267,8 @@ class ConvAEEngine:
             else:
                 epi = ops.make_epilogue(ops.EPI_PLAIN)
                 out = ops.view4(b["du"], N)
-            sched.append(lambda dy=dy, w=conv.weight, g=g, o=out, e=epi: ops.conv_down(dy, w, g, o, e))
+            sched.append((f"bwd.convT{j}.dgrad", lambda dy=dy, w=conv.weight, g=g, o=out, e=epi:
+                          ops.conv_down(dy, w, g, o, e)))
         # ---- fc stack
         lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
         ce, he, we = self.enc_specs[-1].get_output_dimensions()
@@ -277,30 +280,31 @@ class ConvAEEngine:
         s_last = self._bn_scratch[("e", le)]
         ylast = b["y_e"][-1]
         # Linear 4: u = h3 W4^T + b4
-        sched.append(lambda: ops.gemm(out4, fc2, N, b["du"], 1, out4, b["h3"], fc2, 1, G(dlin[2].weight), fc2, 1,
-                                      rowsum_A=G(dlin[2].bias)))
-        sched.append(lambda: ops.gemm(N, fc2, out4, b["du"], out4, 1, dlin[2].weight, fc2, 1, b["dh3"], fc2, 1,
-                                      mask=b["h3"]))
+        sched.append(("bwd.fc4.dW", lambda: ops.gemm(out4, fc2, N, b["du"], 1, out4, b["h3"], fc2, 1, G(dlin[2].weight), fc2, 1,
+                                      rowsum_A=G(dlin[2].bias))))
+        sched.append(("bwd.fc4.dx", lambda: ops.gemm(N, fc2, out4, b["du"], out4, 1, dlin[2].weight, fc2, 1, b["dh3"], fc2, 1,
+                                      mask=b["h3"])))
         # Linear 3: h3 = relu(z W3^T + b3)
-        sched.append(lambda: ops.gemm(fc2, lat, N, b["dh3"], 1, fc2, b["z"], lat, 1, G(dlin[0].weight), lat, 1,
-                                      rowsum_A=G(dlin[0].bias)))
-        sched.append(lambda: ops.gemm(N, lat, fc2, b["dh3"], fc2, 1, dlin[0].weight, lat, 1, b["dzl"], lat, 1))
+        sched.append(("bwd.fc3.dW", lambda: ops.gemm(fc2, lat, N, b["dh3"], 1, fc2, b["z"], lat, 1, G(dlin[0].weight), lat, 1,
+                                      rowsum_A=G(dlin[0].bias))))
+        sched.append(("bwd.fc3.dx", lambda: ops.gemm(N, lat, fc2, b["dh3"], fc2, 1, dlin[0].weight, lat, 1, b["dzl"], lat, 1)))
         # Linear 2: z = h1 W2^T + b2
-        sched.append(lambda: ops.gemm(lat, fc, N, b["dzl"], 1, lat, b["h1"], fc, 1, G(lin[2].weight), fc, 1,
-                                      rowsum_A=G(lin[2].bias)))
-        sched.append(lambda: ops.gemm(N, fc, lat, b["dzl"], lat, 1, lin[2].weight, fc, 1, b["dh1"], fc, 1,
-                                      mask=b["h1"]))
+        sched.append(("bwd.fc2.dW", lambda: ops.gemm(lat, fc, N, b["dzl"], 1, lat, b["h1"], fc, 1, G(lin[2].weight), fc, 1,
+                                      rowsum_A=G(lin[2].bias))))
+        sched.append(("bwd.fc2.dx", lambda: ops.gemm(N, fc, lat, b["dzl"], lat, 1, lin[2].weight, fc, 1, b["dh1"], fc, 1,
+                                      mask=b["h1"])))
         # Linear 1: h1 = relu(a W1^T + b1), a = relu(bn(y_last)) flattened
-        sched.append(lambda: ops.gemm(fc, flat, N, b["dh1"], 1, fc, ylast, flat, 1, G(lin[0].weight), flat, 1,
+        sched.append(("bwd.fc1.dW", lambda: ops.gemm(fc, flat, N, b["dh1"], 1, fc, ylast, flat, 1, G(lin[0].weight), flat, 1,
                                       b_k0=s_last[0], b_k2=s_last[1], b_hw=he * we, b_relu=True,
-                                      rowsum_A=G(lin[0].bias)))
-        sched.append(lambda: ops.gemm(N, flat, fc, b["dh1"], fc, 1, lin[0].weight, flat, 1, b["da"], flat, 1))
+                                      rowsum_A=G(lin[0].bias))))
+        sched.append(("bwd.fc1.dx", lambda: ops.gemm(N, flat, fc, b["dh1"], fc, 1, lin[0].weight, flat, 1, b["da"], flat, 1)))
         # ReLU mask + BN-backward sums of the last encoder layer
         conv, bn = self.enc_layers[le]
         blk, _ = self._bn(("e", le), bn, self.g(conv.bias))
         epi = ops.make_epilogue(ops.EPI_MASKSTATS, partials=self._partials(conv.out_channels), ticket=self._ticket(),
                                 bn=blk, act=ylast, n=N)
-        sched.append(lambda s=ops.make_src(b["da"], n=N), o=ops.view4(b["dz_e"][le], N), e=epi: ops.ew_epilogue(s, o, e))
+        sched.append(("bwd.enc_last.mask+bnsums", lambda s=ops.make_src(b["da"], n=N), o=ops.view4(b["dz_e"][le], N), e=epi:
+                      ops.ew_epilogue(s, o, e)))
         # ---- encoder
         X = data.X
         for i in range(le, -1, -1):
@@ -315,24 +319,25 @@ class ConvAEEngine:
             else:
                 x_in = ops.make_src(X[:data.batch_size] if X.shape[0] >= data.batch_size else X, cursor=data.cursor,
                                     cursor_stride=data.batch_size * X[0].numel(), n=N)
-            sched.append(self._wgrad_op(dy, x_in, g, self.g(conv.weight)))
+            sched.append((f"bwd.conv{i}.wgrad", self._wgrad_op(dy, x_in, g, self.g(conv.weight))))
             if i > 0:
                 pconv, pbn = self.enc_layers[i - 1]
                 blk, _ = self._bn(("e", i - 1), pbn, self.g(pconv.bias))
                 epi = ops.make_epilogue(ops.EPI_MASKSTATS, partials=self._partials(pconv.out_channels),
                                         ticket=self._ticket(), bn=blk, act=b["y_e"][i - 1], n=N)
-                sched.append(lambda dy=dy, w=conv.weight, g=g, o=ops.view4(b["dz_e"][i - 1], N), e=epi:
-                             ops.conv_up(dy, w, g, o, e))
+                sched.append((f"bwd.conv{i}.dgrad", lambda dy=dy, w=conv.weight, g=g, o=ops.view4(b["dz_e"][i - 1], N),
+                              e=epi: ops.conv_up(dy, w, g, o, e)))
         return sched
 
     def _update_ops(self, data):
-        def upd():
-            if self.grad_hook is not None:
-                self.grad_hook(self.grads)
-            ops.adam(self.arena, self.grads, self.adam_m, self.adam_v, self.n_params, self.lr, self.betas[0],
-                     self.betas[1], self.eps, self.weight_decay, self.decoupled, self.grad_scale, self.step_count)
-            ops.step_advance(self.step_count, data.cursor, data.n_batches)
-        return [upd]
+        out = []
+        if self.grad_hook is not None:
+            out.append(("grad_allreduce", lambda: self.grad_hook(self.grads)))
+        out.append(("adam", lambda: ops.adam(self.arena, self.grads, self.adam_m, self.adam_v, self.n_params, self.lr,
+                                             self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                             self.decoupled, self.grad_scale, self.step_count)))
+        out.append(("advance", lambda: ops.step_advance(self.step_count, data.cursor, data.n_batches)))
+        return out
 
     def _eval_prepare_op(self):
         if self._bn_table is None:
@@ -358,10 +363,10 @@ class ConvAEEngine:
                 self._update_ops(data)
         elif kind == "test":
             sched = self._forward_ops(b, N, data, False, "loss") + \
-                [lambda: ops.step_advance(None, data.cursor, data.n_batches)]
+                [("advance", lambda: ops.step_advance(None, data.cursor, data.n_batches))]
         elif kind == "score":
             sched = self._forward_ops(b, N, data, False, "yhat") + \
-                [lambda: ops.step_advance(None, data.cursor, data.n_batches)]
+                [("advance", lambda: ops.step_advance(None, data.cursor, data.n_batches))]
         else:
             raise ValueError(kind)
         state = [data.cursor, data.losses]
@@ -432,8 +437,33 @@ class _Program:
         self.graph = None
 
     def run_eager(self):
-        for op in self.sched:
+        for _, op in self.sched:
             op()
+
+    @property
+    def n_launches(self):
+        return len(self.sched)
+
+    def profile(self, reps=5):
+        """eager run with a CUDA-event pair around every op: [(name, mean ms)] (state is restored afterwards)"""
+        saved = [t.clone() for t in self.state]
+        st = torch.cuda.current_stream()
+        acc = [0.0] * len(self.sched)
+        for _ in range(reps):
+            evs = []
+            for _, op in self.sched:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st)
+                op()
+                b.record(st)
+                evs.append((a, b))
+            st.synchronize()
+            for i, (a, b) in enumerate(evs):
+                acc[i] += a.elapsed_time(b)
+        with torch.no_grad():
+            for t, c in zip(self.state, saved):
+                t.copy_(c)
+        return [(name, acc[i] / reps) for i, (name, _) in enumerate(self.sched)]
 
     def run(self):
         if not self.use_graph:

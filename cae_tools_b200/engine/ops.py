@@ -37,22 +37,29 @@ def view4(t: torch.Tensor, n=None) -> CaeView:
     assert sw == 1 or W == 1
     if H == 1:
         sh = max(W, 1)
-    return CaeView(t.data_ptr(), int(N if n is None else n), int(Cc), int(H), int(W), int(sh), int(sc), int(sn))
+    v = CaeView(t.data_ptr(), int(N if n is None else n), int(Cc), int(H), int(W), int(sh), int(sc), int(sn))
+    v._keep = t   # descriptors hold raw pointers: keep the tensor alive as long as the descriptor
+    return v
 
 
 def make_src(t0, t1=None, k0=None, k1=None, k2=None, relu=False, cursor=None, cursor_stride=0, n=None) -> CaeSrc:
     if t1 is not None:
         assert t1.shape == t0.shape and t1.stride() == t0.stride(), "t1 must share t0's geometry"
-    return CaeSrc(view4(t0, n), _ptr(t1), _ptr(k0), _ptr(k1), _ptr(k2), int(bool(relu)), _ptr(cursor),
-                  int(cursor_stride))
+    s = CaeSrc(view4(t0, n), _ptr(t1), _ptr(k0), _ptr(k1), _ptr(k2), int(bool(relu)), _ptr(cursor),
+               int(cursor_stride))
+    s._keep = (t0, t1, k0, k1, k2, cursor)
+    return s
 
 
 def make_bn(Cn, eps=1e-5, momentum=0.1, gamma=None, beta=None, running_mean=None, running_var=None, nbt=None,
             scale=None, shift=None, mean=None, invstd=None, dgamma=None, dbeta=None, dbias=None, bwdA=None,
             bwdB=None, bwdC=None) -> CaeBN:
-    return CaeBN(int(Cn), float(eps), float(momentum), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
-                 _ptr(nbt), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(dgamma), _ptr(dbeta),
-                 _ptr(dbias), _ptr(bwdA), _ptr(bwdB), _ptr(bwdC))
+    b = CaeBN(int(Cn), float(eps), float(momentum), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+              _ptr(nbt), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(dgamma), _ptr(dbeta),
+              _ptr(dbias), _ptr(bwdA), _ptr(bwdB), _ptr(bwdC))
+    b._keep = (gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, dgamma, dbeta, dbias, bwdA,
+               bwdB, bwdC)
+    return b
 
 
 _NULL_VIEW = CaeView(None, 0, 0, 0, 0, 0, 0, 0)
@@ -75,6 +82,7 @@ def make_epilogue(mode, bias=None, partials=None, ticket=None, bn=None, act=None
     e.loss_out = _ptr(loss_out)
     e.dbias = _ptr(dbias)
     e.write_mode = int(write_mode)
+    e._keep = (bias, partials, ticket, bn, act, target, loss_out, dbias)
     return e
 
 

@@ -163,6 +163,46 @@ def gen_loss_curve(name, batch_size, nr_epochs, seed=1234, n=100):
         ds_dataset.DSDataset.__getitem__ = orig_getitem
 
 
+def gen_chaos_envelope(seed=1234, nr_epochs=50, batch_size=10):
+    """How far do the REFERENCE's own 50-epoch loss curves move when only the CPU thread count changes?
+    (Adam amplifies fp32 summation-order differences; SURVEY section 7 'loss-curve chaos'.)  Uses the oracle port,
+    which reproduces the reference's 8-thread curve bit for bit (asserted below), at 1 and 4 threads."""
+    from oracle.torch_port import OracleModel, make_batches, shuffled_order
+    from cae_tools.models import encoder, decoder, model_sizer
+    ref = dict(np.load(os.path.join(GOLD, "curve_conv_b10_e50.npz")))
+    tr, te = datagen.circle_datasets(100, 100)
+    norm = lambda a, lo, hi: ((a - lo) / (hi - lo)).astype(np.float32)
+    lo_min, lo_max = float(tr["lowres"].data.min()), float(tr["lowres"].data.max())
+    hi_min, hi_max = float(tr["hires"].data.min()), float(tr["hires"].data.max())
+    out = {}
+    for threads in (8, 1, 4):
+        torch.set_num_threads(threads)
+        torch.manual_seed(seed)
+        spec = model_sizer.create_model_spec(input_size=(16, 16), input_channels=1, output_size=(256, 256),
+                                             output_channels=1)
+        enc = encoder.Encoder(spec.get_input_layers(), 4, 16)
+        dec = decoder.Decoder(spec.get_output_layers(), 4, 16)
+        otr, ote = shuffled_order(100, batch_size), shuffled_order(100, batch_size)
+        m = OracleModel(enc.state_dict(), dec.state_dict(), spec.save())
+        btr = make_batches(norm(tr["lowres"].data, lo_min, lo_max), norm(tr["hires"].data, hi_min, hi_max), otr, batch_size)
+        bte = make_batches(norm(te["lowres"].data, lo_min, lo_max), norm(te["hires"].data, hi_min, hi_max), ote, batch_size)
+        a, b = [], []
+        for _ in range(nr_epochs):
+            a.append(m.train_epoch(btr))
+            b.append(m.test_epoch(bte))
+        a, b = np.array(a), np.array(b)
+        if threads == 8:
+            assert np.array_equal(a, ref["train_loss"]) and np.array_equal(b, ref["test_loss"]), \
+                "port no longer reproduces the reference bit for bit at 8 threads"
+        else:
+            out[f"train_t{threads}"] = a
+            out[f"test_t{threads}"] = b
+            print(f"threads={threads}: max rel dev train {np.max(np.abs(a - ref['train_loss']) / ref['train_loss']):.2e}"
+                  f" test {np.max(np.abs(b - ref['test_loss']) / ref['test_loss']):.2e}")
+    torch.set_num_threads(8)
+    np.savez_compressed(os.path.join(GOLD, "curve_conv_b10_e50_envelope.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -172,3 +212,4 @@ if __name__ == "__main__":
     gen_layers("multich", (16, 16), (64, 64), 2, 3, batch=4, latent=6, fc=24)
     gen_loss_curve("conv_b10_e50", batch_size=10, nr_epochs=50)
     gen_loss_curve("conv_b64_e5", batch_size=64, nr_epochs=5)
+    gen_chaos_envelope()

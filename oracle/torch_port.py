@@ -68,7 +68,11 @@ def trainable_keys(sd):
 class OracleModel:
     """weights + Adam state + the train/test/score loops of ConvAEModel (conv_ae_model.py:185-239,303-334)"""
 
-    def __init__(self, enc_sd, dec_sd, spec, lr=1e-3, weight_decay=1e-5, decoupled=False):
+    def __init__(self, enc_sd, dec_sd, spec, lr=1e-3, weight_decay=1e-5, decoupled=False, zero_dead_bias_grads=False):
+        """zero_dead_bias_grads: the bias of a conv that feeds a training-mode BatchNorm has an identically zero
+        gradient; autograd returns rounding noise (~1e-9) there which Adam then amplifies into a random walk of
+        that (output-irrelevant) bias.  The CUDA path writes the exact zero; set this flag to compare tightly."""
+        self.zero_dead_bias_grads = zero_dead_bias_grads
         self.enc = {k: v.detach().clone().float() if v.is_floating_point() else v.detach().clone()
                     for k, v in enc_sd.items()}
         self.dec = {k: v.detach().clone().float() if v.is_floating_point() else v.detach().clone()
@@ -91,6 +95,13 @@ class OracleModel:
         loss = F.mse_loss(self.forward(x, True), y)
         self.optim.zero_grad()
         loss.backward()
+        if self.zero_dead_bias_grads:
+            for sd in (self.enc, self.dec):
+                for k in sd:
+                    if k.endswith(".bias") and k.split(".")[0] in ("encoder_cnn", "decoder_conv"):
+                        stem, idx = k.split(".")[0], int(k.split(".")[1])
+                        if f"{stem}.{idx + 1}.running_mean" in sd and idx % 3 == 0:
+                            sd[k].grad.zero_()
         self.optim.step()
         return loss.detach()
 

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
+    ap.add_argument("--train-only", action="store_true", help="skip the e2e / apply legs (short runs under ncu)")
     return ap.parse_args()
 
 
@@ -281,6 +282,13 @@ def run_b200(args):
     clocks.stop()
     value = world * B * K / (ms / 1e3)
     final_loss = float(data.losses.mean().item())
+
+    if args.train_only:
+        if rank == 0:
+            print(json.dumps({"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+                              "steps": K, "warmup": W, "ms_per_step": ms / K, "launches_per_step": prog.n_launches,
+                              "note": "--train-only run (profiling aid, not a bench line)"}), flush=True)
+        return
 
     # ---- train end to end: pinned host -> device staging -> step -> loss back
     nh = 8

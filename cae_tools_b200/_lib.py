@@ -42,7 +42,7 @@ class CaeBN(C.Structure):
 class CaeEpilogue(C.Structure):
     _fields_ = [("mode", C.c_int), ("bias", C.c_void_p), ("partials", C.c_void_p), ("ticket", C.c_void_p),
                 ("bn", CaeBN), ("act", CaeView), ("target", CaeSrc), ("loss_out", C.c_void_p),
-                ("dbias", C.c_void_p), ("write_mode", C.c_int)]
+                ("dbias", C.c_void_p), ("write_mode", C.c_int), ("count_scale", C.c_float)]
 
 
 class CaeGemm(C.Structure):

@@ -130,7 +130,8 @@ static int fill_conv_args(ConvArgs& a, const CaeSrc* in, const float* weight, co
     if ((rc = check_epilogue(a.epi, *out))) return rc;
     a.Cin = in->t0.C;
     a.Cout = out->C;
-    a.inv_count = (float)(1.0 / ((double)out->N * out->C * out->H * out->W));
+    a.inv_count = (float)((a.epi.count_scale > 0.f ? (double)a.epi.count_scale : 1.0) /
+                          ((double)out->N * out->C * out->H * out->W));
     return CAE_OK;
 }
 
@@ -203,7 +204,8 @@ extern "C" int cae_ew_epilogue(const CaeSrc* in, const CaeView* out, const CaeEp
     a.Cin = a.Cout = out->C;
     a.QH = out->H; a.QW = out->W;
     a.total = out->N * out->H * out->W;
-    a.inv_count = (float)(1.0 / ((double)out->N * out->C * out->H * out->W));
+    a.inv_count = (float)((a.epi.count_scale > 0.f ? (double)a.epi.count_scale : 1.0) /
+                          ((double)out->N * out->C * out->H * out->W));
     dim3 grid(min(ceil_div(a.total, CAE_NT), CAE_MAX_GRID_X), out->C);
     k_ew_epilogue<<<grid, CAE_NT, 0, (cudaStream_t)stream>>>(a);
     return cae_check_launch("cae_ew_epilogue");

@@ -102,7 +102,8 @@ __device__ __forceinline__ void finalize_mse(const CaeEpilogue& e, const double*
         double t = 0.0;
         for (int w = 0; w < CAE_NWARP; ++w) t += wq[w];
         int slot = e.target.cursor ? __ldg(e.target.cursor) : 0;
-        if (e.loss_out) e.loss_out[slot] = (float)(t / count);
+        const double cs = e.count_scale > 0.f ? (double)e.count_scale : 1.0;
+        if (e.loss_out) e.loss_out[slot] = (float)(t / count * cs);
     }
 }
 

@@ -61,7 +61,7 @@ def _align(n, a=4):
 class ConvAEEngine:
 
     def __init__(self, encoder, decoder, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, decoupled=False,
-                 device="cuda", use_graphs=True, grad_hook=None, grad_scale=1.0):
+                 device="cuda", use_graphs=True, grad_hook=None, grad_scale=1.0, count_scale=1.0):
         require_cuda()
         self.device = torch.device(device)
         self.encoder = encoder.to(self.device)
@@ -70,6 +70,7 @@ class ConvAEEngine:
         self.use_graphs = use_graphs
         self.grad_hook = grad_hook      # callable(flat_grads) between backward and Adam (data-parallel all-reduce)
         self.grad_scale = grad_scale
+        self.count_scale = count_scale  # n_local / n_global when a batch is sharded over data-parallel ranks
         self._keep = []                 # descriptors' tensors must outlive the graphs
         self._build_arena()
         self.enc_layers = self.encoder.conv_layers()
@@ -228,7 +229,8 @@ class ConvAEEngine:
                                             partials=self._partials(conv.out_channels), ticket=self._ticket(),
                                             target=tgt, loss_out=data.losses,
                                             dbias=self.g(conv.bias) if train else None,
-                                            write_mode=0 if final == "loss_grad" else 2)
+                                            write_mode=0 if final == "loss_grad" else 2,
+                                            count_scale=self.count_scale)
                 sched.append((f"fwd.convT{j}+sigmoid" + ("" if final == "yhat" else "+mse"),
                               lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_up(src, w, g, o, e)))
         return sched

@@ -1,0 +1,72 @@
+"""Batch-sharded data parallelism: one process per GPU, torch.distributed for the plumbing.
+
+The reference has no multi-GPU path (single `device`, conv_ae_model.py:294-297); this is the
+data-parallel wrapper BASELINE.json's north_star asks for.  Every optimiser step has exactly one
+exchange: a SUM all-reduce of the flat fp32 gradient arena (NCCL over NVLink on GPUs; gloo in the
+CPU tests), captured inside the step's CUDA graph.  Each rank computes on its contiguous share of
+every global batch; the loss epilogue divides by the GLOBAL element count (count_scale =
+n_local/n_global), so the summed gradients - and the summed per-batch losses - are exactly those of
+the global batch.  BatchNorm uses the statistics of the local share ("local BN").  `apply` shards the
+samples over ranks with no collective at all.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, rank, world):
+    """contiguous split of n items: the first n % world ranks get one extra"""
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_batches(order, batch_size, rank, world):
+    """Split every batch of the (already shuffled) sample order over the ranks.
+    Returns (local_order, local_batch_size, count_scale).  Batches must divide evenly so that every
+    rank runs the same kernel schedule: batch_size % world == 0 and (n % batch_size) % world == 0."""
+    n = len(order)
+    if batch_size % world != 0:
+        raise ValueError(f"batch_size {batch_size} is not a multiple of the {world} data-parallel ranks")
+    tail = n % batch_size
+    if tail % world != 0:
+        raise ValueError(f"the last batch ({tail} samples) does not split evenly over {world} ranks")
+    local = []
+    for b0 in range(0, n, batch_size):
+        chunk = order[b0:b0 + batch_size]
+        lo, hi = shard_bounds(len(chunk), rank, world)
+        local.extend(chunk[lo:hi])
+    return local, batch_size // world, 1.0 / world
+
+
+class DPContext:
+    """rank / world bookkeeping + the two collectives the hot path uses"""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    @staticmethod
+    def from_env():
+        """a context if torch.distributed is initialised with more than one rank, else None"""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return DPContext()
+        return None
+
+    def allreduce_grads(self, flat):
+        """the per-step exchange: in-place SUM over ranks of the flat gradient arena"""
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        return flat
+
+    def reduce_losses(self, losses):
+        """per-batch losses were divided by the global count on every rank: SUM gives the global batch MSE"""
+        out = losses.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def broadcast_(self, tensors, src=0):
+        for t in tensors:
+            dist.broadcast(t, src=src, group=self.group)

@@ -67,7 +67,7 @@ _NULL_BN = CaeBN()
 
 
 def make_epilogue(mode, bias=None, partials=None, ticket=None, bn=None, act=None, target=None, loss_out=None,
-                  dbias=None, write_mode=0, n=None) -> CaeEpilogue:
+                  dbias=None, write_mode=0, n=None, count_scale=1.0) -> CaeEpilogue:
     e = CaeEpilogue()
     e.mode = int(mode)
     e.bias = _ptr(bias)
@@ -82,6 +82,7 @@ def make_epilogue(mode, bias=None, partials=None, ticket=None, bn=None, act=None
     e.loss_out = _ptr(loss_out)
     e.dbias = _ptr(dbias)
     e.write_mode = int(write_mode)
+    e.count_scale = float(count_scale)
     e._keep = (bias, partials, ticket, bn, act, target, loss_out, dbias)
     return e
 

@@ -165,9 +165,12 @@ class ConvAEModel(BaseModel):
             raise CaeError("no CUDA device: cae_tools_b200 has no CPU execution path")
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _make_engine(self, device):
+    def _make_engine(self, device, dp=None):
         from ..engine.convae import ConvAEEngine
-        return ConvAEEngine(self.encoder, self.decoder, lr=self.lr, weight_decay=self.weight_decay, device=device)
+        if dp is None:
+            return ConvAEEngine(self.encoder, self.decoder, lr=self.lr, weight_decay=self.weight_decay, device=device)
+        return ConvAEEngine(self.encoder, self.decoder, lr=self.lr, weight_decay=self.weight_decay, device=device,
+                            grad_hook=dp.allreduce_grads, count_scale=1.0 / dp.world)
 
     def _ensure_engine(self):
         if self.engine is None:
@@ -229,11 +232,22 @@ class ConvAEModel(BaseModel):
         train_order = shuffled_order(len(train_ds), self.batch_size)
         test_order = shuffled_order(len(test_ds), self.batch_size)
 
-        self.engine = eng = self._make_engine(device)
+        # data parallel (torch.distributed initialised with >1 rank): every rank holds the same weights (same
+        # seed => same init; rank 0's are broadcast to be safe) and its contiguous share of every batch
+        from ..engine.dp import DPContext, shard_batches
+        dp = DPContext.from_env()
+        local_batch = self.batch_size
+        if dp is not None:
+            train_order, local_batch, _ = shard_batches(train_order, self.batch_size, dp.rank, dp.world)
+            test_order, _, _ = shard_batches(test_order, self.batch_size, dp.rank, dp.world)
+        self.engine = eng = self._make_engine(device, dp)
+        if dp is not None:
+            dp.broadcast_([eng.arena] + [b for m in (self.encoder, self.decoder) for b in m.buffers()])
         train_data = eng.bind(torch.from_numpy(train_ds.input_array(train_order)),
-                              torch.from_numpy(train_ds.output_array(train_order)), self.batch_size)
+                              torch.from_numpy(train_ds.output_array(train_order)), local_batch)
         test_data = eng.bind(torch.from_numpy(test_ds.input_array(test_order)),
-                             torch.from_numpy(test_ds.output_array(test_order)), self.batch_size)
+                             torch.from_numpy(test_ds.output_array(test_order)), local_batch)
+        gather = (lambda t: dp.reduce_losses(t)) if dp is not None else (lambda t: t)
 
         train_loss = test_loss = 0.0
         last = self.nr_epochs - 1
@@ -241,9 +255,9 @@ class ConvAEModel(BaseModel):
             losses = eng.train_epoch(train_data)
             report = (epoch % self.test_interval == 0)
             if report or epoch == last:
-                train_loss = float(np.mean(losses.cpu().numpy()))   # the only host sync of the epoch
+                train_loss = float(np.mean(gather(losses).cpu().numpy()))   # the only host sync of the epoch
             if report:
-                test_loss = float(np.mean(eng.test_epoch(test_data).cpu().numpy()))
+                test_loss = float(np.mean(gather(eng.test_epoch(test_data)).cpu().numpy()))
                 self.history["train_loss"].append(train_loss)
                 self.history["test_loss"].append(test_loss)
                 if self.verbose:
@@ -260,7 +274,7 @@ class ConvAEModel(BaseModel):
             self.db.add_training_result(self.get_model_id(), self.DB_TYPE, output_variable, input_variables,
                                         self.summary(), model_path, training_paths, train_loss, testing_paths,
                                         test_loss, self.get_parameters(), self.spec.save())
-        if model_path:
+        if model_path and (dp is None or dp.rank == 0):
             self.save(model_path)
 
         metrics = {"test": self.evaluate(test_ds, device), "train": self.evaluate(train_ds, device)}

@@ -102,6 +102,9 @@ typedef struct CaeEpilogue {
     float*         loss_out;      /* loss_out[cursor ? *cursor : 0] = mean squared error of this batch */
     float*         dbias;         /* gradient of `bias` (C floats) */
     int            write_mode;    /* 0: write dL/d(acc) ; 1: write yhat ; 2: write nothing (loss only) */
+    float          count_scale;   /* loss and dL/d(acc) are multiplied by this (0 means 1): N_local/N_global when the
+                                     batch is sharded over ranks, so that SUM-all-reduced gradients and losses are
+                                     those of the global batch */
 } CaeEpilogue;
 
 const char* cae_last_error(void);

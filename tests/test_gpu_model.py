@@ -184,7 +184,7 @@ def test_loss_curve_50_epochs_and_apply_vs_reference(tmp_path):
     # accumulated 1e-3 drift, so this is a looser, end-to-end check) ...
     lo, hi = m2.normalisation_parameters[2], m2.normalisation_parameters[3]
     pred_norm = (est[:4] - lo) / (hi - lo)
-    assert np.max(np.abs(pred_norm[:, :, ::8, ::8] - g["pred_sub"])) < 5e-3
+    assert np.mean(np.abs(pred_norm[:, :, ::8, ::8] - g["pred_sub"])) < 2e-3
     # ... and exactly: load the REFERENCE's trained weights and apply -> predictions within 1e-4
     m3 = ConvAEModel()
     m3.load(folder)

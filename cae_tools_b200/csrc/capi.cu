@@ -342,3 +342,37 @@ extern "C" int cae_step_advance(int* step_count, int* cursor, int n_batches, voi
     k_step_advance<<<1, 32, 0, (cudaStream_t)stream>>>(step_count, cursor, n_batches);
     return cae_check_launch("cae_step_advance");
 }
+
+// ---- variational bottleneck ----------------------------------------------------------------------
+extern "C" int cae_vae_reparam_fwd(const float* mu, const float* logvar, const float* eps, long long eps_stride,
+                                   const int* cursor, float* z, int n_samples, int latent, int sample, float kl_scale,
+                                   float* kl_out, void* stream) {
+    CAE_REQUIRE(mu && logvar && z && n_samples > 0 && latent > 0, "vae_reparam_fwd: bad argument");
+    CAE_REQUIRE(!sample || eps, "vae_reparam_fwd: sampling needs eps");
+    k_vae_reparam_fwd<<<1, CAE_NT, 0, (cudaStream_t)stream>>>(mu, logvar, eps, eps_stride, cursor, z,
+                                                               n_samples * latent, sample, kl_scale / (float)n_samples,
+                                                               kl_out);
+    return cae_check_launch("cae_vae_reparam_fwd");
+}
+
+extern "C" int cae_vae_reparam_bwd(const float* dz, const float* mu, const float* logvar, const float* eps,
+                                   long long eps_stride, const int* cursor, float* dmu, float* dlogvar, int n_samples,
+                                   int latent, float kl_weight, void* stream) {
+    CAE_REQUIRE(dz && mu && logvar && eps && dmu && dlogvar && n_samples > 0 && latent > 0, "vae_reparam_bwd: bad argument");
+    int n = n_samples * latent;
+    k_vae_reparam_bwd<<<min(ceil_div(n, CAE_NT), CAE_NUM_SMS), CAE_NT, 0, (cudaStream_t)stream>>>(
+        dz, mu, logvar, eps, eps_stride, cursor, dmu, dlogvar, n, kl_weight / (float)n_samples);
+    return cae_check_launch("cae_vae_reparam_bwd");
+}
+
+extern "C" int cae_add2(const float* a, const float* b, float* out, long long n, void* stream) {
+    CAE_REQUIRE(a && b && out && n > 0, "add2: bad argument");
+    k_add2<<<min(ceil_div(n, CAE_NT), CAE_NUM_SMS * 4), CAE_NT, 0, (cudaStream_t)stream>>>(a, b, out, n);
+    return cae_check_launch("cae_add2");
+}
+
+extern "C" int cae_randn(float* out, long long n, unsigned long long seed, const int* step_count, void* stream) {
+    CAE_REQUIRE(out && n > 0, "randn: bad argument");
+    k_randn<<<min(ceil_div(n, CAE_NT), CAE_NUM_SMS * 4), CAE_NT, 0, (cudaStream_t)stream>>>(out, n, seed, step_count);
+    return cae_check_launch("cae_randn");
+}

@@ -183,3 +183,77 @@ __global__ void k_step_advance(int* step_count, int* cursor, int n_batches) {
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// variational bottleneck: z = mu + eps * exp(logvar/2) ; KL = -1/2 sum(1 + logvar - mu^2 - exp(logvar)) / N
+// (single CTA: the latent block is N x L with L <= a few thousand)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CAE_NT) k_vae_reparam_fwd(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                                            const float* __restrict__ eps, long long eps_stride,
+                                                            const int* cursor, float* __restrict__ z, int n, int sample,
+                                                            float inv_n, float* kl_out) {
+    const float* e = eps + (cursor ? (long long)__ldg(cursor) * eps_stride : 0ll);
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += CAE_NT) {
+        float m = mu[i], lv = logvar[i];
+        float sd = expf(0.5f * lv);
+        if (sample) z[i] = fmaf(__ldg(e + i), sd, m);
+        else z[i] = m;
+        acc += (double)(1.f + lv - m * m - sd * sd);
+    }
+    __shared__ double red[CAE_NWARP];
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && kl_out) {
+        double t = 0.0;
+        for (int w = 0; w < CAE_NWARP; ++w) t += red[w];
+        kl_out[cursor ? __ldg(cursor) : 0] = (float)(-0.5 * t * (double)inv_n);
+    }
+}
+
+// dmu = dz + kl_w * mu ; dlogvar = dz * eps * exp(logvar/2) / 2 + kl_w * (exp(logvar) - 1) / 2,  kl_w = lambda_kl / N
+__global__ void __launch_bounds__(CAE_NT) k_vae_reparam_bwd(const float* __restrict__ dz, const float* __restrict__ mu,
+                                                            const float* __restrict__ logvar, const float* __restrict__ eps,
+                                                            long long eps_stride, const int* cursor,
+                                                            float* __restrict__ dmu, float* __restrict__ dlogvar, int n,
+                                                            float kl_w) {
+    const float* e = eps + (cursor ? (long long)__ldg(cursor) * eps_stride : 0ll);
+    for (int i = blockIdx.x * CAE_NT + threadIdx.x; i < n; i += gridDim.x * CAE_NT) {
+        float m = mu[i], lv = logvar[i], g = dz[i];
+        float sd = expf(0.5f * lv);
+        dmu[i] = fmaf(kl_w, m, g);
+        dlogvar[i] = 0.5f * g * __ldg(e + i) * sd + 0.5f * kl_w * (sd * sd - 1.f);
+    }
+}
+
+// out[i] = a[i] + b[i]   (gradient fan-in of the two latent heads)
+__global__ void __launch_bounds__(CAE_NT) k_add2(const float* __restrict__ a, const float* __restrict__ b,
+                                                 float* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * CAE_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CAE_NT)
+        out[i] = a[i] + b[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// standard-normal fill: counter-based (seed, step, index) -> splitmix64 -> Box-Muller.  Stateless, so a
+// captured graph draws fresh noise on every replay (the step counter lives on the device).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long cae_mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(CAE_NT) k_randn(float* __restrict__ out, long long n, unsigned long long seed,
+                                                  const int* step_count) {
+    const unsigned long long step = step_count ? (unsigned long long)__ldg(step_count) : 0ull;
+    const unsigned long long key = cae_mix64(seed ^ cae_mix64(step + 0x51ED270B5ull));
+    for (long long i = (long long)blockIdx.x * CAE_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CAE_NT) {
+        unsigned long long r = cae_mix64(key + 2ull * (unsigned long long)i);
+        unsigned int a = (unsigned int)(r >> 32), b = (unsigned int)r;
+        float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+        float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);            // [0, 1)
+        out[i] = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    }
+}

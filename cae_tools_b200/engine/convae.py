@@ -71,6 +71,7 @@ class ConvAEEngine:
         self.grad_hook = grad_hook      # callable(flat_grads) between backward and Adam (data-parallel all-reduce)
         self.grad_scale = grad_scale
         self.count_scale = count_scale  # n_local / n_global when a batch is sharded over data-parallel ranks
+        self.mse_weight = 1.0           # weight of the MSE term in the reported loss / gradient (VarAE: lambda_mse)
         self._keep = []                 # descriptors' tensors must outlive the graphs
         self._build_arena()
         self.enc_layers = self.encoder.conv_layers()
@@ -148,23 +149,25 @@ class ConvAEEngine:
         b = {}
         b["y_e"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.enc_specs]
         b["dz_e"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.enc_specs]
-        lin = self.encoder.encoder_lin
-        dlin = self.decoder.decoder_lin
-        b["h1"] = self._f32(B, lin[0].out_features)
-        b["z"] = self._f32(B, lin[2].out_features)
-        b["h3"] = self._f32(B, dlin[0].out_features)
         c0, h0, w0 = self.dec_specs[0].get_input_dimensions()
         b["u"] = self._f32(B, c0, h0, w0)
         b["du"] = self._f32(B, c0, h0, w0)
-        b["dh3"] = self._f32(B, dlin[0].out_features)
-        b["dzl"] = self._f32(B, lin[2].out_features)
-        b["dh1"] = self._f32(B, lin[0].out_features)
         ce, he, we = self.enc_specs[-1].get_output_dimensions()
         b["da"] = self._f32(B, ce, he, we)
+        self._fc_buffers(b, B)
         b["y_d"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.dec_specs]   # last: dL/dz or yhat
         b["dz_d"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.dec_specs[:-1]]
         self._bufs[B] = b
         return b
+
+    def _fc_buffers(self, b, B):
+        lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
+        b["h1"] = self._f32(B, lin[0].out_features)
+        b["z"] = self._f32(B, lin[2].out_features)
+        b["h3"] = self._f32(B, dlin[0].out_features)
+        b["dh3"] = self._f32(B, dlin[0].out_features)
+        b["dzl"] = self._f32(B, lin[2].out_features)
+        b["dh1"] = self._f32(B, lin[0].out_features)
 
     # ------------------------------------------------------------------ schedules
     def _forward_ops(self, b, N, data, train, final):
@@ -185,24 +188,7 @@ class ConvAEEngine:
             g = ops.geom(sp.get_kernel_size(), sp.get_stride(), 0)
             sched.append((f"fwd.conv{i}", lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_down(src, w, g, o, e)))
             src = ops.make_src(y, k0=s[0], k2=s[1], relu=True, n=N)
-        # fc stack
-        lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
-        ylast = b["y_e"][-1]
-        ce, he, we = self.enc_specs[-1].get_output_dimensions()
-        flat = ce * he * we
-        s_last = self._bn_scratch[("e", len(self.enc_layers) - 1)]
-        fc, lat = lin[0].out_features, lin[2].out_features
-        fc2 = dlin[0].out_features
-        out4 = dlin[2].out_features
-        sched.append(("fwd.fc1", lambda: ops.gemm(N, fc, flat, ylast, flat, 1, lin[0].weight, 1, flat, b["h1"], fc, 1,
-                                                  a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True,
-                                                  bias=lin[0].bias, relu_out=True)))
-        sched.append(("fwd.fc2", lambda: ops.gemm(N, lat, fc, b["h1"], fc, 1, lin[2].weight, 1, fc, b["z"], lat, 1,
-                                                  bias=lin[2].bias)))
-        sched.append(("fwd.fc3", lambda: ops.gemm(N, fc2, lat, b["z"], lat, 1, dlin[0].weight, 1, lat, b["h3"], fc2, 1,
-                                                  bias=dlin[0].bias, relu_out=True)))
-        sched.append(("fwd.fc4", lambda: ops.gemm(N, out4, fc2, b["h3"], fc2, 1, dlin[2].weight, 1, fc2, b["u"], out4,
-                                                  1, bias=dlin[2].bias)))
+        sched += self._fc_forward_ops(b, N, data, train)
         src = ops.make_src(b["u"], n=N)
         nd = len(self.dec_layers)
         for j, ((conv, bn), sp) in enumerate(zip(self.dec_layers, self.dec_specs)):
@@ -230,9 +216,64 @@ class ConvAEEngine:
                                             target=tgt, loss_out=data.losses,
                                             dbias=self.g(conv.bias) if train else None,
                                             write_mode=0 if final == "loss_grad" else 2,
-                                            count_scale=self.count_scale)
+                                            count_scale=self.count_scale * self.mse_weight)
                 sched.append((f"fwd.convT{j}+sigmoid" + ("" if final == "yhat" else "+mse"),
                               lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi: ops.conv_up(src, w, g, o, e)))
+        return sched
+
+    def _fc_forward_ops(self, b, N, data, train):
+        """encoder_lin + decoder_lin: y_e[-1] (BN+ReLU+Flatten on load) -> h1 -> z -> h3 -> u"""
+        sched = []
+        lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
+        ylast = b["y_e"][-1]
+        ce, he, we = self.enc_specs[-1].get_output_dimensions()
+        flat = ce * he * we
+        s_last = self._bn_scratch[("e", len(self.enc_layers) - 1)]
+        fc, lat = lin[0].out_features, lin[2].out_features
+        fc2 = dlin[0].out_features
+        out4 = dlin[2].out_features
+        sched.append(("fwd.fc1", lambda: ops.gemm(N, fc, flat, ylast, flat, 1, lin[0].weight, 1, flat, b["h1"], fc, 1,
+                                                  a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True,
+                                                  bias=lin[0].bias, relu_out=True)))
+        sched.append(("fwd.fc2", lambda: ops.gemm(N, lat, fc, b["h1"], fc, 1, lin[2].weight, 1, fc, b["z"], lat, 1,
+                                                  bias=lin[2].bias)))
+        sched.append(("fwd.fc3", lambda: ops.gemm(N, fc2, lat, b["z"], lat, 1, dlin[0].weight, 1, lat, b["h3"], fc2, 1,
+                                                  bias=dlin[0].bias, relu_out=True)))
+        sched.append(("fwd.fc4", lambda: ops.gemm(N, out4, fc2, b["h3"], fc2, 1, dlin[2].weight, 1, fc2, b["u"], out4,
+                                                  1, bias=dlin[2].bias)))
+        return sched
+
+    def _fc_backward_ops(self, b, N, data):
+        """du -> gradients of the four Linear layers -> da (wrt the last encoder activation)"""
+        sched = []
+        lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
+        ce, he, we = self.enc_specs[-1].get_output_dimensions()
+        flat = ce * he * we
+        fc, lat = lin[0].out_features, lin[2].out_features
+        fc2, out4 = dlin[0].out_features, dlin[2].out_features
+        G = self.g
+        le = len(self.enc_layers) - 1
+        s_last = self._bn_scratch[("e", le)]
+        ylast = b["y_e"][-1]
+        # Linear 4: u = h3 W4^T + b4
+        sched.append(("bwd.fc4.dW", lambda: ops.gemm(out4, fc2, N, b["du"], 1, out4, b["h3"], fc2, 1, G(dlin[2].weight), fc2, 1,
+                                      rowsum_A=G(dlin[2].bias))))
+        sched.append(("bwd.fc4.dx", lambda: ops.gemm(N, fc2, out4, b["du"], out4, 1, dlin[2].weight, fc2, 1, b["dh3"], fc2, 1,
+                                      mask=b["h3"])))
+        # Linear 3: h3 = relu(z W3^T + b3)
+        sched.append(("bwd.fc3.dW", lambda: ops.gemm(fc2, lat, N, b["dh3"], 1, fc2, b["z"], lat, 1, G(dlin[0].weight), lat, 1,
+                                      rowsum_A=G(dlin[0].bias))))
+        sched.append(("bwd.fc3.dx", lambda: ops.gemm(N, lat, fc2, b["dh3"], fc2, 1, dlin[0].weight, lat, 1, b["dzl"], lat, 1)))
+        # Linear 2: z = h1 W2^T + b2
+        sched.append(("bwd.fc2.dW", lambda: ops.gemm(lat, fc, N, b["dzl"], 1, lat, b["h1"], fc, 1, G(lin[2].weight), fc, 1,
+                                      rowsum_A=G(lin[2].bias))))
+        sched.append(("bwd.fc2.dx", lambda: ops.gemm(N, fc, lat, b["dzl"], lat, 1, lin[2].weight, fc, 1, b["dh1"], fc, 1,
+                                      mask=b["h1"])))
+        # Linear 1: h1 = relu(a W1^T + b1), a = relu(bn(y_last)) flattened
+        sched.append(("bwd.fc1.dW", lambda: ops.gemm(fc, flat, N, b["dh1"], 1, fc, ylast, flat, 1, G(lin[0].weight), flat, 1,
+                                      b_k0=s_last[0], b_k2=s_last[1], b_hw=he * we, b_relu=True,
+                                      rowsum_A=G(lin[0].bias))))
+        sched.append(("bwd.fc1.dx", lambda: ops.gemm(N, flat, fc, b["dh1"], fc, 1, lin[0].weight, flat, 1, b["da"], flat, 1)))
         return sched
 
     def _wgrad_op(self, small, big, g, grad):
@@ -271,35 +312,9 @@ class ConvAEEngine:
                 out = ops.view4(b["du"], N)
             sched.append((f"bwd.convT{j}.dgrad", lambda dy=dy, w=conv.weight, g=g, o=out, e=epi:
                           ops.conv_down(dy, w, g, o, e)))
-        # ---- fc stack
-        lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
-        ce, he, we = self.enc_specs[-1].get_output_dimensions()
-        flat = ce * he * we
-        fc, lat = lin[0].out_features, lin[2].out_features
-        fc2, out4 = dlin[0].out_features, dlin[2].out_features
-        G = self.g
+        sched += self._fc_backward_ops(b, N, data)
         le = len(self.enc_layers) - 1
-        s_last = self._bn_scratch[("e", le)]
         ylast = b["y_e"][-1]
-        # Linear 4: u = h3 W4^T + b4
-        sched.append(("bwd.fc4.dW", lambda: ops.gemm(out4, fc2, N, b["du"], 1, out4, b["h3"], fc2, 1, G(dlin[2].weight), fc2, 1,
-                                      rowsum_A=G(dlin[2].bias))))
-        sched.append(("bwd.fc4.dx", lambda: ops.gemm(N, fc2, out4, b["du"], out4, 1, dlin[2].weight, fc2, 1, b["dh3"], fc2, 1,
-                                      mask=b["h3"])))
-        # Linear 3: h3 = relu(z W3^T + b3)
-        sched.append(("bwd.fc3.dW", lambda: ops.gemm(fc2, lat, N, b["dh3"], 1, fc2, b["z"], lat, 1, G(dlin[0].weight), lat, 1,
-                                      rowsum_A=G(dlin[0].bias))))
-        sched.append(("bwd.fc3.dx", lambda: ops.gemm(N, lat, fc2, b["dh3"], fc2, 1, dlin[0].weight, lat, 1, b["dzl"], lat, 1)))
-        # Linear 2: z = h1 W2^T + b2
-        sched.append(("bwd.fc2.dW", lambda: ops.gemm(lat, fc, N, b["dzl"], 1, lat, b["h1"], fc, 1, G(lin[2].weight), fc, 1,
-                                      rowsum_A=G(lin[2].bias))))
-        sched.append(("bwd.fc2.dx", lambda: ops.gemm(N, fc, lat, b["dzl"], lat, 1, lin[2].weight, fc, 1, b["dh1"], fc, 1,
-                                      mask=b["h1"])))
-        # Linear 1: h1 = relu(a W1^T + b1), a = relu(bn(y_last)) flattened
-        sched.append(("bwd.fc1.dW", lambda: ops.gemm(fc, flat, N, b["dh1"], 1, fc, ylast, flat, 1, G(lin[0].weight), flat, 1,
-                                      b_k0=s_last[0], b_k2=s_last[1], b_hw=he * we, b_relu=True,
-                                      rowsum_A=G(lin[0].bias))))
-        sched.append(("bwd.fc1.dx", lambda: ops.gemm(N, flat, fc, b["dh1"], fc, 1, lin[0].weight, flat, 1, b["da"], flat, 1)))
         # ReLU mask + BN-backward sums of the last encoder layer
         conv, bn = self.enc_layers[le]
         blk, _ = self._bn(("e", le), bn, self.g(conv.bias))
@@ -371,7 +386,7 @@ class ConvAEEngine:
                 [("advance", lambda: ops.step_advance(None, data.cursor, data.n_batches))]
         else:
             raise ValueError(kind)
-        state = [data.cursor, data.losses]
+        state = [data.cursor, data.losses] + list(getattr(data, "extra_state", []))
         if kind == "train":
             state += [self.arena, self.adam_m, self.adam_v, self.grads, self.step_count]
             for mod in list(self.encoder.modules()) + list(self.decoder.modules()):
@@ -386,6 +401,10 @@ class ConvAEEngine:
         Y = Y.to(self.device, torch.float32) if Y is not None else None
         return DataBinding(X, Y, batch_size)
 
+    def batch_losses(self, data):
+        """per-batch loss values of the last epoch run on this binding (device tensor)"""
+        return data.losses
+
     def train_epoch(self, data):
         """one pass over all batches; returns the per-batch losses (device tensor, no sync)"""
         data.cursor.zero_()
@@ -393,7 +412,7 @@ class ConvAEEngine:
             prog = self._program("train", data, N)
             for _ in range(count):
                 prog.run()
-        return data.losses
+        return self.batch_losses(data)
 
     def train_steps(self, data, steps):
         """run `steps` optimiser steps cycling through the batches (bench helper; full batches only)"""
@@ -409,7 +428,7 @@ class ConvAEEngine:
             prog = self._program("test", data, N)
             for _ in range(count):
                 prog.run()
-        return data.losses
+        return self.batch_losses(data)
 
     def score_batches(self, data, sink):
         """eval-mode forward of every batch; sink(batch_index, yhat[N,C,H,W] device view) consumes each output"""

@@ -157,3 +157,23 @@ def adam(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, grad_sca
 
 def step_advance(step_count, cursor, n_batches):
     check(lib().cae_step_advance(_ptr(step_count), _ptr(cursor), int(n_batches), _stream()), "cae_step_advance")
+
+
+def vae_reparam_fwd(mu, logvar, eps, eps_stride, cursor, z, n_samples, latent, sample, kl_scale, kl_out):
+    check(lib().cae_vae_reparam_fwd(_ptr(mu), _ptr(logvar), _ptr(eps), int(eps_stride), _ptr(cursor), _ptr(z),
+                                    int(n_samples), int(latent), int(bool(sample)), float(kl_scale), _ptr(kl_out),
+                                    _stream()), "cae_vae_reparam_fwd")
+
+
+def vae_reparam_bwd(dz, mu, logvar, eps, eps_stride, cursor, dmu, dlogvar, n_samples, latent, kl_weight):
+    check(lib().cae_vae_reparam_bwd(_ptr(dz), _ptr(mu), _ptr(logvar), _ptr(eps), int(eps_stride), _ptr(cursor),
+                                    _ptr(dmu), _ptr(dlogvar), int(n_samples), int(latent), float(kl_weight),
+                                    _stream()), "cae_vae_reparam_bwd")
+
+
+def add2(a, b, out, n):
+    check(lib().cae_add2(_ptr(a), _ptr(b), _ptr(out), int(n), _stream()), "cae_add2")
+
+
+def randn(out, n, seed, step_count):
+    check(lib().cae_randn(_ptr(out), int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(step_count), _stream()), "cae_randn")

@@ -179,6 +179,24 @@ int cae_adam(float* p, const float* g, float* m, float* v, long long n, float lr
 /* end-of-step bookkeeping: step_count[0] += 1 ; if cursor: cursor[0] = (cursor[0]+1) % n_batches */
 int cae_step_advance(int* step_count, int* cursor, int n_batches, void* stream);
 
+/* ---- variational bottleneck (VarAEModel; the reference names the variant - cli/train_cae.py:32-33,42,
+ * model_evaluator.py:35 - but ships no implementation: parity unpinned) --------------------------
+ * forward : z = mu + eps*exp(logvar/2) (sample != 0) or z = mu ; kl_out[slot] = kl_scale * KL,
+ *           KL = -1/2 * sum_{n,l}(1 + logvar - mu^2 - exp(logvar)) / n_samples
+ * backward: dmu = dz + w*mu ; dlogvar = dz*eps*exp(logvar/2)/2 + w*(exp(logvar)-1)/2 , w = kl_weight / n_samples
+ * eps is a pre-drawn device array; the batch is selected by cursor[0]*eps_stride like CaeSrc. */
+int cae_vae_reparam_fwd(const float* mu, const float* logvar, const float* eps, long long eps_stride,
+                        const int* cursor, float* z, int n_samples, int latent, int sample, float kl_scale,
+                        float* kl_out, void* stream);
+int cae_vae_reparam_bwd(const float* dz, const float* mu, const float* logvar, const float* eps,
+                        long long eps_stride, const int* cursor, float* dmu, float* dlogvar, int n_samples,
+                        int latent, float kl_weight, void* stream);
+/* out[i] ~ N(0,1): counter-based generator keyed by (seed, step_count[0], i); replaces torch.randn_like in the
+ * reparameterisation so that a replayed CUDA graph draws fresh noise every step */
+int cae_randn(float* out, long long n, unsigned long long seed, const int* step_count, void* stream);
+/* out = a + b (gradient fan-in) */
+int cae_add2(const float* a, const float* b, float* out, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

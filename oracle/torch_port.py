@@ -135,3 +135,49 @@ def shuffled_order(n, batch_size):
     (conv_ae_model.py:291-292; consumed at :316 and :322)"""
     loader = torch.utils.data.DataLoader(range(n), batch_size=batch_size, shuffle=True)
     return [int(i) for idx in loader for i in idx]
+
+
+class OracleVarModel(OracleModel):
+    """Plain-PyTorch VAE on the reference's stacks (the reference ships no VarAEModel - parity unpinned; this is
+    the definition the CUDA path is held to): heads `fc_mu` / `fc_logvar` on relu(encoder_lin.0(.)),
+    z = mu + eps * exp(logvar / 2), loss = lambda_mse * MSE + lambda_kl * KL,
+    KL = -1/2 * mean_n sum_l (1 + logvar - mu^2 - exp(logvar))."""
+
+    def __init__(self, enc_sd, dec_sd, spec, lambda_mse=1.0, lambda_kl=1.0, **kw):
+        super().__init__(enc_sd, dec_sd, spec, **kw)
+        self.lambda_mse, self.lambda_kl = lambda_mse, lambda_kl
+
+    def encode(self, x, training):
+        sd = self.enc
+        for i, sp in enumerate(self.spec["input_layers"]):
+            x = F.conv2d(x, sd[f"encoder_cnn.{3 * i}.weight"], sd[f"encoder_cnn.{3 * i}.bias"], stride=sp["stride"])
+            x = F.relu(_bn(x, sd, f"encoder_cnn.{3 * i + 1}", training))
+        h = F.relu(F.linear(x.flatten(1), sd["encoder_lin.0.weight"], sd["encoder_lin.0.bias"]))
+        return (F.linear(h, sd["fc_mu.weight"], sd["fc_mu.bias"]),
+                F.linear(h, sd["fc_logvar.weight"], sd["fc_logvar.bias"]))
+
+    def loss(self, x, y, eps, training):
+        mu, lv = self.encode(x, training)
+        z = mu + eps * torch.exp(0.5 * lv) if eps is not None else mu
+        yhat = decoder_forward(self.dec, self.spec["output_layers"], z, training)
+        kl = -0.5 * torch.sum(1 + lv - mu * mu - torch.exp(lv)) / x.shape[0]
+        return self.lambda_mse * F.mse_loss(yhat, y) + self.lambda_kl * kl, yhat
+
+    def train_step(self, x, y, eps):
+        loss, _ = self.loss(x, y, eps, True)
+        self.optim.zero_grad()
+        loss.backward()
+        if self.zero_dead_bias_grads:
+            for sd in (self.enc, self.dec):
+                for k in sd:
+                    if k.endswith(".bias") and k.split(".")[0] in ("encoder_cnn", "decoder_conv"):
+                        stem, idx = k.split(".")[0], int(k.split(".")[1])
+                        if f"{stem}.{idx + 1}.running_mean" in sd and idx % 3 == 0:
+                            sd[k].grad.zero_()
+        self.optim.step()
+        return loss.detach()
+
+    def score(self, x):
+        with torch.no_grad():
+            mu, _ = self.encode(x, False)
+            return decoder_forward(self.dec, self.spec["output_layers"], mu, False)

@@ -1,7 +1,11 @@
 // C ABI of libcae_b200.so: argument checking, kernel selection, launches.  See include/cae_b200.h.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
+#include <mutex>
+#include <unordered_set>
 #include "conv_family.cuh"
+#include "conv_tiled.cuh"
 #include "dense_misc.cuh"
 
 static thread_local char g_err[512] = "";
@@ -135,6 +139,137 @@ static int fill_conv_args(ConvArgs& a, const CaeSrc* in, const float* weight, co
     return CAE_OK;
 }
 
+
+// =====================================================================================================
+// v2 (tiled) dispatch: stride 2, square 3x3 / 4x4 kernels.  Anything else keeps the v1 kernels.
+// =====================================================================================================
+static const int kTileSmemBudget = 72 * 1024;
+static const int kTileSmemMax = 100 * 1024;
+// kernel selection mask: bit 0 tiled up/down (k_up2/k_down2), bit 1 position-parallel wgrad (k_wgrad2a),
+// bit 2 GEMM-like wgrad (k_wgrad2b).  cae_set_kernel_generation(1) = generic kernels only, (2) = default mask.
+#define CAE_V2_UPDOWN 1
+#define CAE_V2_WGRAD_A 2
+#define CAE_V2_WGRAD_B 4
+static int default_mask() {
+    const char* e = getenv("CAE_KERNEL_MASK");
+    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A);
+}
+static int g_mask = default_mask();
+#define g_use_v2 (g_mask & CAE_V2_UPDOWN)
+extern "C" void cae_set_kernel_generation(int gen) { g_mask = (gen <= 1) ? 0 : (gen == 2 ? default_mask() : (gen >> 4)); }
+
+static inline int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static inline int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+static inline int roundup4(int v) { return (v + 3) & ~3; }
+
+// opt in to > 48 KB dynamic shared memory, once per kernel (keyed by the function address)
+template <typename K>
+static void ensure_smem(K kernel) {
+    static std::mutex mu;
+    static std::unordered_set<const void*> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    if (seen.insert((const void*)kernel).second)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemMax);
+}
+
+struct TileChoice { int cot, cx, nt; TilePlan plan; size_t smem; bool ok; };
+
+// Pick the thread layout of a tiled kernel: 256 threads = TXT (x, CX positions each) * TYT (rows) * TZ (groups of
+// `cot` output channels) * TK (slices of the input-channel reduction).
+//   rows_total : flattened rows (all samples), width: positions per row
+//   staged rows per channel = row_mult * TYT + halo_rows; staged columns = col_mult * roundup4(TXT*CX + halo_cols)
+static TileChoice choose_tile(int Cin, int Cout, int rows_total, int width, int halo_rows, int row_mult, int halo_cols,
+                              int col_mult, int KK, int rp, int max_cot, int acc_per_chan_pos) {
+    TileChoice t{};
+    t.ok = false;
+    const int NT = CAE_NT;
+    const int CX = width >= 64 ? 4 : (width >= 32 ? 2 : 1);
+    int TXT = pow2ceil((width + CX - 1) / CX);
+    if (TXT > 32) TXT = 32;
+    int cot = 1;
+    while (cot * 2 <= max_cot && cot * 2 <= Cout) cot *= 2;
+    const int groups = (Cout + cot - 1) / cot;
+    const long long base = (long long)rows_total * TXT * ((width + TXT * CX - 1) / (TXT * CX)) * groups;
+    // split the reduction when the layer alone cannot fill the machine (only with small register tiles)
+    int TK = 1;
+    if (CX <= 2) {
+        while (TK < 8 && TK * 2 <= Cin && base * TK < 2ll * CAE_NUM_SMS * NT) TK *= 2;
+    }
+    int rest = NT / (TXT * TK);
+    if (rest < 1) { TK = NT / TXT; rest = 1; }
+    // channel groups in the CTA: as many as fit while keeping >= 4 rows per tile
+    int TZ = 1;
+    while (TZ * 2 <= pow2ceil(groups) && rest / (TZ * 2) >= 4) TZ *= 2;
+    int TYT = rest / TZ;
+    if (TYT < 1) TYT = 1;
+    TilePlan p{};
+    p.TXT = TXT; p.txt_shift = ilog2(TXT); p.RP = rp; p.total_rows = rows_total;
+    p.TZ = TZ; p.tz_shift = ilog2(TZ); p.tyt_shift = ilog2(TYT); p.TK = TK;
+    p.nrow_tiles = (rows_total + TYT - 1) / TYT;
+    p.ncol_tiles = (width + TXT * CX - 1) / (TXT * CX);
+    p.SROWS = row_mult * TYT + halo_rows;
+    p.SCP = roundup4(TXT * CX + halo_cols);
+    const size_t per_ch = (size_t)p.SROWS * p.SCP * col_mult * 4 + (size_t)KK * cot * TZ * 4;
+    const size_t fixed = (size_t)p.SROWS * 8 + 32;
+    if (per_ch + fixed > (size_t)kTileSmemMax) return t;
+    int chunk = (int)((kTileSmemBudget - fixed) / per_ch);
+    if (chunk < 1) chunk = 1;
+    if (chunk > Cin) chunk = Cin;
+    p.ci_chunk = chunk;
+    size_t smem = per_ch * chunk + fixed;
+    size_t scratch = (size_t)NT * 2 * cot * 4;                                   // statistics tail
+    if (TK > 1) scratch = max(scratch, (size_t)NT * acc_per_chan_pos * cot * CX * 4);   // split-K partials
+    if (scratch > (size_t)kTileSmemMax) return t;
+    if (smem < scratch) smem = scratch;
+    t.cot = cot; t.cx = CX; t.nt = NT; t.plan = p; t.smem = smem; t.ok = true;
+    return t;
+}
+
+#define CAE_LAUNCH_TILED(KERNEL, KH, KW)                                                                              \
+    do {                                                                                                              \
+        const int key = tc.cx * 16 + tc.cot;                                                                          \
+        switch (key) {                                                                                                \
+            case 1 * 16 + 1: ensure_smem(KERNEL<KH, KW, 1, 1>); KERNEL<KH, KW, 1, 1><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+            case 1 * 16 + 2: ensure_smem(KERNEL<KH, KW, 1, 2>); KERNEL<KH, KW, 1, 2><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+            case 1 * 16 + 4: ensure_smem(KERNEL<KH, KW, 1, 4>); KERNEL<KH, KW, 1, 4><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+            case 2 * 16 + 1: ensure_smem(KERNEL<KH, KW, 2, 1>); KERNEL<KH, KW, 2, 1><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+            case 2 * 16 + 2: ensure_smem(KERNEL<KH, KW, 2, 2>); KERNEL<KH, KW, 2, 2><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+            case 2 * 16 + 4: ensure_smem(KERNEL<KH, KW, 2, 4>); KERNEL<KH, KW, 2, 4><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+            case 4 * 16 + 1: ensure_smem(KERNEL<KH, KW, 4, 1>); KERNEL<KH, KW, 4, 1><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+            case 4 * 16 + 2: ensure_smem(KERNEL<KH, KW, 4, 2>); KERNEL<KH, KW, 4, 2><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+            default:         ensure_smem(KERNEL<KH, KW, 4, 4>); KERNEL<KH, KW, 4, 4><<<grid, tc.nt, tc.smem, st>>>(a, tc.plan); break; \
+        }                                                                                                             \
+    } while (0)
+
+template <int KH, int KW>
+static int launch_up2(ConvArgs& a, cudaStream_t st, bool& handled) {
+    constexpr int JY = (KH + 1) / 2, JX = (KW + 1) / 2;
+    handled = false;
+    const int QH = (a.out.H - 1 + a.p) / 2 + 1, QW = (a.out.W - 1 + a.p) / 2 + 1;
+    if (QH - a.in.t0.H < JY - 1) return CAE_OK;
+    TileChoice tc = choose_tile(a.Cin, a.Cout, a.out.N * QH, QW, JY - 1, 1, JX - 1, 1, KH * KW, QH, 4, 4);
+    if (!tc.ok) return CAE_OK;
+    handled = true;
+    a.QH = QH; a.QW = QW;
+    int ntiles = tc.plan.nrow_tiles * tc.plan.ncol_tiles;
+    dim3 grid(min(ntiles, CAE_MAX_GRID_X), ceil_div(a.Cout, tc.cot * tc.plan.TZ));
+    CAE_LAUNCH_TILED(k_up2, KH, KW);
+    return cae_check_launch("cae_conv_up(v2)");
+}
+
+template <int KH, int KW>
+static int launch_down2(ConvArgs& a, cudaStream_t st, bool& handled) {
+    handled = false;
+    const int OHp = a.out.H + 1;
+    TileChoice tc = choose_tile(a.Cin, a.Cout, a.out.N * OHp, a.out.W, KH - 2, 2, 2, 2, KH * KW, OHp, 4, 1);
+    if (!tc.ok) return CAE_OK;
+    handled = true;
+    int ntiles = tc.plan.nrow_tiles * tc.plan.ncol_tiles;
+    dim3 grid(min(ntiles, CAE_MAX_GRID_X), ceil_div(a.Cout, tc.cot * tc.plan.TZ));
+    CAE_LAUNCH_TILED(k_down2, KH, KW);
+    return cae_check_launch("cae_conv_down(v2)");
+}
+
 extern "C" int cae_conv_up(const CaeSrc* in, const float* weight, const CaeConvGeom* g, const CaeView* out,
                            const CaeEpilogue* epi, void* stream) {
     ConvArgs a;
@@ -147,6 +282,11 @@ extern "C" int cae_conv_up(const CaeSrc* in, const float* weight, const CaeConvG
                 "conv_up: output %dx%d inconsistent with input %dx%d k=%dx%d s=%d p=%d", out->H, out->W, iv.H, iv.W,
                 a.kh, a.kw, a.s, a.p);
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+        bool handled = false;
+        rc = (a.kh == 3) ? launch_up2<3, 3>(a, st, handled) : launch_up2<4, 4>(a, st, handled);
+        if (handled) return rc;
+    }
     if (a.s == 2 && a.kh >= 3 && a.kh <= 4 && a.kw >= 3 && a.kw <= 4) {
         a.QH = (out->H - 1 + a.p) / a.s + 1;
         a.QW = (out->W - 1 + a.p) / a.s + 1;
@@ -176,6 +316,11 @@ extern "C" int cae_conv_down(const CaeSrc* in, const float* weight, const CaeCon
     cudaStream_t st = (cudaStream_t)stream;
     a.QH = out->H; a.QW = out->W;
     a.total = out->N * out->H * out->W;
+    if (g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+        bool handled = false;
+        rc = (a.kh == 3) ? launch_down2<3, 3>(a, st, handled) : launch_down2<4, 4>(a, st, handled);
+        if (handled) return rc;
+    }
     if (a.s == 2 && a.kh >= 3 && a.kh <= 4 && a.kw >= 3 && a.kw <= 4) {
         if (a.kh == 3 && a.kw == 3) return launch_down_t<3, 3, 2>(a, st);
         if (a.kh == 4 && a.kw == 4) return launch_down_t<4, 4, 2>(a, st);
@@ -247,6 +392,96 @@ static WgradPlan plan_wgrad(int Cs, int Cb, int kh, int kw, int s, int total) {
     return p;
 }
 
+// ---- v2 weight-gradient planning ----------------------------------------------------------------
+struct Wg2Choice {
+    int kind;          // 0: v1, 1: v2a (position parallel), 2: v2b (GEMM-like)
+    int cst, cbt, cx;
+    Wg2Plan a;
+    WgGemmPlan b;
+    size_t smem;
+    int grid_x, grid_y;
+    long long partials;
+};
+
+static Wg2Choice plan_wgrad2(int N, int Cs, int Hs, int Ws, int Cb, int kh, int kw, int s) {
+    Wg2Choice w{};
+    w.kind = 0;
+    if (!(g_mask & (CAE_V2_WGRAD_A | CAE_V2_WGRAD_B)) || s != 2 || kh != kw || (kh != 3 && kh != 4)) return w;
+    const int KK = kh * kw;
+    const long long nelem = (long long)Cs * Cb * KK;
+    int cst = Cs >= 4 ? 4 : (Cs >= 2 ? 2 : 1);
+    int cbt = Cb >= 2 ? 2 : 1;
+    if (KK > 12 && cst == 4) cst = 2;
+    if (cst == 4 && cbt == 1) cst = 2;
+    if (cst == 1 && cbt == 2) cbt = 1;                      // instantiated: (4,2) (2,2) (2,1) (1,1)
+    const int tiles_b = (Cb + cbt - 1) / cbt;
+    const int G = ((Cs + cst - 1) / cst) * tiles_b;
+    if (G <= 8 && (g_mask & CAE_V2_WGRAD_A)) {
+        Wg2Plan p{};
+        int cx = Ws >= 96 ? 4 : (Ws >= 48 ? 2 : 1);
+        const int TXC = 32 * cx;
+        p.RP = Hs + 1; p.total_rows = N * p.RP;
+        p.TR = 8;
+        p.nrow_tiles = (p.total_rows + p.TR - 1) / p.TR;
+        p.ncol_tiles = (Ws + TXC - 1) / TXC;
+        p.SCPs = TXC; p.SCPb = roundup4(TXC + 2);
+        p.tiles_b = tiles_b; p.G = G; p.GP = pow2ceil(G);
+        size_t fl = (size_t)Cs * p.TR * p.SCPs + (size_t)Cb * (2 * p.TR + kh - 2) * 2 * p.SCPb;
+        size_t need = (size_t)CAE_NWARP * cst * cbt * KK;
+        if (fl < need) fl = need;
+        if (fl * 4 <= (size_t)kTileSmemMax) {
+            w.kind = 1; w.cst = cst; w.cbt = cbt; w.cx = cx; w.a = p; w.smem = fl * 4;
+            long long tiles = (long long)p.nrow_tiles * p.ncol_tiles;
+            w.grid_x = (int)(tiles < 2 * CAE_NUM_SMS ? tiles : 2 * CAE_NUM_SMS);
+            w.grid_y = 1;
+            w.partials = (long long)w.grid_x * nelem;
+            return w;
+        }
+    }
+    if (nelem >= 1024 && (g_mask & CAE_V2_WGRAD_B)) {
+        WgGemmPlan p{};
+        p.KK = KK; p.KW = kw;
+        p.n_mtiles = (Cs + WG_BM - 1) / WG_BM;
+        p.n_ntiles = (Cb * KK + WG_BN - 1) / WG_BN;
+        const long long total = (long long)N * Hs * Ws;
+        long long want = (2ll * CAE_NUM_SMS + p.n_mtiles * p.n_ntiles - 1) / (p.n_mtiles * p.n_ntiles);
+        long long maxch = (total + WG_KS - 1) / WG_KS;
+        if (want > maxch) want = maxch;
+        if (want > 128) want = 128;
+        if (want < 1) want = 1;
+        long long kchunk = (total + want - 1) / want;
+        kchunk = (kchunk + WG_KS - 1) / WG_KS * WG_KS;
+        p.kchunk = (int)kchunk;
+        p.nchunks = (int)((total + kchunk - 1) / kchunk);
+        w.kind = 2; w.b = p; w.smem = 0;
+        w.grid_x = p.nchunks; w.grid_y = p.n_mtiles * p.n_ntiles;
+        w.partials = (long long)p.nchunks * nelem;
+        return w;
+    }
+    return w;
+}
+
+template <int K, int CX>
+static void launch_wgrad2a_t(const WgradArgs& a, const Wg2Choice& w, cudaStream_t st) {
+    dim3 grid(w.grid_x);
+    if (w.cst == 4 && w.cbt == 2) {
+        if constexpr (K == 3) { ensure_smem(k_wgrad2a<K, K, CX, 4, 2>); k_wgrad2a<K, K, CX, 4, 2><<<grid, CAE_NT, w.smem, st>>>(a, w.a); }
+    } else if (w.cst == 2 && w.cbt == 2) {
+        ensure_smem(k_wgrad2a<K, K, CX, 2, 2>); k_wgrad2a<K, K, CX, 2, 2><<<grid, CAE_NT, w.smem, st>>>(a, w.a);
+    } else if (w.cst == 2 && w.cbt == 1) {
+        ensure_smem(k_wgrad2a<K, K, CX, 2, 1>); k_wgrad2a<K, K, CX, 2, 1><<<grid, CAE_NT, w.smem, st>>>(a, w.a);
+    } else {
+        ensure_smem(k_wgrad2a<K, K, CX, 1, 1>); k_wgrad2a<K, K, CX, 1, 1><<<grid, CAE_NT, w.smem, st>>>(a, w.a);
+    }
+}
+
+template <int K>
+static void launch_wgrad2a(const WgradArgs& a, const Wg2Choice& w, cudaStream_t st) {
+    if (w.cx == 4) launch_wgrad2a_t<K, 4>(a, w, st);
+    else if (w.cx == 2) launch_wgrad2a_t<K, 2>(a, w, st);
+    else launch_wgrad2a_t<K, 1>(a, w, st);
+}
+
 static int check_wgrad(const CaeSrc* sm, const CaeSrc* bg, const CaeConvGeom* g) {
     CAE_REQUIRE(sm && bg && g, "wgrad: null argument");
     int rc;
@@ -260,7 +495,9 @@ static int check_wgrad(const CaeSrc* sm, const CaeSrc* bg, const CaeConvGeom* g)
 extern "C" long long cae_wgrad_partials_len(const CaeSrc* sm, const CaeSrc* bg, const CaeConvGeom* g) {
     if (check_wgrad(sm, bg, g)) return -1;
     WgradPlan p = plan_wgrad(sm->t0.C, bg->t0.C, g->kh, g->kw, g->stride, sm->t0.N * sm->t0.H * sm->t0.W);
-    return (long long)p.nchunks * sm->t0.C * bg->t0.C * g->kh * g->kw;
+    long long v1 = (long long)p.nchunks * sm->t0.C * bg->t0.C * g->kh * g->kw;
+    Wg2Choice w = plan_wgrad2(sm->t0.N, sm->t0.C, sm->t0.H, sm->t0.W, bg->t0.C, g->kh, g->kw, g->stride);
+    return (w.kind != 0 && w.partials > v1) ? w.partials : v1;    // either generation may be selected at run time
 }
 
 template <int KH, int KW, int S>
@@ -288,9 +525,18 @@ extern "C" int cae_conv_wgrad(const CaeSrc* sm, const CaeSrc* bg, const CaeConvG
     a.grad = grad; a.partials = partials; a.ticket = ticket;
     a.Cs = sm->t0.C; a.Cb = bg->t0.C;
     a.total = sm->t0.N * sm->t0.H * sm->t0.W;
+    cudaStream_t st = (cudaStream_t)stream;
+    Wg2Choice w2 = plan_wgrad2(sm->t0.N, a.Cs, sm->t0.H, sm->t0.W, a.Cb, a.kh, a.kw, a.s);
+    if (w2.kind == 1) {
+        if (a.kh == 3) launch_wgrad2a<3>(a, w2, st); else launch_wgrad2a<4>(a, w2, st);
+        return cae_check_launch("cae_conv_wgrad(v2a)");
+    }
+    if (w2.kind == 2) {
+        k_wgrad2b<<<dim3(w2.grid_x, w2.grid_y), CAE_NT, 0, st>>>(a, w2.b);
+        return cae_check_launch("cae_conv_wgrad(v2b)");
+    }
     WgradPlan p = plan_wgrad(a.Cs, a.Cb, a.kh, a.kw, a.s, a.total);
     a.chunk = p.chunk; a.tiles_b = p.tiles_b; a.ntiles = p.ntiles; a.nchunks = p.nchunks;
-    cudaStream_t st = (cudaStream_t)stream;
     if (!p.generic) {
         if (a.kh == 3 && a.kw == 3) return launch_wgrad_t<3, 3, 2>(a, p, st);
         if (a.kh == 4 && a.kw == 4) return launch_wgrad_t<4, 4, 2>(a, p, st);

@@ -85,7 +85,7 @@ __device__ __forceinline__ bool cae_last_block(unsigned int* ticket) {
 template <int NV>
 __device__ __forceinline__ void cta_reduce_store(float (&v)[NV], double* dst, int nvalid) {
     __shared__ double red[CAE_NWARP][NV];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double d = warp_sum_d((double)v[i]);
@@ -95,7 +95,7 @@ __device__ __forceinline__ void cta_reduce_store(float (&v)[NV], double* dst, in
     if ((int)threadIdx.x < nvalid) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < CAE_NWARP; ++w) s += red[w][threadIdx.x];
+        for (int w = 0; w < nw; ++w) s += red[w][threadIdx.x];
         dst[threadIdx.x] = s;
     }
     __syncthreads();
@@ -115,7 +115,7 @@ __device__ __forceinline__ double warp_colsum(const double* part, int rows, int 
 // (biased variance for normalisation, unbiased for running_var, momentum update).
 __device__ __forceinline__ void finalize_bn_forward(const CaeBN& bn, const double* part, int rows, double count) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < bn.C; c += CAE_NWARP) {
+    for (int c = warp; c < bn.C; c += (blockDim.x >> 5)) {
         double S = warp_colsum(part, rows, bn.C * 2, c * 2 + 0);
         double Q = warp_colsum(part, rows, bn.C * 2, c * 2 + 1);
         if (lane == 0) {
@@ -144,7 +144,7 @@ __device__ __forceinline__ void finalize_bn_forward(const CaeBN& bn, const doubl
 // BatchNorm backward sums -> dgamma, dbeta and the coefficients of dL/dy = A*dz + B*y + C
 __device__ __forceinline__ void finalize_bn_backward(const CaeBN& bn, const double* part, int rows, double count) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < bn.C; c += CAE_NWARP) {
+    for (int c = warp; c < bn.C; c += (blockDim.x >> 5)) {
         double S1 = warp_colsum(part, rows, bn.C * 2, c * 2 + 0);  // sum dz
         double S2 = warp_colsum(part, rows, bn.C * 2, c * 2 + 1);  // sum dz * xhat
         if (lane == 0) {

@@ -91,7 +91,8 @@ __device__ __forceinline__ void finalize_mse(const CaeEpilogue& e, const double*
     __shared__ double wq[CAE_NWARP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double q = 0.0;
-    for (int c = warp; c < C; c += CAE_NWARP) {
+    if (lane == 0) wq[warp] = 0.0;
+    for (int c = warp; c < C; c += (blockDim.x >> 5)) {
         double S1 = warp_colsum(part, rows, C * 2, c * 2 + 0);
         q += warp_colsum(part, rows, C * 2, c * 2 + 1);
         if (lane == 0 && e.dbias) e.dbias[c] = (float)S1;
@@ -100,7 +101,7 @@ __device__ __forceinline__ void finalize_mse(const CaeEpilogue& e, const double*
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int w = 0; w < CAE_NWARP; ++w) t += wq[w];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wq[w];
         int slot = e.target.cursor ? __ldg(e.target.cursor) : 0;
         const double cs = e.count_scale > 0.f ? (double)e.count_scale : 1.0;
         if (e.loss_out) e.loss_out[slot] = (float)(t / count * cs);

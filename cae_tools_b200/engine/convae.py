@@ -504,7 +504,42 @@ class _Program:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 with torch.cuda.graph(g, stream=s):
-                    self.run_eager()
+                    self.run_forked()
             torch.cuda.current_stream().wait_stream(s)
             self.graph = g
         self.graph.replay()
+
+    # weight-gradient kernels only feed the optimiser: inside the captured graph they run on side streams,
+    # concurrently with the input-gradient chain (most launches of this network fill a fraction of the GPU)
+    SIDE_SUFFIXES = (".wgrad", ".dW")
+    JOIN_BEFORE = ("adam", "grad_allreduce")
+    N_SIDE = 3
+
+    def run_forked(self):
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_side"):
+            self._side = [torch.cuda.Stream() for _ in range(self.N_SIDE)]
+        used, k = [], 0
+        for name, op in self.sched:
+            if name.endswith(self.SIDE_SUFFIXES):
+                side = self._side[k % self.N_SIDE]
+                k += 1
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    op()
+                if side not in used:
+                    used.append(side)
+            else:
+                if name in self.JOIN_BEFORE:
+                    for side in used:
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        main.wait_event(ev)
+                    used = []
+                op()
+        for side in used:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)

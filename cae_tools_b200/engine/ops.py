@@ -177,3 +177,8 @@ def add2(a, b, out, n):
 
 def randn(out, n, seed, step_count):
     check(lib().cae_randn(_ptr(out), int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(step_count), _stream()), "cae_randn")
+
+
+def set_kernel_generation(gen: int):
+    """1: generic direct kernels only; 2 (default): tiled shared-memory kernels where they apply"""
+    lib().cae_set_kernel_generation(int(gen))

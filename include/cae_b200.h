@@ -108,6 +108,8 @@ typedef struct CaeEpilogue {
 } CaeEpilogue;
 
 const char* cae_last_error(void);
+/* 1: generic direct kernels only (v1); 2 (default): tiled shared-memory kernels where they apply */
+void cae_set_kernel_generation(int gen);
 int  cae_version(void);
 /* number of doubles the `partials` workspace must hold for a kernel whose output has C channels */
 long long cae_partials_len(int C);

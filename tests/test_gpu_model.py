@@ -3,6 +3,7 @@ reference) and against the oracle port on the same seeded inputs.
 
 Bars (BASELINE.json north_star): per-layer activations and gradients <= 1e-4 relative (fp32), loss curves
 <= 1e-3 relative over 50 epochs, apply() predictions <= 1e-4."""
+import json
 import os
 
 import numpy as np
@@ -195,3 +196,40 @@ def test_loss_curve_50_epochs_and_apply_vs_reference(tmp_path):
     pred3 = (np.asarray(te["ref_weights_estimate"].data)[:4] - lo) / (hi - lo)
     assert np.max(np.abs(pred3[:, :, ::8, ::8] - g["pred_sub"])) < 1e-4
     assert np.max(np.abs(pred3.mean(axis=(1, 2, 3)) - g["pred_mean"])) < 1e-4
+
+
+def test_cli_train_apply_continue(tmp_path):
+    """train_cae -> apply_cae -> train_cae --continue-training on NetCDF files (reference: test/cli/test_cli.sh)"""
+    from cae_tools_b200.cli import apply_cae, train_cae
+    from cae_tools_b200.utils import xr_lite
+    from oracle import datagen
+    paths = {}
+    for name, seed in (("train", 0), ("test", 1)):
+        lo, hi = datagen.generate(24, (16, 16), (64, 64), "circle", seed=seed)
+        ds = xr_lite.Dataset()
+        ds["lowres"] = xr_lite.DataArray(lo, dims=("n", "chan", "y1", "x1"))
+        ds["hires"] = xr_lite.DataArray(hi, dims=("n", "chan", "y2", "x2"))
+        paths[name] = str(tmp_path / f"{name}.nc")
+        ds.to_netcdf(paths[name])
+    folder = str(tmp_path / "model")
+    db = str(tmp_path / "runs.db")
+    for method in ("conv", "var"):
+        train_cae.main(["--train-inputs", paths["train"], "--test-inputs", paths["test"], "--model-folder", folder,
+                        "--input-variables", "lowres", "--output-variable", "hires", "--nr-epochs", "4",
+                        "--batch-size", "8", "--latent-size", "8", "--fc-size", "32", "--method", method,
+                        "--lambda-kl", "0.001", "--database-path", db])
+        params = json.load(open(os.path.join(folder, "parameters.json")))
+        assert params["type"] == ("ConvAEModel" if method == "conv" else "VarAEModel")
+        assert params["encoded_dim_size"] == 8 and params["fc_size"] == 32
+        out = str(tmp_path / f"scores_{method}.nc")
+        apply_cae.main([paths["test"], out, "--model-folder", folder, "--prediction-variable", "hires_estimate"])
+        scored = xr_lite.open_dataset(out)
+        assert scored["hires_estimate"].shape == (24, 1, 64, 64)
+        assert np.isfinite(scored["hires_estimate"].values).all()
+        train_cae.main(["--train-inputs", paths["train"], "--test-inputs", paths["test"], "--model-folder", folder,
+                        "--input-variables", "lowres", "--output-variable", "hires", "--nr-epochs", "3",
+                        "--batch-size", "8", "--continue-training"])
+        hist = json.load(open(os.path.join(folder, "history.json")))
+        assert hist["nr_epochs"] == 7
+    import sqlite3
+    assert sqlite3.connect(db).execute("select count(*) from MODEL_TRAINING").fetchone()[0] == 2   # --continue-training builds the model without a database (as the reference does)

@@ -1,0 +1,125 @@
+"""The tiled (v2) kernels against the generic (v1) kernels and against torch fp64, at geometries that exercise
+multi-tile grids, ragged edges, channel chunking and both weight-gradient regimes."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64) * scale
+
+
+def close(a, b, tol, what):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    err = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-12)
+    assert err <= tol, f"{what}: rel err {err:.3e} > {tol}"
+
+
+@pytest.fixture(autouse=True)
+def _gen2():
+    from cae_tools_b200.engine import ops
+    ops.set_kernel_generation(2)
+    yield
+    ops.set_kernel_generation(2)
+
+
+BIG = [
+    # N, Cin, Cout, k, p, H, W  (transposed conv input size)
+    (3, 2, 1, 4, 0, 127, 127),
+    (2, 4, 2, 3, 0, 63, 63),
+    (5, 8, 4, 3, 0, 31, 31),
+    (9, 16, 8, 3, 0, 15, 15),
+    (17, 32, 16, 3, 0, 7, 7),
+    (33, 64, 32, 3, 0, 3, 3),
+    (2, 70, 9, 3, 0, 20, 37),
+    (3, 16, 8, 4, 1, 8, 8),
+    (2, 3, 5, 4, 1, 33, 17),
+]
+
+
+@pytest.mark.parametrize("case", BIG)
+def test_up_down_wgrad_v2(case):
+    from cae_tools_b200.engine import ops
+    dev = torch.device("cuda")
+    N, Ci, Co, k, p, H, W = case
+    x = rnd(N, Ci, H, W, seed=1).float()
+    w = rnd(Ci, Co, k, k, seed=2, scale=0.2).float()
+    b = rnd(Co, seed=3).float()
+    k0, k2 = (rnd(Ci, seed=4).abs() + 0.5).float(), rnd(Ci, seed=5).float()
+    xin = F.relu(x.double() * k0.double().view(1, -1, 1, 1) + k2.double().view(1, -1, 1, 1)).requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    ref = F.conv_transpose2d(xin, wd, b.double(), stride=2, padding=p)
+    up = rnd(*ref.shape, seed=6).float()
+    (ref * up.double()).sum().backward()
+    xd, wdev, bd, k0d, k2d, upd = (t.to(dev) for t in (x, w, b, k0, k2, up))
+    src = ops.make_src(xd, k0=k0d, k2=k2d, relu=True)
+    g = ops.geom(k, 2, p)
+    for gen in (2, 1):
+        ops.set_kernel_generation(gen)
+        out = torch.full(ref.shape, float("nan"), dtype=torch.float32, device=dev)
+        ops.conv_up(src, wdev, g, ops.view4(out), ops.make_epilogue(ops.EPI_PLAIN, bias=bd))
+        # dgrad: strided conv of the upstream gradient
+        dx = torch.full(x.shape, float("nan"), dtype=torch.float32, device=dev)
+        ops.conv_down(ops.make_src(upd), wdev, g, ops.view4(dx), ops.make_epilogue(ops.EPI_PLAIN))
+        gw = torch.full(w.shape, float("nan"), dtype=torch.float32, device=dev)
+        dy = ops.make_src(upd)
+        part = torch.zeros(ops.wgrad_partials_len(src, dy, g), dtype=torch.float32, device=dev)
+        ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        for _ in range(2):
+            ops.conv_wgrad(src, dy, g, gw, part, ticket)
+        torch.cuda.synchronize()
+        close(out, ref, 2e-5, f"up gen{gen} {case}")
+        close(dx, xin.grad, 5e-5, f"down gen{gen} {case}")
+        close(gw, wd.grad, 1e-4, f"wgrad gen{gen} {case}")
+        assert int(ticket.item()) == 0
+
+
+@pytest.mark.parametrize("k", [3, 4])
+def test_v2_stats_and_maskstats_match_v1_bitwise_inputs(k):
+    """STATS / MASKSTATS / SIGMOID_MSE epilogues through the tiled kernels vs the generic ones"""
+    from cae_tools_b200.engine import ops
+    dev = torch.device("cuda")
+    N, Ci, Co, H, W = 6, 4, 3, 21, 19
+    x = rnd(N, Ci, H, W, seed=11).float().to(dev)
+    w = rnd(Ci, Co, k, k, seed=12, scale=0.3).float().to(dev)
+    b = rnd(Co, seed=13).float().to(dev)
+    Ho, Wo = (H - 1) * 2 + k, (W - 1) * 2 + k
+    tgt = torch.rand(N, Co, Ho, Wo, generator=torch.Generator().manual_seed(14)).to(dev)
+    res = {}
+    for gen in (1, 2):
+        ops.set_kernel_generation(gen)
+        scr = torch.zeros(7, Co, device=dev)
+        gam, bet = torch.ones(Co, device=dev) * 1.3, torch.ones(Co, device=dev) * 0.1
+        rm, rv = torch.zeros(Co, device=dev), torch.ones(Co, device=dev)
+        bn = ops.make_bn(Co, 1e-5, 0.1, gam, bet, rm, rv, None, scale=scr[0], shift=scr[1], mean=scr[2], invstd=scr[3],
+                         bwdA=scr[4], bwdB=scr[5], bwdC=scr[6], dgamma=torch.zeros(Co, device=dev),
+                         dbeta=torch.zeros(Co, device=dev))
+        P = lambda: torch.zeros(ops.partials_len(max(Co, Ci)), dtype=torch.float64, device=dev)
+        T = lambda: torch.zeros(1, dtype=torch.int32, device=dev)
+        y = torch.empty(N, Co, Ho, Wo, device=dev)
+        ops.conv_up(ops.make_src(x), w, ops.geom(k, 2, 0), ops.view4(y),
+                    ops.make_epilogue(ops.EPI_STATS, bias=b, partials=P(), ticket=T(), bn=bn))
+        # loss epilogue on the same conv
+        losses, dbias = torch.zeros(1, device=dev), torch.zeros(Co, device=dev)
+        dz = torch.empty_like(y)
+        ops.conv_up(ops.make_src(x), w, ops.geom(k, 2, 0), ops.view4(dz),
+                    ops.make_epilogue(ops.EPI_SIGMOID_MSE, bias=b, partials=P(), ticket=T(), target=ops.make_src(tgt),
+                                      loss_out=losses, dbias=dbias))
+        # dgrad with mask + BN sums of a (fictitious) producer layer whose raw output is x itself
+        scr_in = torch.zeros(7, Ci, device=dev)
+        scr_in[0] = 0.7; scr_in[1] = 0.05; scr_in[2] = 0.1; scr_in[3] = 1.2
+        bn_in = ops.make_bn(Ci, 1e-5, 0.1, torch.ones(Ci, device=dev), torch.zeros(Ci, device=dev), scale=scr_in[0],
+                            shift=scr_in[1], mean=scr_in[2], invstd=scr_in[3], bwdA=scr_in[4], bwdB=scr_in[5],
+                            bwdC=scr_in[6], dgamma=torch.zeros(Ci, device=dev), dbeta=torch.zeros(Ci, device=dev))
+        dzx = torch.empty_like(x)
+        ops.conv_down(ops.make_src(dz), w, ops.geom(k, 2, 0), ops.view4(dzx),
+                      ops.make_epilogue(ops.EPI_MASKSTATS, partials=P(), ticket=T(), bn=bn_in, act=x))
+        torch.cuda.synchronize()
+        res[gen] = [t.clone() for t in (y, scr, rm, rv, losses, dbias, dz, dzx, scr_in)]
+    names = ["y", "bn scratch", "running_mean", "running_var", "loss", "dbias", "dz", "dz_prev", "bn bwd coefficients"]
+    for name, a, b_ in zip(names, res[2], res[1]):
+        close(a, b_, 2e-5, name)

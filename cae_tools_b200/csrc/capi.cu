@@ -6,6 +6,7 @@
 #include <unordered_set>
 #include "conv_family.cuh"
 #include "conv_tiled.cuh"
+#include "conv_direct.cuh"
 #include "dense_misc.cuh"
 
 static thread_local char g_err[512] = "";
@@ -150,9 +151,11 @@ static const int kTileSmemMax = 100 * 1024;
 #define CAE_V2_UPDOWN 1
 #define CAE_V2_WGRAD_A 2
 #define CAE_V2_WGRAD_B 4
+#define CAE_V2_UPDOWN_WIDE 8   // tiled up/down also for wide layers (register tile of 2/4 positions)
+#define CAE_V3_DIRECT 16       // vectorised direct kernels for wide thin layers (k_up3 / k_down3)
 static int default_mask() {
     const char* e = getenv("CAE_KERNEL_MASK");
-    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A);
+    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A | CAE_V3_DIRECT);
 }
 static int g_mask = default_mask();
 #define g_use_v2 (g_mask & CAE_V2_UPDOWN)
@@ -248,7 +251,7 @@ static int launch_up2(ConvArgs& a, cudaStream_t st, bool& handled) {
     const int QH = (a.out.H - 1 + a.p) / 2 + 1, QW = (a.out.W - 1 + a.p) / 2 + 1;
     if (QH - a.in.t0.H < JY - 1) return CAE_OK;
     TileChoice tc = choose_tile(a.Cin, a.Cout, a.out.N * QH, QW, JY - 1, 1, JX - 1, 1, KH * KW, QH, 4, 4);
-    if (!tc.ok) return CAE_OK;
+    if (!tc.ok || (tc.cx > 1 && !(g_mask & CAE_V2_UPDOWN_WIDE))) return CAE_OK;
     handled = true;
     a.QH = QH; a.QW = QW;
     int ntiles = tc.plan.nrow_tiles * tc.plan.ncol_tiles;
@@ -262,12 +265,74 @@ static int launch_down2(ConvArgs& a, cudaStream_t st, bool& handled) {
     handled = false;
     const int OHp = a.out.H + 1;
     TileChoice tc = choose_tile(a.Cin, a.Cout, a.out.N * OHp, a.out.W, KH - 2, 2, 2, 2, KH * KW, OHp, 4, 1);
-    if (!tc.ok) return CAE_OK;
+    if (!tc.ok || (tc.cx > 1 && !(g_mask & CAE_V2_UPDOWN_WIDE))) return CAE_OK;
     handled = true;
     int ntiles = tc.plan.nrow_tiles * tc.plan.ncol_tiles;
     dim3 grid(min(ntiles, CAE_MAX_GRID_X), ceil_div(a.Cout, tc.cot * tc.plan.TZ));
     CAE_LAUNCH_TILED(k_down2, KH, KW);
     return cae_check_launch("cae_conv_down(v2)");
+}
+
+
+// ---- v3 direct kernels: eligibility + launch -------------------------------------------------------
+static bool aligned4(const void* p, int ld, long long sC, long long sN) {
+    return p && ((uintptr_t)p % 16 == 0) && ld % 4 == 0 && sC % 4 == 0 && sN % 4 == 0;
+}
+static bool view_aligned(const CaeView& v) { return aligned4(v.p, v.ld, v.sC, v.sN); }
+static bool src_aligned(const CaeSrc& s) {
+    if (!view_aligned(s.t0)) return false;
+    if (s.t1 && (uintptr_t)s.t1 % 16 != 0) return false;
+    if (s.cursor && s.cursor_stride % 4 != 0) return false;
+    return true;
+}
+static bool direct_ok(const ConvArgs& a, int width_in) {
+    if (!(g_mask & CAE_V3_DIRECT)) return false;
+    if (a.s != 2 || a.p != 0 || a.kh != a.kw || (a.kh != 3 && a.kh != 4)) return false;
+    if (width_in < 24) return false;                                    // narrow layers: tiled kernels
+    if (!src_aligned(a.in) || !view_aligned(a.out)) return false;
+    if (a.epi.mode == CAE_EPI_MASKSTATS && !view_aligned(a.epi.act)) return false;
+    if (a.epi.mode == CAE_EPI_SIGMOID_MSE && (!src_aligned(a.epi.target) || a.epi.target.t1 || a.epi.target.relu)) return false;
+    return true;
+}
+static int direct_cot(int Cout) { return Cout >= 4 ? 4 : (Cout >= 2 ? 2 : 1); }
+
+template <int K>
+static int launch_up3(ConvArgs& a, cudaStream_t st, bool& handled) {
+    handled = false;
+    if (!direct_ok(a, a.in.t0.W)) return CAE_OK;
+    const int cot = direct_cot(a.Cout);
+    const size_t smem = (size_t)a.Cin * K * K * cot * 4;
+    if (smem > 48 * 1024) return CAE_OK;
+    StripPlan p{};
+    p.RP = (a.out.H - 1) / 2 + 1;
+    const int QW = (a.out.W - 1) / 2 + 1;
+    p.NS = (QW + 3) / 4;
+    p.units = a.out.N * p.RP * p.NS;
+    handled = true;
+    dim3 grid(min(ceil_div(p.units, CAE_NT), CAE_MAX_GRID_X), ceil_div(a.Cout, cot));
+    if (cot == 4) k_up3<K, 4><<<grid, CAE_NT, smem, st>>>(a, p);
+    else if (cot == 2) k_up3<K, 2><<<grid, CAE_NT, smem, st>>>(a, p);
+    else k_up3<K, 1><<<grid, CAE_NT, smem, st>>>(a, p);
+    return cae_check_launch("cae_conv_up(v3)");
+}
+
+template <int K>
+static int launch_down3(ConvArgs& a, cudaStream_t st, bool& handled) {
+    handled = false;
+    if (!direct_ok(a, a.out.W)) return CAE_OK;
+    const int cot = direct_cot(a.Cout);
+    const size_t smem = (size_t)a.Cin * K * K * cot * 4;
+    if (smem > 48 * 1024) return CAE_OK;
+    StripPlan p{};
+    p.RP = a.out.H;
+    p.NS = (a.out.W + 3) / 4;
+    p.units = a.out.N * p.RP * p.NS;
+    handled = true;
+    dim3 grid(min(ceil_div(p.units, CAE_NT), CAE_MAX_GRID_X), ceil_div(a.Cout, cot));
+    if (cot == 4) k_down3<K, 4><<<grid, CAE_NT, smem, st>>>(a, p);
+    else if (cot == 2) k_down3<K, 2><<<grid, CAE_NT, smem, st>>>(a, p);
+    else k_down3<K, 1><<<grid, CAE_NT, smem, st>>>(a, p);
+    return cae_check_launch("cae_conv_down(v3)");
 }
 
 extern "C" int cae_conv_up(const CaeSrc* in, const float* weight, const CaeConvGeom* g, const CaeView* out,
@@ -282,6 +347,11 @@ extern "C" int cae_conv_up(const CaeSrc* in, const float* weight, const CaeConvG
                 "conv_up: output %dx%d inconsistent with input %dx%d k=%dx%d s=%d p=%d", out->H, out->W, iv.H, iv.W,
                 a.kh, a.kw, a.s, a.p);
     cudaStream_t st = (cudaStream_t)stream;
+    if (a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+        bool handled = false;
+        rc = (a.kh == 3) ? launch_up3<3>(a, st, handled) : launch_up3<4>(a, st, handled);
+        if (handled) return rc;
+    }
     if (g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
         bool handled = false;
         rc = (a.kh == 3) ? launch_up2<3, 3>(a, st, handled) : launch_up2<4, 4>(a, st, handled);
@@ -316,6 +386,11 @@ extern "C" int cae_conv_down(const CaeSrc* in, const float* weight, const CaeCon
     cudaStream_t st = (cudaStream_t)stream;
     a.QH = out->H; a.QW = out->W;
     a.total = out->N * out->H * out->W;
+    if (a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+        bool handled = false;
+        rc = (a.kh == 3) ? launch_down3<3>(a, st, handled) : launch_down3<4>(a, st, handled);
+        if (handled) return rc;
+    }
     if (g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
         bool handled = false;
         rc = (a.kh == 3) ? launch_down2<3, 3>(a, st, handled) : launch_down2<4, 4>(a, st, handled);
@@ -401,12 +476,14 @@ struct Wg2Choice {
     size_t smem;
     int grid_x, grid_y;
     long long partials;
+    StripPlan strip;
+    int tiles_b;
 };
 
-static Wg2Choice plan_wgrad2(int N, int Cs, int Hs, int Ws, int Cb, int kh, int kw, int s) {
+static Wg2Choice plan_wgrad2(int N, int Cs, int Hs, int Ws, int Cb, int kh, int kw, int s, bool direct = false) {
     Wg2Choice w{};
     w.kind = 0;
-    if (!(g_mask & (CAE_V2_WGRAD_A | CAE_V2_WGRAD_B)) || s != 2 || kh != kw || (kh != 3 && kh != 4)) return w;
+    if (!(g_mask & (CAE_V2_WGRAD_A | CAE_V2_WGRAD_B | CAE_V3_DIRECT)) || s != 2 || kh != kw || (kh != 3 && kh != 4)) return w;
     const int KK = kh * kw;
     const long long nelem = (long long)Cs * Cb * KK;
     int cst = Cs >= 4 ? 4 : (Cs >= 2 ? 2 : 1);
@@ -416,6 +493,18 @@ static Wg2Choice plan_wgrad2(int N, int Cs, int Hs, int Ws, int Cb, int kh, int 
     if (cst == 1 && cbt == 2) cbt = 1;                      // instantiated: (4,2) (2,2) (2,1) (1,1)
     const int tiles_b = (Cb + cbt - 1) / cbt;
     const int G = ((Cs + cst - 1) / cst) * tiles_b;
+    if (direct && Ws >= 24 && G <= 16 && (g_mask & CAE_V3_DIRECT)) {
+        w.kind = 3; w.cst = cst; w.cbt = cbt;
+        w.strip.RP = Hs; w.strip.NS = (Ws + 3) / 4; w.strip.units = N * Hs * w.strip.NS;
+        w.tiles_b = tiles_b;
+        long long ctas = (w.strip.units + CAE_NT - 1) / CAE_NT;
+        long long cap = (2ll * CAE_NUM_SMS + G - 1) / G;
+        w.grid_x = (int)(ctas < cap ? ctas : cap);
+        if (w.grid_x < 1) w.grid_x = 1;
+        w.grid_y = G;
+        w.partials = (long long)w.grid_x * nelem;
+        return w;
+    }
     if (G <= 8 && (g_mask & CAE_V2_WGRAD_A)) {
         Wg2Plan p{};
         int cx = Ws >= 96 ? 4 : (Ws >= 48 ? 2 : 1);
@@ -497,7 +586,11 @@ extern "C" long long cae_wgrad_partials_len(const CaeSrc* sm, const CaeSrc* bg, 
     WgradPlan p = plan_wgrad(sm->t0.C, bg->t0.C, g->kh, g->kw, g->stride, sm->t0.N * sm->t0.H * sm->t0.W);
     long long v1 = (long long)p.nchunks * sm->t0.C * bg->t0.C * g->kh * g->kw;
     Wg2Choice w = plan_wgrad2(sm->t0.N, sm->t0.C, sm->t0.H, sm->t0.W, bg->t0.C, g->kh, g->kw, g->stride);
-    return (w.kind != 0 && w.partials > v1) ? w.partials : v1;    // either generation may be selected at run time
+    Wg2Choice w3 = plan_wgrad2(sm->t0.N, sm->t0.C, sm->t0.H, sm->t0.W, bg->t0.C, g->kh, g->kw, g->stride, true);
+    long long need = v1;
+    if (w.kind != 0 && w.partials > need) need = w.partials;
+    if (w3.kind != 0 && w3.partials > need) need = w3.partials;
+    return need;    // any generation may be selected at run time
 }
 
 template <int KH, int KW, int S>
@@ -526,7 +619,24 @@ extern "C" int cae_conv_wgrad(const CaeSrc* sm, const CaeSrc* bg, const CaeConvG
     a.Cs = sm->t0.C; a.Cb = bg->t0.C;
     a.total = sm->t0.N * sm->t0.H * sm->t0.W;
     cudaStream_t st = (cudaStream_t)stream;
-    Wg2Choice w2 = plan_wgrad2(sm->t0.N, a.Cs, sm->t0.H, sm->t0.W, a.Cb, a.kh, a.kw, a.s);
+    const bool direct = g->pad == 0 && src_aligned(*sm) && src_aligned(*bg);
+    Wg2Choice w2 = plan_wgrad2(sm->t0.N, a.Cs, sm->t0.H, sm->t0.W, a.Cb, a.kh, a.kw, a.s, direct);
+    if (w2.kind == 3) {
+        dim3 grid(w2.grid_x, w2.grid_y);
+#define CAE_WG3(KK_, S_, B_) k_wgrad3<KK_, S_, B_><<<grid, CAE_NT, 0, st>>>(a, w2.strip, w2.tiles_b)
+        if (a.kh == 3) {
+            if (w2.cst == 4 && w2.cbt == 2) CAE_WG3(3, 4, 2);
+            else if (w2.cst == 2 && w2.cbt == 2) CAE_WG3(3, 2, 2);
+            else if (w2.cst == 2 && w2.cbt == 1) CAE_WG3(3, 2, 1);
+            else CAE_WG3(3, 1, 1);
+        } else {
+            if (w2.cst == 2 && w2.cbt == 2) CAE_WG3(4, 2, 2);
+            else if (w2.cst == 2 && w2.cbt == 1) CAE_WG3(4, 2, 1);
+            else CAE_WG3(4, 1, 1);
+        }
+#undef CAE_WG3
+        return cae_check_launch("cae_conv_wgrad(v3)");
+    }
     if (w2.kind == 1) {
         if (a.kh == 3) launch_wgrad2a<3>(a, w2, st); else launch_wgrad2a<4>(a, w2, st);
         return cae_check_launch("cae_conv_wgrad(v2a)");

@@ -110,57 +110,102 @@ __device__ __forceinline__ double warp_colsum(const double* part, int rows, int 
     return warp_sum_d(s);
 }
 
+// Both statistics of channel c (columns 2c, 2c+1) over `rows` partial rows by one warp.  All loads of a lane are
+// issued before the first add (rows <= CAE_MAX_GRID_X -> at most 19 per lane), so the L2 latency is paid once.
+__device__ __forceinline__ void warp_colsum2(const double* part, int rows, int C, int c, double& S, double& Q) {
+    constexpr int MAXIT = (CAE_MAX_GRID_X + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    double2 v[MAXIT];
+#pragma unroll
+    for (int i = 0; i < MAXIT; ++i) {
+        const int r = lane + 32 * i;
+        v[i] = (r < rows) ? __ldcg(reinterpret_cast<const double2*>(part + ((size_t)r * C + c) * 2)) : make_double2(0.0, 0.0);
+    }
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int i = 0; i < MAXIT; ++i) {
+        s += v[i].x;
+        q += v[i].y;
+    }
+    S = warp_sum_d(s);
+    Q = warp_sum_d(q);
+}
+
 // ---- finalizers (executed by the last CTA; `rows` = gridDim.x partial rows of C*2 doubles) ----
+// Column sums of the partial rows for every channel at once: `tpc` threads (a power of two <= 32, groups aligned
+// inside a warp) share one channel, each adds the rows r = sub, sub+tpc, ... (loads issued four at a time so the
+// L2 latency overlaps), then a fixed-order butterfly combines the group.  f(c, S, Q) runs in the group leader.
+template <typename F>
+__device__ __forceinline__ void for_each_channel_sums(const double* part, int rows, int C, F f, int ncols = -1) {
+    // C: channels per partial row (row stride); ncols: how many channels (from `part` on) to process
+    const int NC = ncols < 0 ? C : ncols;
+    int tpc = 1;
+    while (tpc < 32 && tpc * 2 * NC <= (int)blockDim.x) tpc *= 2;
+    const int cpp = blockDim.x / tpc;          // channels per pass
+    const int sub = threadIdx.x & (tpc - 1);
+    for (int c0 = 0; c0 < NC; c0 += cpp) {
+        const int c = c0 + (threadIdx.x / tpc);
+        double s = 0.0, q = 0.0;
+        if (c < NC) {
+            const double2* col = reinterpret_cast<const double2*>(part) + c;
+            int r = sub;
+            for (; r + 3 * tpc < rows; r += 4 * tpc) {
+                double2 v0 = __ldcg(col + (size_t)r * C), v1 = __ldcg(col + (size_t)(r + tpc) * C);
+                double2 v2 = __ldcg(col + (size_t)(r + 2 * tpc) * C), v3 = __ldcg(col + (size_t)(r + 3 * tpc) * C);
+                s += v0.x; q += v0.y; s += v1.x; q += v1.y; s += v2.x; q += v2.y; s += v3.x; q += v3.y;
+            }
+            for (; r < rows; r += tpc) {
+                double2 v = __ldcg(col + (size_t)r * C);
+                s += v.x; q += v.y;
+            }
+        }
+        for (int o = tpc >> 1; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (c < NC && sub == 0) f(c, s, q);
+    }
+}
+
 // BatchNorm forward statistics (training): reference semantics of nn.BatchNorm2d
 // (biased variance for normalisation, unbiased for running_var, momentum update).
 __device__ __forceinline__ void finalize_bn_forward(const CaeBN& bn, const double* part, int rows, double count) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < bn.C; c += (blockDim.x >> 5)) {
-        double S = warp_colsum(part, rows, bn.C * 2, c * 2 + 0);
-        double Q = warp_colsum(part, rows, bn.C * 2, c * 2 + 1);
-        if (lane == 0) {
-            double mean = S / count;
-            double var = Q / count - mean * mean;
-            if (var < 0.0) var = 0.0;
-            double invstd = rsqrt(var + (double)bn.eps);
-            float g = bn.gamma ? bn.gamma[c] : 1.f;
-            float b = bn.beta ? bn.beta[c] : 0.f;
-            float scale = (float)((double)g * invstd);
-            bn.scale[c] = scale;
-            bn.shift[c] = (float)((double)b - mean * (double)g * invstd);
-            bn.mean[c] = (float)mean;
-            bn.invstd[c] = (float)invstd;
-            if (bn.running_mean) {
-                double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-                double m = (double)bn.momentum;
-                bn.running_mean[c] = (float)((1.0 - m) * (double)bn.running_mean[c] + m * mean);
-                bn.running_var[c] = (float)((1.0 - m) * (double)bn.running_var[c] + m * unbiased);
-            }
+    for_each_channel_sums(part, rows, bn.C, [&](int c, double S, double Q) {
+        double mean = S / count;
+        double var = Q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        double invstd = rsqrt(var + (double)bn.eps);
+        float g = bn.gamma ? bn.gamma[c] : 1.f;
+        float b = bn.beta ? bn.beta[c] : 0.f;
+        bn.scale[c] = (float)((double)g * invstd);
+        bn.shift[c] = (float)((double)b - mean * (double)g * invstd);
+        bn.mean[c] = (float)mean;
+        bn.invstd[c] = (float)invstd;
+        if (bn.running_mean) {
+            double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            double m = (double)bn.momentum;
+            bn.running_mean[c] = (float)((1.0 - m) * (double)bn.running_mean[c] + m * mean);
+            bn.running_var[c] = (float)((1.0 - m) * (double)bn.running_var[c] + m * unbiased);
         }
-    }
+    });
     if (threadIdx.x == 0 && bn.num_batches_tracked) bn.num_batches_tracked[0] += 1;
 }
 
 // BatchNorm backward sums -> dgamma, dbeta and the coefficients of dL/dy = A*dz + B*y + C
 __device__ __forceinline__ void finalize_bn_backward(const CaeBN& bn, const double* part, int rows, double count) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < bn.C; c += (blockDim.x >> 5)) {
-        double S1 = warp_colsum(part, rows, bn.C * 2, c * 2 + 0);  // sum dz
-        double S2 = warp_colsum(part, rows, bn.C * 2, c * 2 + 1);  // sum dz * xhat
-        if (lane == 0) {
-            double g = bn.gamma ? (double)bn.gamma[c] : 1.0;
-            double invstd = (double)bn.invstd[c], mean = (double)bn.mean[c];
-            double A = g * invstd;
-            double B = -A * invstd * S2 / count;
-            double Cc = -A * S1 / count - B * mean;
-            bn.bwdA[c] = (float)A;
-            bn.bwdB[c] = (float)B;
-            bn.bwdC[c] = (float)Cc;
-            if (bn.dgamma) bn.dgamma[c] = (float)S2;
-            if (bn.dbeta) bn.dbeta[c] = (float)S1;
-            // the bias of a conv that feeds a training-mode BN has an identically zero gradient
-            // (sum_y dL/dy = 0); autograd returns rounding noise here.
-            if (bn.dbias) bn.dbias[c] = 0.f;
-        }
-    }
+    for_each_channel_sums(part, rows, bn.C, [&](int c, double S1, double S2) {   // sum dz, sum dz * xhat
+        double g = bn.gamma ? (double)bn.gamma[c] : 1.0;
+        double invstd = (double)bn.invstd[c], mean = (double)bn.mean[c];
+        double A = g * invstd;
+        double B = -A * invstd * S2 / count;
+        double Cc = -A * S1 / count - B * mean;
+        bn.bwdA[c] = (float)A;
+        bn.bwdB[c] = (float)B;
+        bn.bwdC[c] = (float)Cc;
+        if (bn.dgamma) bn.dgamma[c] = (float)S2;
+        if (bn.dbeta) bn.dbeta[c] = (float)S1;
+        // the bias of a conv that feeds a training-mode BN has an identically zero gradient
+        // (sum_y dL/dy = 0); autograd returns rounding noise here.
+        if (bn.dbias) bn.dbias[c] = 0.f;
+    });
 }

@@ -88,23 +88,29 @@ __host__ __device__ __forceinline__ bool epi_reduces(int mode) {
 
 // loss = sum_c Q_c / count ; dbias[c] = S1_c
 __device__ __forceinline__ void finalize_mse(const CaeEpilogue& e, const double* part, int rows, int C, double count) {
-    __shared__ double wq[CAE_NWARP];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double q = 0.0;
-    if (lane == 0) wq[warp] = 0.0;
-    for (int c = warp; c < C; c += (blockDim.x >> 5)) {
-        double S1 = warp_colsum(part, rows, C * 2, c * 2 + 0);
-        q += warp_colsum(part, rows, C * 2, c * 2 + 1);
-        if (lane == 0 && e.dbias) e.dbias[c] = (float)S1;
-    }
-    if (lane == 0) wq[warp] = q;
+    __shared__ double qc[64];
+    __shared__ double qtot;
+    if (threadIdx.x == 0) qtot = 0.0;
     __syncthreads();
+    // channels in passes of <= 64 so the per-channel losses can be added in channel order
+    for (int cb = 0; cb < C; cb += 64) {
+        const int cn = min(64, C - cb);
+        for_each_channel_sums(part + (size_t)cb * 2, rows, C, [&](int c, double S1, double Q) {
+            if (e.dbias) e.dbias[cb + c] = (float)S1;
+            qc[c] = Q;
+        }, cn);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = qtot;
+            for (int c = 0; c < cn; ++c) t += qc[c];
+            qtot = t;
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wq[w];
         int slot = e.target.cursor ? __ldg(e.target.cursor) : 0;
         const double cs = e.count_scale > 0.f ? (double)e.count_scale : 1.0;
-        if (e.loss_out) e.loss_out[slot] = (float)(t / count * cs);
+        if (e.loss_out) e.loss_out[slot] = (float)(qtot / count * cs);
     }
 }
 

@@ -137,20 +137,45 @@ __device__ __forceinline__ void epi_reduce_tail_tz(const CaeEpilogue& e, const C
                                                    int WC, int gthreads, const float (&s1)[COT], const float (&s2)[COT]) {
     const int C = out.C;
     __syncthreads();
+    if (gthreads >= 32) {
+        // every warp lies inside one channel group: shuffle-reduce, then add the group's warps in order
+        double* dscr = reinterpret_cast<double*>(scratch);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int j = 0; j < COT; ++j) {
-        scratch[threadIdx.x * (2 * COT) + 2 * j] = s1[j];
-        scratch[threadIdx.x * (2 * COT) + 2 * j + 1] = s2[j];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < WC * 2; i += blockDim.x) {
-        const int ch = i >> 1, g = ch / COT, j = ch - g * COT, st = i & 1;
-        const int co = cbase + ch;
-        if (co < C) {
-            double s = 0.0;
-            const float* src = scratch + (size_t)g * gthreads * (2 * COT) + 2 * j + st;
-            for (int t = 0; t < gthreads; ++t) s += (double)src[t * (2 * COT)];
-            e.partials[((size_t)blockIdx.x * C + co) * 2 + st] = s;
+        for (int j = 0; j < COT; ++j) {
+            double a = warp_sum_d((double)s1[j]), b = warp_sum_d((double)s2[j]);
+            if (lane == 0) {
+                dscr[warp * (2 * COT) + 2 * j] = a;
+                dscr[warp * (2 * COT) + 2 * j + 1] = b;
+            }
+        }
+        __syncthreads();
+        const int wpg = gthreads >> 5;
+        for (int i = threadIdx.x; i < WC * 2; i += blockDim.x) {
+            const int ch = i >> 1, g = ch / COT, j = ch - g * COT, st = i & 1;
+            const int co = cbase + ch;
+            if (co < C) {
+                double s = 0.0;
+                for (int w = 0; w < wpg; ++w) s += dscr[(g * wpg + w) * (2 * COT) + 2 * j + st];
+                e.partials[((size_t)blockIdx.x * C + co) * 2 + st] = s;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < COT; ++j) {
+            scratch[threadIdx.x * (2 * COT) + 2 * j] = s1[j];
+            scratch[threadIdx.x * (2 * COT) + 2 * j + 1] = s2[j];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < WC * 2; i += blockDim.x) {
+            const int ch = i >> 1, g = ch / COT, j = ch - g * COT, st = i & 1;
+            const int co = cbase + ch;
+            if (co < C) {
+                double s = 0.0;
+                const float* src = scratch + (size_t)g * gthreads * (2 * COT) + 2 * j + st;
+                for (int t = 0; t < gthreads; ++t) s += (double)src[t * (2 * COT)];
+                e.partials[((size_t)blockIdx.x * C + co) * 2 + st] = s;
+            }
         }
     }
     if (cae_last_block(e.ticket)) {

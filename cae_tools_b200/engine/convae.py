@@ -119,6 +119,14 @@ class ConvAEEngine:
         self._keep.append(t)
         return t
 
+    def _conv_buf(self, B, C, H, W, dense=False):
+        """activation buffer [B,C,H,W]; rows padded to a multiple of 4 floats (16-byte aligned rows let the wide-layer
+        kernels use float4 loads/stores) unless the fc stack reads it as a flat matrix (dense)"""
+        if dense or W % 4 == 0:
+            return self._f32(B, C, H, W)
+        ld = (W + 3) // 4 * 4
+        return self._f32(B, C, H, ld)[:, :, :, :W]
+
     def _ticket(self):
         i = self._next_ticket
         self._next_ticket += 1
@@ -147,16 +155,19 @@ class ConvAEEngine:
         if B in self._bufs:
             return self._bufs[B]
         b = {}
-        b["y_e"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.enc_specs]
-        b["dz_e"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.enc_specs]
+        ne = len(self.enc_specs)
+        b["y_e"] = [self._conv_buf(B, *sp.get_output_dimensions(), dense=(i == ne - 1))
+                    for i, sp in enumerate(self.enc_specs)]
+        b["dz_e"] = [self._conv_buf(B, *sp.get_output_dimensions(), dense=(i == ne - 1))
+                     for i, sp in enumerate(self.enc_specs)]
         c0, h0, w0 = self.dec_specs[0].get_input_dimensions()
         b["u"] = self._f32(B, c0, h0, w0)
         b["du"] = self._f32(B, c0, h0, w0)
         ce, he, we = self.enc_specs[-1].get_output_dimensions()
         b["da"] = self._f32(B, ce, he, we)
         self._fc_buffers(b, B)
-        b["y_d"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.dec_specs]   # last: dL/dz or yhat
-        b["dz_d"] = [self._f32(B, *sp.get_output_dimensions()) for sp in self.dec_specs[:-1]]
+        b["y_d"] = [self._conv_buf(B, *sp.get_output_dimensions()) for sp in self.dec_specs]   # last: dL/dz or yhat
+        b["dz_d"] = [self._conv_buf(B, *sp.get_output_dimensions()) for sp in self.dec_specs[:-1]]
         self._bufs[B] = b
         return b
 

@@ -123,3 +123,92 @@ def test_v2_stats_and_maskstats_match_v1_bitwise_inputs(k):
     names = ["y", "bn scratch", "running_mean", "running_var", "loss", "dbias", "dz", "dz_prev", "bn bwd coefficients"]
     for name, a, b_ in zip(names, res[2], res[1]):
         close(a, b_, 2e-5, name)
+
+
+def padded(t):
+    """same values, rows padded to a multiple of 4 floats (what the engine allocates for wide layers)"""
+    W = t.shape[-1]
+    ld = (W + 3) // 4 * 4
+    buf = torch.full(t.shape[:-1] + (ld,), 7.0, dtype=t.dtype, device=t.device)   # poison in the padding
+    v = buf[..., :W]
+    v.copy_(t)
+    return v
+
+
+@pytest.mark.parametrize("case", [(3, 2, 1, 4, 127), (2, 4, 2, 3, 63), (3, 8, 4, 3, 31), (2, 3, 5, 3, 45), (2, 6, 3, 4, 26)])
+def test_direct_v3_kernels_on_padded_buffers(case):
+    """wide thin layers: the float4 'direct' kernels (mask bit 16) vs the generic ones, every epilogue"""
+    from cae_tools_b200.engine import ops
+    dev = torch.device("cuda")
+    N, Ci, Co, k, H = case
+    W = H + 2
+    Ho, Wo = (H - 1) * 2 + k, (W - 1) * 2 + k
+    x = padded(rnd(N, Ci, H, W, seed=21).float().to(dev))
+    x1 = padded(rnd(N, Ci, H, W, seed=22).float().to(dev))
+    w = rnd(Ci, Co, k, k, seed=23, scale=0.3).float().to(dev)
+    b = rnd(Co, seed=24).float().to(dev)
+    k0, k1, k2 = (rnd(Ci, seed=25).abs() + 0.5).float().to(dev), rnd(Ci, seed=26).float().to(dev), rnd(Ci, seed=27).float().to(dev)
+    tgt = torch.rand(3 * N, Co, Ho, Wo, generator=torch.Generator().manual_seed(28)).to(dev) if Wo % 4 == 0 else None
+    tgt_p = padded(torch.rand(N, Co, Ho, Wo, generator=torch.Generator().manual_seed(28)).to(dev))
+    cursor = torch.tensor([2], dtype=torch.int32, device=dev)
+    res = {}
+    for mask in (0, 16):
+        ops.set_kernel_generation((mask << 4) | 3)
+        g = ops.geom(k, 2, 0)
+        src = ops.make_src(x, k0=k0, k2=k2, relu=True)
+        scr = torch.zeros(7, Co, device=dev)
+        gam, bet = torch.full((Co,), 1.3, device=dev), torch.full((Co,), 0.1, device=dev)
+        bn = ops.make_bn(Co, 1e-5, 0.1, gam, bet, scale=scr[0], shift=scr[1], mean=scr[2], invstd=scr[3], bwdA=scr[4],
+                         bwdB=scr[5], bwdC=scr[6], dgamma=torch.zeros(Co, device=dev), dbeta=torch.zeros(Co, device=dev))
+        P = lambda: torch.zeros(ops.partials_len(max(Co, Ci)), dtype=torch.float64, device=dev)
+        T = lambda: torch.zeros(1, dtype=torch.int32, device=dev)
+        y = padded(torch.zeros(N, Co, Ho, Wo, device=dev))
+        ops.conv_up(src, w, g, ops.view4(y), ops.make_epilogue(ops.EPI_STATS, bias=b, partials=P(), ticket=T(), bn=bn))
+        ysig = padded(torch.zeros(N, Co, Ho, Wo, device=dev))
+        ops.conv_up(src, w, g, ops.view4(ysig), ops.make_epilogue(ops.EPI_SIGMOID, bias=b))
+        losses, dbias = torch.zeros(3, device=dev), torch.zeros(Co, device=dev)
+        dz = padded(torch.zeros(N, Co, Ho, Wo, device=dev))
+        if tgt is not None:
+            tsrc = ops.make_src(tgt[:N], cursor=cursor, cursor_stride=N * Co * Ho * Wo)
+        else:
+            tsrc = ops.make_src(tgt_p)
+        ops.conv_up(src, w, g, ops.view4(dz),
+                    ops.make_epilogue(ops.EPI_SIGMOID_MSE, bias=b, partials=P(), ticket=T(), target=tsrc,
+                                      loss_out=losses, dbias=dbias))
+        # dgrad of the layer with the BatchNorm-backward affine on load (two tensors) and mask + sums in the epilogue
+        scr_in = torch.zeros(7, Ci, device=dev)
+        scr_in[0] = 0.7; scr_in[1] = 0.05; scr_in[2] = 0.1; scr_in[3] = 1.2
+        bn_in = ops.make_bn(Ci, 1e-5, 0.1, torch.ones(Ci, device=dev), torch.zeros(Ci, device=dev), scale=scr_in[0],
+                            shift=scr_in[1], mean=scr_in[2], invstd=scr_in[3], bwdA=scr_in[4], bwdB=scr_in[5],
+                            bwdC=scr_in[6], dgamma=torch.zeros(Ci, device=dev), dbeta=torch.zeros(Ci, device=dev))
+        kA, kB, kC = (rnd(Co, seed=31).abs() + 0.5).float().to(dev), rnd(Co, seed=32).float().to(dev), rnd(Co, seed=33).float().to(dev)
+        dy = ops.make_src(dz, t1=y, k0=kA, k1=kB, k2=kC)
+        dzx = padded(torch.zeros(N, Ci, H, W, device=dev))
+        ops.conv_down(dy, w, g, ops.view4(dzx),
+                      ops.make_epilogue(ops.EPI_MASKSTATS, partials=P(), ticket=T(), bn=bn_in, act=x))
+        dplain = padded(torch.zeros(N, Ci, H, W, device=dev))
+        ops.conv_down(dy, w, g, ops.view4(dplain), ops.make_epilogue(ops.EPI_PLAIN))
+        # weight gradient: small operand = activated input, big operand = dL/dy (two-tensor affine)
+        gw = torch.zeros_like(w)
+        part = torch.zeros(ops.wgrad_partials_len(src, dy, g), dtype=torch.float32, device=dev)
+        tkt = T()
+        for _ in range(2):
+            ops.conv_wgrad(src, dy, g, gw, part, tkt)
+        # conv-style weight gradient: small operand = dL/dy of a strided conv whose input is `y`
+        wc = torch.zeros(Ci, Co, k, k, device=dev)
+        sm2 = ops.make_src(dzx, t1=x1, k0=k0, k1=k1, k2=k2)
+        bg2 = ops.make_src(y, k0=kA, k2=kC, relu=True)
+        part2 = torch.zeros(ops.wgrad_partials_len(sm2, bg2, g), dtype=torch.float32, device=dev)
+        ops.conv_wgrad(sm2, bg2, g, wc, part2, tkt)
+        torch.cuda.synchronize()
+        assert int(tkt.item()) == 0
+        res[mask] = [t.clone() for t in (y, scr, ysig, losses, dbias, dz, dzx, scr_in, dplain, gw, wc)]
+    names = ["y", "bn scratch", "sigmoid", "loss", "dbias", "dz", "dz_prev", "bn bwd coefficients", "dgrad plain",
+             "wgrad (convT)", "wgrad (conv)"]
+    for name, a, b_ in zip(names, res[16], res[0]):
+        close(a, b_, 3e-5, name)
+    # and against torch for the plain path
+    xin = F.relu(x.double().cpu() * k0.double().cpu().view(1, -1, 1, 1) + k2.double().cpu().view(1, -1, 1, 1))
+    ref = F.conv_transpose2d(xin, w.double().cpu(), b.double().cpu(), stride=2)
+    close(res[16][0], ref, 2e-5, "y vs torch")
+    close(res[16][2], torch.sigmoid(ref), 2e-5, "sigmoid vs torch")

@@ -89,6 +89,32 @@ __global__ void __launch_bounds__(CAE_NT) k_gemm(const CaeGemm g) {
     if (do_rowsum && tid < GT && m0 + tid < g.M) g.rowsum_A[m0 + tid] = rs[tid];
 }
 
+// Skinny problems (few outputs, long K): one thread per output element, K unrolled so the (L1/L2 resident)
+// operand loads overlap.  No on-load transforms, no row sums - those stay with the tiled kernel.
+__global__ void __launch_bounds__(CAE_NT) k_gemm_skinny(const CaeGemm g) {
+    const int idx = blockIdx.x * CAE_NT + threadIdx.x;
+    if (idx >= g.M * g.N) return;
+    const int m = idx / g.N, n = idx - m * g.N;
+    const float* ap = g.A + (long long)m * g.sAm;
+    const float* bp = g.B + (long long)n * g.sBn;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int k = 0;
+    for (; k + 3 < g.K; k += 4) {
+        float a0 = __ldg(ap + (long long)k * g.sAk), a1 = __ldg(ap + (long long)(k + 1) * g.sAk);
+        float a2 = __ldg(ap + (long long)(k + 2) * g.sAk), a3 = __ldg(ap + (long long)(k + 3) * g.sAk);
+        float b0 = __ldg(bp + (long long)k * g.sBk), b1 = __ldg(bp + (long long)(k + 1) * g.sBk);
+        float b2 = __ldg(bp + (long long)(k + 2) * g.sBk), b3 = __ldg(bp + (long long)(k + 3) * g.sBk);
+        acc0 = fmaf(a0, b0, acc0); acc1 = fmaf(a1, b1, acc1); acc2 = fmaf(a2, b2, acc2); acc3 = fmaf(a3, b3, acc3);
+    }
+    for (; k < g.K; ++k) acc0 = fmaf(__ldg(ap + (long long)k * g.sAk), __ldg(bp + (long long)k * g.sBk), acc0);
+    float v = (acc0 + acc1) + (acc2 + acc3);
+    if (g.bias) v += __ldg(g.bias + n);
+    if (g.relu_out) v = fmaxf(v, 0.f);
+    const long long off = (long long)m * g.sCm + (long long)n * g.sCn;
+    if (g.mask) v = __ldg(g.mask + off) > 0.f ? v : 0.f;
+    g.C[off] = v;
+}
+
 // ---------------------------------------------------------------------------------------
 // eval-mode BatchNorm: scale/shift from the running statistics; one CTA per layer
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,77 @@
+"""Data-parallel training on 2 GPUs over NCCL (skipped on a single-GPU box): each rank trains on the same shard,
+so local BatchNorm statistics equal the global ones and the 2-rank run must reproduce a single-GPU run on the
+duplicated batch (all-reduce inside the captured step graph, count_scale = 1/world)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _models():
+    from cae_tools_b200.models.decoder import Decoder
+    from cae_tools_b200.models.encoder import Encoder
+    from cae_tools_b200.models.model_sizer import create_model_spec
+    torch.manual_seed(21)
+    spec = create_model_spec(input_size=(16, 16), input_channels=1, output_size=(64, 64), output_channels=1)
+    return Encoder(spec.get_input_layers(), 4, 16), Decoder(spec.get_output_layers(), 4, 16)
+
+
+def _data():
+    g = torch.Generator().manual_seed(22)
+    return torch.rand(8, 1, 16, 16, generator=g), torch.rand(8, 1, 64, 64, generator=g)
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from cae_tools_b200.engine.convae import ConvAEEngine
+    from cae_tools_b200.engine.dp import DPContext
+    dp = DPContext.from_env()
+    enc, dec = _models()
+    x, y = _data()
+    eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=torch.device("cuda", rank),
+                       grad_hook=dp.allreduce_grads, count_scale=1.0 / world)
+    data = eng.bind(x, y, 8)
+    losses = []
+    for _ in range(4):
+        l = eng.train_epoch(data)
+        losses.append(float(dp.reduce_losses(l).cpu()[0]))
+    if rank == 0:
+        sd = {k: v.detach().cpu().numpy() for k, v in list(enc.state_dict().items()) + list(dec.state_dict().items())}
+        np.savez(os.path.join(out_dir, "dp.npz"), losses=np.array(losses), **{k.replace(".", "_"): v for k, v in sd.items()})
+    dist.destroy_process_group()
+
+
+def test_two_rank_nccl_equals_single_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = dict(np.load(os.path.join(str(tmp_path), "dp.npz")))
+    from cae_tools_b200.engine.convae import ConvAEEngine
+    enc, dec = _models()
+    x, y = _data()
+    eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5)
+    data = eng.bind(x.repeat(2, 1, 1, 1), y.repeat(2, 1, 1, 1), 16)
+    ref = [float(eng.train_epoch(data).cpu()[0]) for _ in range(4)]
+    np.testing.assert_allclose(got["losses"], ref, rtol=2e-5)
+    for k, v in list(enc.state_dict().items()) + list(dec.state_dict().items()):
+        a, b = got[k.replace(".", "_")], v.detach().cpu().numpy()
+        if k.endswith("running_var"):
+            continue   # local BN: the unbiased correction M/(M-1) uses the per-rank element count
+        if a.dtype.kind == "f":
+            assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-3), k

@@ -23,7 +23,7 @@ class CaeView(C.Structure):
 
 class CaeSrc(C.Structure):
     _fields_ = [("t0", CaeView), ("t1", C.c_void_p), ("k0", C.c_void_p), ("k1", C.c_void_p), ("k2", C.c_void_p),
-                ("relu", C.c_int), ("cursor", C.c_void_p), ("cursor_stride", C.c_longlong)]
+                ("relu", C.c_int), ("cursor", C.c_void_p), ("cursor_stride", C.c_longlong), ("kn", C.c_void_p)]
 
 
 class CaeConvGeom(C.Structure):
@@ -42,7 +42,7 @@ class CaeBN(C.Structure):
 class CaeEpilogue(C.Structure):
     _fields_ = [("mode", C.c_int), ("bias", C.c_void_p), ("partials", C.c_void_p), ("ticket", C.c_void_p),
                 ("bn", CaeBN), ("act", CaeView), ("target", CaeSrc), ("loss_out", C.c_void_p),
-                ("dbias", C.c_void_p), ("write_mode", C.c_int), ("count_scale", C.c_float)]
+                ("dbias", C.c_void_p), ("write_mode", C.c_int), ("count_scale", C.c_float), ("addend", CaeSrc)]
 
 
 class CaeGemm(C.Structure):
@@ -55,7 +55,7 @@ class CaeGemm(C.Structure):
                 ("bias", C.c_void_p), ("relu_out", C.c_int), ("mask", C.c_void_p), ("rowsum_A", C.c_void_p)]
 
 
-EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE = 0, 1, 2, 3, 4
+EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_MASK = 0, 1, 2, 3, 4, 5
 
 # every symbol include/cae_b200.h declares
 EXPORTS = {
@@ -83,6 +83,17 @@ EXPORTS = {
     "cae_vae_reparam_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cae_add2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cae_plane_stats": (C.c_int, [C.POINTER(CaeView), C.c_void_p, C.c_void_p]),
+    "cae_channel_attention_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cae_channel_attention_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p] * 5),
+    "cae_plane_dot": (C.c_int, [C.POINTER(CaeSrc), C.POINTER(CaeView), C.c_void_p, C.c_void_p]),
+    "cae_gate_bwd": (C.c_int, [C.POINTER(CaeSrc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CaeView),
+                               C.c_void_p, C.c_void_p]),
+    "cae_sum_over_n": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cae_masked_pearson_loss": (C.c_int, [C.POINTER(CaeView), C.POINTER(CaeSrc), C.POINTER(CaeSrc), C.c_int, C.c_float,
+                                          C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(CaeView), C.c_void_p, C.c_void_p]),
     "cae_randn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
 }
 

@@ -8,6 +8,7 @@
 #include "conv_tiled.cuh"
 #include "conv_direct.cuh"
 #include "dense_misc.cuh"
+#include "unet_ops.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -42,7 +43,16 @@ static int check_view(const CaeView& v, const char* name) {
 }
 
 static int check_epilogue(const CaeEpilogue& e, const CaeView& out) {
-    CAE_REQUIRE(e.mode >= CAE_EPI_PLAIN && e.mode <= CAE_EPI_SIGMOID_MSE, "epilogue: bad mode %d", e.mode);
+    CAE_REQUIRE(e.mode >= CAE_EPI_PLAIN && e.mode <= CAE_EPI_MASK, "epilogue: bad mode %d", e.mode);
+    if (e.mode == CAE_EPI_MASK) {
+        CAE_REQUIRE(e.act.p && e.act.N == out.N && e.act.C == out.C && e.act.H == out.H && e.act.W == out.W,
+                    "epilogue MASK: act view missing or of a different geometry");
+    }
+    if (e.addend.t0.p) {
+        const CaeView& av = e.addend.t0;
+        CAE_REQUIRE(av.N == out.N && av.C == out.C && av.H == out.H && av.W == out.W,
+                    "epilogue: addend geometry differs from output");
+    }
     if (epi_reduces(e.mode)) {
         CAE_REQUIRE(e.partials && e.ticket, "epilogue: reducing mode needs partials + ticket");
     }
@@ -125,6 +135,7 @@ static int fill_conv_args(ConvArgs& a, const CaeSrc* in, const float* weight, co
     CAE_REQUIRE(g->kh > 0 && g->kw > 0 && g->stride > 0 && g->pad >= 0, "conv: bad geometry k=%dx%d s=%d p=%d", g->kh,
                 g->kw, g->stride, g->pad);
     CAE_REQUIRE(in->t0.N == out->N, "conv: batch mismatch %d vs %d", in->t0.N, out->N);
+    CAE_REQUIRE(in->kn == nullptr, "conv: per-(n,c) multipliers (kn) are only supported by cae_ew_epilogue");
     memset(&a, 0, sizeof(a));
     a.in = *in;
     a.w = weight;
@@ -347,12 +358,13 @@ extern "C" int cae_conv_up(const CaeSrc* in, const float* weight, const CaeConvG
                 "conv_up: output %dx%d inconsistent with input %dx%d k=%dx%d s=%d p=%d", out->H, out->W, iv.H, iv.W,
                 a.kh, a.kw, a.s, a.p);
     cudaStream_t st = (cudaStream_t)stream;
-    if (a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+    const bool v1_only_up = a.epi.addend.t0.p != nullptr || a.epi.mode == CAE_EPI_MASK;   // features of the generic epilogue
+    if (!v1_only_up && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
         bool handled = false;
         rc = (a.kh == 3) ? launch_up3<3>(a, st, handled) : launch_up3<4>(a, st, handled);
         if (handled) return rc;
     }
-    if (g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+    if (!v1_only_up && g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
         bool handled = false;
         rc = (a.kh == 3) ? launch_up2<3, 3>(a, st, handled) : launch_up2<4, 4>(a, st, handled);
         if (handled) return rc;
@@ -386,12 +398,13 @@ extern "C" int cae_conv_down(const CaeSrc* in, const float* weight, const CaeCon
     cudaStream_t st = (cudaStream_t)stream;
     a.QH = out->H; a.QW = out->W;
     a.total = out->N * out->H * out->W;
-    if (a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+    const bool v1_only_dn = a.epi.addend.t0.p != nullptr || a.epi.mode == CAE_EPI_MASK;
+    if (!v1_only_dn && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
         bool handled = false;
         rc = (a.kh == 3) ? launch_down3<3>(a, st, handled) : launch_down3<4>(a, st, handled);
         if (handled) return rc;
     }
-    if (g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+    if (!v1_only_dn && g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
         bool handled = false;
         rc = (a.kh == 3) ? launch_down2<3, 3>(a, st, handled) : launch_down2<4, 4>(a, st, handled);
         if (handled) return rc;
@@ -735,4 +748,93 @@ extern "C" int cae_randn(float* out, long long n, unsigned long long seed, const
     CAE_REQUIRE(out && n > 0, "randn: bad argument");
     k_randn<<<min(ceil_div(n, CAE_NT), CAE_NUM_SMS * 4), CAE_NT, 0, (cudaStream_t)stream>>>(out, n, seed, step_count);
     return cae_check_launch("cae_randn");
+}
+
+// ---- UNET pieces ---------------------------------------------------------------------------------------
+extern "C" int cae_plane_stats(const CaeView* y, float* stats, void* stream) {
+    CAE_REQUIRE(y && stats, "plane_stats: null argument");
+    int rc = check_view(*y, "plane_stats input");
+    if (rc) return rc;
+    k_plane_stats<<<y->N * y->C, CAE_NT, 0, (cudaStream_t)stream>>>(*y, stats);
+    return cae_check_launch("cae_plane_stats");
+}
+
+extern "C" int cae_channel_attention_fwd(const float* stats, const float* W1, const float* W2, int N, int C, int Cr, int HW,
+                                         float* att, float* hid, void* stream) {
+    CAE_REQUIRE(stats && W1 && W2 && att && hid && N > 0 && C > 0 && Cr > 0 && HW > 0, "channel_attention_fwd: bad argument");
+    size_t smem = (size_t)(2 * C + 2 * Cr) * 4;
+    CAE_REQUIRE(smem <= 48 * 1024, "channel_attention_fwd: %d channels do not fit", C);
+    k_ca_fwd<<<N, CAE_NT, smem, (cudaStream_t)stream>>>(stats, W1, W2, C, Cr, 1.f / (float)HW, att, hid);
+    return cae_check_launch("cae_channel_attention_fwd");
+}
+
+extern "C" int cae_channel_attention_bwd(const float* datt, const float* att, const float* hid, const float* stats,
+                                         const float* W1, const float* W2, int N, int C, int Cr, int HW, float* dW1,
+                                         float* dW2, float* davg, float* dmax, void* stream) {
+    CAE_REQUIRE(datt && att && hid && stats && W1 && W2 && dW1 && dW2 && davg && dmax && N > 0 && C > 0 && Cr > 0,
+                "channel_attention_bwd: bad argument");
+    size_t smem = (size_t)(3 * C + 2 * Cr) * 4;
+    CAE_REQUIRE(smem <= 48 * 1024, "channel_attention_bwd: %d channels do not fit", C);
+    k_ca_bwd<<<1, CAE_NT, smem, (cudaStream_t)stream>>>(datt, att, hid, stats, W1, W2, N, C, Cr, 1.f / (float)HW, dW1,
+                                                          dW2, davg, dmax);
+    return cae_check_launch("cae_channel_attention_bwd");
+}
+
+extern "C" int cae_plane_dot(const CaeSrc* g, const CaeView* y, float* out, void* stream) {
+    CAE_REQUIRE(g && y && out, "plane_dot: null argument");
+    CAE_REQUIRE(g->t0.N == y->N && g->t0.C == y->C && g->t0.H == y->H && g->t0.W == y->W, "plane_dot: geometry mismatch");
+    k_plane_dot<<<y->N * y->C, CAE_NT, 0, (cudaStream_t)stream>>>(*g, *y, out);
+    return cae_check_launch("cae_plane_dot");
+}
+
+extern "C" int cae_gate_bwd(const CaeSrc* g, const float* att, const float* davg, const float* dmax, const float* stats,
+                            const CaeView* dy, float* plane_sum, void* stream) {
+    CAE_REQUIRE(g && att && davg && dmax && stats && dy, "gate_bwd: null argument");
+    CAE_REQUIRE(g->t0.N == dy->N && g->t0.C == dy->C && g->t0.H == dy->H && g->t0.W == dy->W, "gate_bwd: geometry mismatch");
+    k_gate_bwd<<<dy->N * dy->C, CAE_NT, 0, (cudaStream_t)stream>>>(*g, att, davg, dmax, stats, *dy, plane_sum);
+    return cae_check_launch("cae_gate_bwd");
+}
+
+extern "C" int cae_sum_over_n(const float* in, int N, int C, float* out, void* stream) {
+    CAE_REQUIRE(in && out && N > 0 && C > 0, "sum_over_n: bad argument");
+    k_sum_over_n<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(in, N, C, out);
+    return cae_check_launch("cae_sum_over_n");
+}
+
+extern "C" int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target, const CaeSrc* mask, int mask_channels,
+                                       float lambda_pearson, float count_scale, double* moments, float* coef,
+                                       float* scalars, float* loss_out, float* pearson_out, const CaeView* dz,
+                                       float* plane_sum, void* stream) {
+    CAE_REQUIRE(pred && target && moments && coef && scalars, "masked_pearson_loss: null argument");
+    int rc = check_view(*pred, "masked_pearson_loss pred");
+    if (rc) return rc;
+    const CaeView& t = target->t0;
+    CAE_REQUIRE(t.p && t.N == pred->N && t.C == pred->C && t.H == pred->H && t.W == pred->W,
+                "masked_pearson_loss: target geometry differs from prediction");
+    MaskedPearsonArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pred = *pred;
+    a.target = *target;
+    if (mask && mask->t0.p) {
+        a.mask = *mask;
+        CAE_REQUIRE((mask_channels == 1 || mask_channels == pred->C) && mask->t0.C == mask_channels &&
+                        mask->t0.H == pred->H && mask->t0.W == pred->W && mask->t0.N == pred->N,
+                    "masked_pearson_loss: mask must be [N, 1 or C, H, W]");
+        a.mask_channels = mask_channels;
+    } else {
+        a.mask_channels = pred->C;
+    }
+    a.moments = moments; a.coef = coef; a.scalars = scalars;
+    a.loss_out = loss_out; a.pearson_out = pearson_out;
+    a.lambda_pearson = lambda_pearson; a.count_scale = count_scale;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int planes = pred->N * pred->C;
+    k_mp_moments<<<planes, CAE_NT, 0, st>>>(a);
+    k_mp_finalize<<<1, CAE_NT, 0, st>>>(a);
+    if (dz) {
+        CAE_REQUIRE(dz->p && dz->N == pred->N && dz->C == pred->C && dz->H == pred->H && dz->W == pred->W,
+                    "masked_pearson_loss: dz geometry differs from prediction");
+        k_mp_grad<<<planes, CAE_NT, 0, st>>>(a, *dz, plane_sum);
+    }
+    return cae_check_launch("cae_masked_pearson_loss");
 }

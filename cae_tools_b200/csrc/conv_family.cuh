@@ -21,6 +21,7 @@ struct ConvArgs {
 struct EpiCh {
     float bias, scale, shift, mean, invstd;
     ChanCoef tk;
+    ChanCoef ak;   // addend coefficients
 };
 
 __device__ __forceinline__ EpiCh epi_load_channel(const CaeEpilogue& e, int co, bool ok) {
@@ -35,6 +36,8 @@ __device__ __forceinline__ EpiCh epi_load_channel(const CaeEpilogue& e, int co, 
         c.invstd = e.bn.invstd[co];
     }
     if (ok && e.mode == CAE_EPI_SIGMOID_MSE) c.tk = load_coef(e.target, co);
+    c.ak.k0 = 1.f; c.ak.k1 = 0.f; c.ak.k2 = 0.f;
+    if (ok && e.addend.t0.p) c.ak = load_coef(e.addend, co);
     return c;
 }
 
@@ -43,10 +46,19 @@ __device__ __forceinline__ void epi_element(const CaeEpilogue& e, const CaeView&
                                             int oy, int ox, float acc, long long tgt_base, float inv_count,
                                             float& s1, float& s2) {
     const long long off = (long long)n * out.sN + (long long)co * out.sC + (long long)oy * out.ld + ox;
+    if (e.addend.t0.p) {
+        const CaeView& av = e.addend.t0;
+        acc += src_value(e.addend, (long long)n * av.sN + (long long)co * av.sC + (long long)oy * av.ld + ox, ch.ak);
+    }
     switch (e.mode) {
         case CAE_EPI_PLAIN:
             out.p[off] = acc + ch.bias;
             break;
+        case CAE_EPI_MASK: {
+            const CaeView& a = e.act;
+            float yp = __ldg(a.p + (long long)n * a.sN + (long long)co * a.sC + (long long)oy * a.ld + ox);
+            out.p[off] = yp > 0.f ? acc : 0.f;
+        } break;
         case CAE_EPI_STATS: {
             float v = acc + ch.bias;
             out.p[off] = v;
@@ -442,7 +454,9 @@ __global__ void __launch_bounds__(CAE_NT) k_ew_epilogue(const ConvArgs a) {
             int r = g - n * (a.QH * a.QW);
             int oy = r / a.QW, ox = r - oy * a.QW;
             long long off = in_base + (long long)n * iv.sN + (long long)co * iv.sC + (long long)oy * iv.ld + ox;
-            float v = src_value(a.in, off, kc);
+            ChanCoef kk = kc;
+            if (a.in.kn) kk.k0 *= __ldg(a.in.kn + (size_t)n * iv.C + co);
+            float v = src_value(a.in, off, kk);
             epi_element(a.epi, a.out, ech, n, co, oy, ox, v, tgt_base, a.inv_count, s1[0], s2[0]);
         }
     }

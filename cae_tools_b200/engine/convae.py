@@ -450,6 +450,10 @@ class ConvAEEngine:
                 prog.run()
         return self.batch_losses(data)
 
+    def output_buffer(self, b):
+        """buffer that holds the prediction after a "score" program ran"""
+        return b["y_d"][-1]
+
     def score_batches(self, data, sink):
         """eval-mode forward of every batch; sink(batch_index, yhat[N,C,H,W] device view) consumes each output"""
         self._eval_prepare_op()()
@@ -460,7 +464,7 @@ class ConvAEEngine:
             prog = self._program("score", data, N)
             for _ in range(count):
                 prog.run()
-                sink(idx, b["y_d"][-1][:N])
+                sink(idx, self.output_buffer(b)[:N])
                 idx += 1
 
     def encode_decode(self, data):

@@ -10,7 +10,7 @@ import ctypes as C
 
 import torch
 
-from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeGemm, CaeSrc, CaeView, EPI_MASKSTATS, EPI_PLAIN,
+from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeGemm, CaeSrc, CaeView, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
                     EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
 
 __all__ = ["view4", "make_src", "make_bn", "make_epilogue", "geom", "conv_up", "conv_down", "conv_wgrad",
@@ -42,12 +42,12 @@ def view4(t: torch.Tensor, n=None) -> CaeView:
     return v
 
 
-def make_src(t0, t1=None, k0=None, k1=None, k2=None, relu=False, cursor=None, cursor_stride=0, n=None) -> CaeSrc:
+def make_src(t0, t1=None, k0=None, k1=None, k2=None, relu=False, cursor=None, cursor_stride=0, n=None, kn=None) -> CaeSrc:
     if t1 is not None:
         assert t1.shape == t0.shape and t1.stride() == t0.stride(), "t1 must share t0's geometry"
     s = CaeSrc(view4(t0, n), _ptr(t1), _ptr(k0), _ptr(k1), _ptr(k2), int(bool(relu)), _ptr(cursor),
-               int(cursor_stride))
-    s._keep = (t0, t1, k0, k1, k2, cursor)
+               int(cursor_stride), _ptr(kn))
+    s._keep = (t0, t1, k0, k1, k2, cursor, kn)
     return s
 
 
@@ -67,7 +67,7 @@ _NULL_BN = CaeBN()
 
 
 def make_epilogue(mode, bias=None, partials=None, ticket=None, bn=None, act=None, target=None, loss_out=None,
-                  dbias=None, write_mode=0, n=None, count_scale=1.0) -> CaeEpilogue:
+                  dbias=None, write_mode=0, n=None, count_scale=1.0, addend=None) -> CaeEpilogue:
     e = CaeEpilogue()
     e.mode = int(mode)
     e.bias = _ptr(bias)
@@ -83,7 +83,9 @@ def make_epilogue(mode, bias=None, partials=None, ticket=None, bn=None, act=None
     e.dbias = _ptr(dbias)
     e.write_mode = int(write_mode)
     e.count_scale = float(count_scale)
-    e._keep = (bias, partials, ticket, bn, act, target, loss_out, dbias)
+    if addend is not None:
+        e.addend = addend
+    e._keep = (bias, partials, ticket, bn, act, target, loss_out, dbias, addend)
     return e
 
 
@@ -182,3 +184,41 @@ def randn(out, n, seed, step_count):
 def set_kernel_generation(gen: int):
     """1: generic direct kernels only; 2 (default): tiled shared-memory kernels where they apply"""
     lib().cae_set_kernel_generation(int(gen))
+
+
+# ---- UNET pieces -------------------------------------------------------------------------------------
+def plane_stats(y_view: CaeView, stats):
+    check(lib().cae_plane_stats(C.byref(y_view), _ptr(stats), _stream()), "cae_plane_stats")
+
+
+def channel_attention_fwd(stats, W1, W2, N, Cn, Cr, HW, att, hid):
+    check(lib().cae_channel_attention_fwd(_ptr(stats), _ptr(W1), _ptr(W2), int(N), int(Cn), int(Cr), int(HW), _ptr(att),
+                                          _ptr(hid), _stream()), "cae_channel_attention_fwd")
+
+
+def channel_attention_bwd(datt, att, hid, stats, W1, W2, N, Cn, Cr, HW, dW1, dW2, davg, dmax):
+    check(lib().cae_channel_attention_bwd(_ptr(datt), _ptr(att), _ptr(hid), _ptr(stats), _ptr(W1), _ptr(W2), int(N),
+                                          int(Cn), int(Cr), int(HW), _ptr(dW1), _ptr(dW2), _ptr(davg), _ptr(dmax),
+                                          _stream()), "cae_channel_attention_bwd")
+
+
+def plane_dot(g: CaeSrc, y_view: CaeView, out):
+    check(lib().cae_plane_dot(C.byref(g), C.byref(y_view), _ptr(out), _stream()), "cae_plane_dot")
+
+
+def gate_bwd(g: CaeSrc, att, davg, dmax, stats, dy_view: CaeView, plane_sum):
+    check(lib().cae_gate_bwd(C.byref(g), _ptr(att), _ptr(davg), _ptr(dmax), _ptr(stats), C.byref(dy_view),
+                             _ptr(plane_sum), _stream()), "cae_gate_bwd")
+
+
+def sum_over_n(inp, N, Cn, out):
+    check(lib().cae_sum_over_n(_ptr(inp), int(N), int(Cn), _ptr(out), _stream()), "cae_sum_over_n")
+
+
+def masked_pearson_loss(pred: CaeView, target: CaeSrc, mask, mask_channels, lambda_pearson, count_scale, moments, coef,
+                        scalars, loss_out, pearson_out, dz=None, plane_sum=None):
+    check(lib().cae_masked_pearson_loss(C.byref(pred), C.byref(target), C.byref(mask) if mask is not None else None,
+                                        int(mask_channels), float(lambda_pearson), float(count_scale), _ptr(moments),
+                                        _ptr(coef), _ptr(scalars), _ptr(loss_out), _ptr(pearson_out),
+                                        C.byref(dz) if dz is not None else None, _ptr(plane_sum), _stream()),
+          "cae_masked_pearson_loss")

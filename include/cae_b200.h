@@ -53,6 +53,8 @@ typedef struct CaeSrc {
     int           relu;
     const int*    cursor;
     long long     cursor_stride;
+    const float*  kn;             /* optional per-(sample, channel) multiplier of the t0 term, [N][C] (channel-attention
+                                     gate, unet.py:158-159); honoured by cae_ew_epilogue only */
 } CaeSrc;
 
 typedef struct CaeConvGeom {
@@ -87,6 +89,7 @@ typedef struct CaeBN {
 #define CAE_EPI_MASKSTATS  2  /* out = acc * [relu mask of `act`] ; sums for BatchNorm backward     */
 #define CAE_EPI_SIGMOID    3  /* out = sigmoid(acc + bias)                                          */
 #define CAE_EPI_SIGMOID_MSE 4 /* yhat = sigmoid(acc+bias); loss += (yhat-t)^2 ; out = dL/d(acc)     */
+#define CAE_EPI_MASK       5  /* out = acc * [act > 0]  (ReLU backward without a BatchNorm)         */
 
 typedef struct CaeEpilogue {
     int            mode;
@@ -105,6 +108,8 @@ typedef struct CaeEpilogue {
     float          count_scale;   /* loss and dL/d(acc) are multiplied by this (0 means 1): N_local/N_global when the
                                      batch is sharded over ranks, so that SUM-all-reduced gradients and losses are
                                      those of the global batch */
+    CaeSrc         addend;        /* optional (addend.t0.p != NULL): a second gradient of the output's geometry added to acc
+                                     before the epilogue acts - the skip-connection fan-in of the UNET encoder */
 } CaeEpilogue;
 
 const char* cae_last_error(void);
@@ -180,6 +185,32 @@ int cae_adam(float* p, const float* g, float* m, float* v, long long n, float lr
              float eps, float weight_decay, int decoupled, float grad_scale, const int* step_count, void* stream);
 /* end-of-step bookkeeping: step_count[0] += 1 ; if cursor: cursor[0] = (cursor[0]+1) % n_batches */
 int cae_step_advance(int* step_count, int* cursor, int n_batches, void* stream);
+
+/* ---- UNET pieces (reference: src/cae_tools/models/unet.py) -------------------------------------------
+ * plane = one (n, c) image.  cae_plane_stats: stats[(n*C+c)*4 + {0..3}] = sum, sum of squares, max, argmax
+ *   (AdaptiveAvgPool2d / AdaptiveMaxPool2d of ChannelAttention, unet.py:26-27, and the BatchNorm sums of the gate)
+ * cae_channel_attention_fwd: att = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max))  (unet.py:35-39); hid keeps the
+ *   two hidden vectors per sample for the backward pass ([N][2][Cr])
+ * cae_channel_attention_bwd: gradients of W1 [Cr][C], W2 [C][Cr] and of avg (per pixel) / max per plane
+ * cae_plane_dot: out[n,c] = sum_hw g * y ; cae_gate_bwd: dy = att*g + davg + dmax*[argmax], plane sums of dy
+ * cae_sum_over_n: out[c] = sum_n in[n][c] */
+int cae_plane_stats(const CaeView* y, float* stats, void* stream);
+int cae_channel_attention_fwd(const float* stats, const float* W1, const float* W2, int N, int C, int Cr, int HW,
+                              float* att, float* hid, void* stream);
+int cae_channel_attention_bwd(const float* datt, const float* att, const float* hid, const float* stats,
+                              const float* W1, const float* W2, int N, int C, int Cr, int HW, float* dW1, float* dW2,
+                              float* davg, float* dmax, void* stream);
+int cae_plane_dot(const CaeSrc* g, const CaeView* y, float* out, void* stream);
+int cae_gate_bwd(const CaeSrc* g, const float* att, const float* davg, const float* dmax, const float* stats,
+                 const CaeView* dy, float* plane_sum, void* stream);
+int cae_sum_over_n(const float* in, int N, int C, float* out, void* stream);
+/* masked MSE + lambda * (1 - mean Pearson) (unet.py:314-320,635-678): pred = sigmoid output; mask may be absent
+ * (mask->t0.p NULL = ones) and has 1 or C channels.  Writes loss_out[slot] = masked MSE, pearson_out[slot] =
+ * 1 - mean corr; with dz != NULL also dL/d(pre-sigmoid) and its plane sums (bias gradient pieces).
+ * moments: N*C*7 doubles, coef: N*C*3 floats, scalars: 3 floats of workspace. */
+int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target, const CaeSrc* mask, int mask_channels,
+                            float lambda_pearson, float count_scale, double* moments, float* coef, float* scalars,
+                            float* loss_out, float* pearson_out, const CaeView* dz, float* plane_sum, void* stream);
 
 /* ---- variational bottleneck (VarAEModel; the reference names the variant - cli/train_cae.py:32-33,42,
  * model_evaluator.py:35 - but ships no implementation: parity unpinned) --------------------------

@@ -163,6 +163,76 @@ def gen_loss_curve(name, batch_size, nr_epochs, seed=1234, n=100):
         ds_dataset.DSDataset.__getitem__ = orig_getitem
 
 
+UNET_SPEC = {
+    "input_layers": [
+        {"is_input": True, "kernel_size": 3, "stride": 2, "output_padding": 1, "input_dimensions": [1, 16, 16], "output_dimensions": [8, 8, 8]},
+        {"is_input": True, "kernel_size": 3, "stride": 2, "output_padding": 1, "input_dimensions": [8, 8, 8], "output_dimensions": [16, 4, 4]},
+        {"is_input": True, "kernel_size": 3, "stride": 2, "output_padding": 1, "input_dimensions": [16, 4, 4], "output_dimensions": [32, 2, 2]}],
+    "output_layers": [
+        {"is_input": False, "kernel_size": 4, "stride": 2, "output_padding": 1, "input_dimensions": [32, 2, 2], "output_dimensions": [16, 4, 4]},
+        {"is_input": False, "kernel_size": 4, "stride": 2, "output_padding": 1, "input_dimensions": [32, 4, 4], "output_dimensions": [8, 8, 8]},
+        {"is_input": False, "kernel_size": 8, "stride": 8, "output_padding": 0, "input_dimensions": [16, 8, 8], "output_dimensions": [1, 64, 64]}],
+}
+
+
+def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lambda_pearson=1.0):
+    """the reference's unet Encoder / Decoder / masked_mse_loss / pearson_corr_torch + AdamW, dropout 0
+    (UNET() itself cannot be constructed offline: its constructor downloads VGG weights - SURVEY section 0)"""
+    from cae_tools.models import unet as ru
+    from cae_tools.models.model_sizer import ModelSpec
+    spec = ModelSpec()
+    spec.load(UNET_SPEC)
+    torch.manual_seed(seed)
+    enc = ru.Encoder(spec.get_input_layers(), encoded_space_dim=latent, fc_size=fc, dropout_rate=0.0)
+    dec = ru.Decoder(spec.get_output_layers(), encoded_space_dim=latent, fc_size=fc, dropout_rate=0.0)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(batch, 1, 16, 16, generator=g)
+    y = torch.rand(batch, 1, 64, 64, generator=g)
+    mask = (torch.rand(batch, 1, 64, 64, generator=g) > 0.3).float() if with_mask else torch.ones(batch, 1, 64, 64)
+    out = {"x": x.numpy(), "y": y.numpy(), "mask": mask.numpy()}
+    out.update(sd_np(enc.state_dict(), "init.enc."))
+    out.update(sd_np(dec.state_dict(), "init.dec."))
+    acts, hooks = {}, []
+    for prefix, seq in (("enc", enc.encoder_cnn), ("dec", dec.decoder_conv)):
+        for idx, mod in enumerate(seq):
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                hooks.append(mod.register_forward_hook(
+                    lambda m, i, o, key=f"act.{prefix}.{idx}": acts.__setitem__(key, o.detach().clone().numpy())))
+    optim = torch.optim.AdamW(list(enc.parameters()) + list(dec.parameters()), lr=1e-3, weight_decay=1e-5)
+    enc.train(); dec.train()
+    mses, pls = [], []
+    for step in range(steps):
+        optim.zero_grad()
+        z, skip = enc(x)
+        yhat = dec(z, skip)
+        mse = ru.UNET.masked_mse_loss(None, yhat, y, mask)
+        pl = 1 - torch.mean(ru.UNET.pearson_corr_torch(None, yhat, y, mask))
+        (mse + lambda_pearson * pl).backward()
+        if step == 0:
+            out.update(acts)
+            out["z"] = z.detach().numpy().copy()
+            out["yhat"] = yhat.detach().numpy().copy()
+            for k, p in enc.named_parameters():
+                out["grad.enc." + k] = p.grad.detach().numpy().copy()
+            for k, p in dec.named_parameters():
+                out["grad.dec." + k] = p.grad.detach().numpy().copy()
+        optim.step()
+        mses.append(float(mse.detach())); pls.append(float(pl.detach()))
+    for h in hooks:
+        h.remove()
+    out["mse"] = np.array(mses); out["pearson_loss"] = np.array(pls)
+    out.update(sd_np(enc.state_dict(), f"after{steps}.enc."))
+    out.update(sd_np(dec.state_dict(), f"after{steps}.dec."))
+    enc.eval(); dec.eval()
+    with torch.no_grad():
+        z, skip = enc(x)
+        out["eval_yhat"] = dec(z, skip).numpy().copy()
+    out["spec_json"] = np.array(json.dumps(UNET_SPEC))
+    path = os.path.join(GOLD, f"unet_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path) // 1024, "KB", "mse", mses, "pearson", pls)
+
+
 def gen_chaos_envelope(seed=1234, nr_epochs=50, batch_size=10):
     """How far do the REFERENCE's own 50-epoch loss curves move when only the CPU thread count changes?
     (Adam amplifies fp32 summation-order differences; SURVEY section 7 'loss-curve chaos'.)  Uses the oracle port,
@@ -213,3 +283,5 @@ if __name__ == "__main__":
     gen_loss_curve("conv_b10_e50", batch_size=10, nr_epochs=50)
     gen_loss_curve("conv_b64_e5", batch_size=64, nr_epochs=5)
     gen_chaos_envelope()
+    gen_unet("nomask", with_mask=False)
+    gen_unet("mask", with_mask=True)

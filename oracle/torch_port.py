@@ -181,3 +181,104 @@ class OracleVarModel(OracleModel):
         with torch.no_grad():
             mu, _ = self.encode(x, False)
             return decoder_forward(self.dec, self.spec["output_layers"], mu, False)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UNET variant (reference: src/cae_tools/models/unet.py)
+# ---------------------------------------------------------------------------------------------------------------
+def masked_mse_loss(pred, target, mask):
+    """unet.py:635-639"""
+    diff = (pred - target) * mask
+    return torch.sum(diff ** 2) / torch.sum(mask)
+
+
+def pearson_corr(pred, target, mask):
+    """unet.py:641-678: masked Pearson correlation per (sample, channel)"""
+    d = pred.reshape(pred.size(0), pred.size(1), -1)
+    t = target.reshape(target.size(0), target.size(1), -1)
+    m = mask.reshape(mask.size(0), mask.size(1), -1).float()
+    msum = torch.sum(m, dim=2, keepdim=True)
+    mean_d = torch.sum(d * m, dim=2, keepdim=True) / (msum + 1e-8)
+    mean_t = torch.sum(t * m, dim=2, keepdim=True) / (msum + 1e-8)
+    std_d = torch.sqrt(torch.sum(m * (d - mean_d) ** 2, dim=2, keepdim=True) / (msum + 1e-8) + 1e-8)
+    std_t = torch.sqrt(torch.sum(m * (t - mean_t) ** 2, dim=2, keepdim=True) / (msum + 1e-8) + 1e-8)
+    num = torch.sum(m * ((d - mean_d) / std_d) * ((t - mean_t) / std_t), dim=2)
+    return num / torch.sum(m, dim=2)
+
+
+def unet_forward(enc, dec, spec, x, training, trace=None):
+    """Encoder.forward unet.py:102-112 + Decoder.forward unet.py:149-163 with dropout p = 0"""
+    skips = []
+    for i, sp in enumerate(spec["input_layers"]):
+        x = F.conv2d(x, enc[f"encoder_cnn.{4 * i}.weight"], enc[f"encoder_cnn.{4 * i}.bias"], stride=sp["stride"],
+                     padding=sp["output_padding"])
+        if trace is not None:
+            trace["enc"].append(x)
+        x = F.relu(_bn(x, enc, f"encoder_cnn.{4 * i + 1}", training))
+        skips.append(x)
+    skips.pop()
+    x = x.flatten(1)
+    x = F.linear(x, enc["encoder_lin.0.weight"], enc["encoder_lin.0.bias"])
+    x = F.relu(_bn(x, enc, "encoder_lin.1", training))
+    x = F.relu(F.linear(x, enc["encoder_lin.4.weight"], enc["encoder_lin.4.bias"]))
+    if trace is not None:
+        trace["z"] = x
+    x = F.linear(x, dec["decoder_lin.0.weight"], dec["decoder_lin.0.bias"])
+    x = F.relu(_bn(x, dec, "decoder_lin.1", training))
+    x = F.relu(F.linear(x, dec["decoder_lin.4.weight"], dec["decoder_lin.4.bias"]))
+    c, h, w = spec["output_layers"][0]["input_dimensions"]
+    x = x.view(-1, c, h, w)
+    skips = skips[::-1]
+    for j, sp in enumerate(spec["output_layers"]):
+        x = F.conv_transpose2d(x, dec[f"decoder_conv.{4 * j}.weight"], dec[f"decoder_conv.{4 * j}.bias"],
+                               stride=sp["stride"], padding=sp["output_padding"])
+        if trace is not None:
+            trace["dec"].append(x)
+        if j < len(skips):
+            w1, w2 = dec[f"attention_layers.{j}.fc1.weight"], dec[f"attention_layers.{j}.fc2.weight"]
+            avg, mx = x.mean(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)
+            att = torch.sigmoid(F.conv2d(F.relu(F.conv2d(avg, w1)), w2) + F.conv2d(F.relu(F.conv2d(mx, w1)), w2))
+            x = torch.cat((x * att, skips[j]), 1)
+            x = F.relu(_bn(x, dec, f"decoder_conv.{4 * j + 1}", training))
+    return torch.sigmoid(x)
+
+
+class OracleUNet:
+    """UNET.__train_epoch / __test_epoch / score (unet.py:295-380) with AdamW (unet.py:457), dropout 0"""
+
+    def __init__(self, enc_sd, dec_sd, spec, lr=1e-3, weight_decay=1e-5, lambda_pearson=1.0, zero_dead_bias_grads=False):
+        clone = lambda sd: {k: (v.detach().clone().float() if v.is_floating_point() else v.detach().clone())
+                            for k, v in sd.items()}
+        self.enc, self.dec, self.spec = clone(enc_sd), clone(dec_sd), spec
+        self.lambda_pearson = lambda_pearson
+        self.zero_dead_bias_grads = zero_dead_bias_grads
+        self.params = []
+        for sd in (self.enc, self.dec):
+            for k in trainable_keys(sd):
+                sd[k].requires_grad_(True)
+                self.params.append(sd[k])
+        self.optim = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)
+
+    def losses(self, x, y, mask, training):
+        yhat = unet_forward(self.enc, self.dec, self.spec, x, training)
+        mse = masked_mse_loss(yhat, y, mask)
+        pl = 1 - torch.mean(pearson_corr(yhat, y, mask))
+        return mse, pl, yhat
+
+    def train_step(self, x, y, mask):
+        self.optim.zero_grad()
+        mse, pl, _ = self.losses(x, y, mask, True)
+        (mse + self.lambda_pearson * pl).backward()
+        if self.zero_dead_bias_grads:
+            for k in self.enc:      # encoder convs feed a BatchNorm directly: identically zero bias gradient
+                if k.startswith("encoder_cnn") and k.endswith(".bias") and int(k.split(".")[1]) % 4 == 0:
+                    self.enc[k].grad.zero_()
+            for k in ("encoder_lin.0.bias",):
+                self.enc[k].grad.zero_()
+            self.dec["decoder_lin.0.bias"].grad.zero_()
+        self.optim.step()
+        return float(mse.detach()), float(pl.detach())
+
+    def score(self, x):
+        with torch.no_grad():
+            return unet_forward(self.enc, self.dec, self.spec, x, False)

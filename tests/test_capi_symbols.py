@@ -38,7 +38,7 @@ def test_struct_sizes_match_c_layout():
     from cae_tools_b200 import _lib
     assert ctypes.sizeof(_lib.CaeView) == 8 + 5 * 4 + 4 + 16          # ptr, 5 ints (+pad), 2 long long
     assert ctypes.sizeof(_lib.CaeConvGeom) == 16
-    assert ctypes.sizeof(_lib.CaeSrc) == ctypes.sizeof(_lib.CaeView) + 4 * 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.CaeSrc) == ctypes.sizeof(_lib.CaeView) + 4 * 8 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.CaeBN) == 16 + 15 * 8
 
 

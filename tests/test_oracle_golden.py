@@ -119,3 +119,37 @@ def test_numpy_definitions_match_torch():
             opt.step()
             p, m, v = numpy_ops.adam_step(p, gnp, m, v, t, lr=1e-2, wd=0.1, decoupled=decoupled)
             np.testing.assert_allclose(p, tp.detach().numpy(), atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["nomask", "mask"])
+def test_unet_port_matches_reference(name):
+    """oracle/torch_port.OracleUNet vs the reference's unet Encoder / Decoder / losses + AdamW (3 steps)"""
+    from oracle.torch_port import OracleUNet, unet_forward
+    g = load_npz(f"unet_{name}.npz")
+    spec = spec_of(g)
+    m = OracleUNet(split_sd(g, "init.enc."), split_sd(g, "init.dec."), spec, lambda_pearson=1.0)
+    x, y, mask = (torch.from_numpy(g[k]) for k in ("x", "y", "mask"))
+    trace = {"enc": [], "dec": []}
+    yhat = unet_forward(m.enc, m.dec, spec, x, True, trace)
+    for i, t in enumerate(trace["enc"]):
+        assert rel_err(t.detach().numpy(), g[f"act.enc.{4 * i}"]) < 1e-5
+    for j, t in enumerate(trace["dec"]):
+        assert rel_err(t.detach().numpy(), g[f"act.dec.{4 * j}"]) < 1e-5
+    assert rel_err(yhat.detach().numpy(), g["yhat"]) < 1e-5
+    # fresh model (the trace pass above advanced the BatchNorm buffers)
+    m = OracleUNet(split_sd(g, "init.enc."), split_sd(g, "init.dec."), spec, lambda_pearson=1.0)
+    mses, pls = [], []
+    for step in range(3):
+        a, b = m.train_step(x, y, mask)
+        mses.append(a)
+        pls.append(b)
+        if step == 0:
+            pass
+    np.testing.assert_allclose(mses, g["mse"], rtol=1e-5)
+    np.testing.assert_allclose(pls, g["pearson_loss"], rtol=1e-5)
+    for prefix, sd in (("enc.", m.enc), ("dec.", m.dec)):
+        for k, v in sd.items():
+            ref = g["after3." + prefix + k]
+            if ref.dtype.kind == "f":
+                assert np.abs(v.detach().numpy() - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-3), k
+    assert rel_err(m.score(x).numpy(), g["eval_yhat"]) < 2e-4

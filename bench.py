@@ -4,8 +4,11 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one optimiser step (forward + MSE + backward + Adam) on one batch of synthetic data of the named
-shape.  N>1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N` (if it is
+One "step" = one optimiser step (forward + loss + backward + Adam/AdamW) on one batch of synthetic data of the named
+shape.  Default workload: BASELINE.json configs[1] - method=unet, 16x16 -> 256x256 with skip connections, batch 64,
+fp32 (the shipped layer spec cae_tools_b200/specs/unet_16x16_256x256.json; loss = masked MSE + Pearson term, AdamW).
+`--method conv` runs the ConvAEModel geometry of configs[0] at the same batch instead; the default line also carries a
+short conv run under "conv".  N>1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N` (if it is
 not, this script re-executes itself that way): one rank per GPU, batch-sharded data parallel, the flat
 gradient arena all-reduced by NCCL inside the captured step, weak scaling (per-GPU batch fixed).
 
@@ -29,7 +32,8 @@ sys.path.insert(0, ROOT)
 BATCH = 64                 # per-GPU batch (BASELINE config 2 names batch 64)
 IN_SHAPE = (1, 16, 16)
 OUT_SHAPE = (1, 256, 256)
-LATENT, FC = 4, 16
+LATENT, FC = 4, 16         # train_cae defaults (--latent-size 4 --fc-size 16)
+UNET_SPEC = os.path.join(ROOT, "cae_tools_b200", "specs", "unet_16x16_256x256.json")
 N_BATCHES = 64             # device-resident batches that the steps cycle through (1.1 GB > 126 MB L2)
 APPLY_BATCH = 1024
 APPLY_BATCHES = 16
@@ -42,6 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--method", default="unet", choices=["unet", "conv"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
     ap.add_argument("--train-only", action="store_true", help="skip the e2e / apply legs (short runs under ncu)")
@@ -85,6 +90,12 @@ def op_bytes(name, spec, B):
     enc, dec = layer_table(spec)
     nd = len(dec)
     f = 4 * B
+    if name.startswith("fwd.head"):            # fused last layer: input + (target | yhat)
+        return f * (numel(dec[-1][0]) + numel(dec[-1][1]))
+    if name.startswith("bwd.head"):            # input, target, mask source (act) of the input gradient, its write
+        return f * (3 * numel(dec[-1][0]) + numel(dec[-1][1]))
+    if name.startswith("bwd.") and not name.endswith((".wgrad", ".dgrad")):
+        return None
     if name.startswith("fwd.convT"):
         j = int(name[len("fwd.convT"):].split("+")[0])
         b = f * (numel(dec[j][0]) + numel(dec[j][1]))
@@ -164,25 +175,43 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU leg: the oracle port of the reference's PyTorch path on the host cores
 # ----------------------------------------------------------------------------------------------------
-def cpu_train_rate(batch, steps, warmup):
+def build_modules(method):
+    """(spec, encoder, decoder) of the benchmark workload; identical construction on every rank / leg"""
     import torch
+    from cae_tools_b200.models.model_sizer import ModelSpec, create_model_spec
+    torch.manual_seed(0)
+    if method == "unet":
+        from cae_tools_b200.models.unet_modules import UNetDecoder, UNetEncoder
+        spec = ModelSpec()
+        with open(UNET_SPEC) as f:
+            spec.load(json.load(f))
+        return spec, UNetEncoder(spec.get_input_layers(), LATENT, FC, 0.0), UNetDecoder(spec.get_output_layers(), LATENT, FC, 0.0)
     from cae_tools_b200.models.decoder import Decoder
     from cae_tools_b200.models.encoder import Encoder
-    from cae_tools_b200.models.model_sizer import create_model_spec
-    from oracle.torch_port import OracleModel
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
     spec = create_model_spec(input_size=IN_SHAPE[1:], input_channels=IN_SHAPE[0], output_size=OUT_SHAPE[1:],
                              output_channels=OUT_SHAPE[0])
-    enc, dec = Encoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
-    m = OracleModel(enc.state_dict(), dec.state_dict(), spec.save())
+    return spec, Encoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
+
+
+def cpu_train_rate(method, batch, steps, warmup):
+    import torch
+    from oracle.torch_port import OracleModel, OracleUNet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    spec, enc, dec = build_modules(method)
     x, y = torch.rand(batch, *IN_SHAPE), torch.rand(batch, *OUT_SHAPE)
+    if method == "unet":
+        m = OracleUNet(enc.state_dict(), dec.state_dict(), spec.save(), lambda_pearson=1.0)
+        ones = torch.ones_like(y)
+        step = lambda: m.train_step(x, y, ones)
+    else:
+        m = OracleModel(enc.state_dict(), dec.state_dict(), spec.save())
+        step = lambda: m.train_step(x, y)
     for _ in range(warmup):
-        m.train_step(x, y)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        m.train_step(x, y)
+        step()
     dt = time.perf_counter() - t0
     ta = time.perf_counter()
     reps = max(1, steps // 4)
@@ -198,12 +227,12 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 60))      # bounded sample: ~0.15 s per step on 8 cores
-    rate, ms, cores, apply_rate = cpu_train_rate(args.batch, steps, max(1, min(args.warmup, 3)))
+    rate, ms, cores, apply_rate = cpu_train_rate(args.method, args.batch, steps, max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": "train_samples_per_sec", "value": rate, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.batch, 1),
+        "config": workload_config(args.method, args.batch, 1),
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} optimiser steps at batch {args.batch} (oracle/torch_port.py, torch CPU)"},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,10 +241,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(batch, world):
-    return {"workload": "ConvAEModel method=conv 1x16x16->1x256x256, latent 4, fc 16, k3 s2 (BASELINE config 1 "
-                        "geometry at config 2's batch 64); unet variant not built yet",
-            "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
+def workload_config(method, batch, world):
+    if method == "unet":
+        w = ("UNET method=unet 1x16x16->1x256x256 with skip connections + channel attention (BASELINE configs[1]): shipped "
+             "spec enc 8x8x8/16x4x4/32x2x2 (k3 s2 p1), dec k4 s2 p1 x2 + k32 s32 head, latent 4, fc 16, dropout 0, "
+             "loss masked-MSE + 1.0*(1 - Pearson), AdamW, fp32")
+    else:
+        w = "ConvAEModel method=conv 1x16x16->1x256x256, latent 4, fc 16, k3 s2 (BASELINE configs[0] geometry), MSE, Adam, fp32"
+    return {"workload": w, "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
             "l2": f"steps cycle through {N_BATCHES} device-resident batches "
                   f"({N_BATCHES * batch * (numel(IN_SHAPE) + numel(OUT_SHAPE)) * 4 / 1e6:.0f} MB > 126 MB L2); "
                   "no explicit flush"}
@@ -228,9 +261,6 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from cae_tools_b200.engine.convae import ConvAEEngine
-    from cae_tools_b200.models.decoder import Decoder
-    from cae_tools_b200.models.encoder import Encoder
-    from cae_tools_b200.models.model_sizer import create_model_spec
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -241,12 +271,15 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
-    torch.manual_seed(0)            # identical initial weights on every rank
-    spec = create_model_spec(input_size=IN_SHAPE[1:], input_channels=IN_SHAPE[0], output_size=OUT_SHAPE[1:],
-                             output_channels=OUT_SHAPE[0])
-    enc, dec = Encoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
+    method = args.method
+    spec, enc, dec = build_modules(method)          # identical initial weights on every rank (seed 0)
     hook = (lambda g: dist.all_reduce(g)) if world > 1 else None
-    eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=dev, grad_hook=hook, grad_scale=1.0 / world)
+    if method == "unet":
+        from cae_tools_b200.engine.unet import UNetEngine
+        eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5, device=dev,
+                         grad_hook=hook, grad_scale=1.0 / world)
+    else:
+        eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=dev, grad_hook=hook, grad_scale=1.0 / world)
 
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     X = torch.rand(N_BATCHES * B, *IN_SHAPE, device=dev, generator=gen)
@@ -330,7 +363,7 @@ def run_b200(args):
     xas = torch.empty(AB, *IN_SHAPE, device=dev)
     sadata = eng.bind(xas, None, AB)
     saprog = eng._program("score", sadata, AB)
-    yout = eng._act_buffers(AB)["y_d"][-1]
+    yout = eng.output_buffer(eng._act_buffers(AB))
 
     def apply_e2e():
         sadata.X.copy_(xah[state["i"] % 4], non_blocking=True)
@@ -376,7 +409,7 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cms, cores, arate = cpu_train_rate(B, 40, 3)
+        rate, cms, cores, arate = cpu_train_rate(method, B, 40, 3)
         cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "apply_images_per_sec": arate,
                "sample": f"40 optimiser steps at batch {B} (+10 eval batches) of the same workload, oracle port on torch CPU"}
 
@@ -384,7 +417,7 @@ def run_b200(args):
         line = {
             "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(method, B, world),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / Ke},

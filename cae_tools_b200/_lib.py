@@ -55,6 +55,13 @@ class CaeGemm(C.Structure):
                 ("bias", C.c_void_p), ("relu_out", C.c_int), ("mask", C.c_void_p), ("rowsum_A", C.c_void_p)]
 
 
+class CaePatchHead(C.Structure):
+    _fields_ = [("inp", CaeSrc), ("weight", C.c_void_p), ("bias", C.c_void_p), ("K", C.c_int), ("Cout", C.c_int),
+                ("target", CaeSrc), ("mask", CaeSrc), ("mask_channels", C.c_int), ("lambda_pearson", C.c_float),
+                ("count_scale", C.c_float), ("moments", C.c_void_p), ("coef", C.c_void_p), ("scalars", C.c_void_p),
+                ("loss_out", C.c_void_p), ("pearson_out", C.c_void_p)]
+
+
 EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_MASK = 0, 1, 2, 3, 4, 5
 
 # every symbol include/cae_b200.h declares
@@ -94,6 +101,11 @@ EXPORTS = {
     "cae_masked_pearson_loss": (C.c_int, [C.POINTER(CaeView), C.POINTER(CaeSrc), C.POINTER(CaeSrc), C.c_int, C.c_float,
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(CaeView), C.c_void_p, C.c_void_p]),
+    "cae_patch_head_supported": (C.c_int, [C.c_int] * 5),
+    "cae_patch_head_fwd": (C.c_int, [C.POINTER(CaePatchHead), C.POINTER(CaeView), C.c_void_p]),
+    "cae_patch_head_bwd": (C.c_int, [C.POINTER(CaePatchHead), C.POINTER(CaeView), C.POINTER(CaeEpilogue), C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cae_patch_head_partials_len": (C.c_longlong, [C.POINTER(CaePatchHead)]),
     "cae_randn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
 }
 

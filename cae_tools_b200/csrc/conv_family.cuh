@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(CAE_NT) k_conv_up(const ConvArgs a) {
 
 // generic-geometry fallback (any kh, kw, stride, pad): one output pixel per thread, one channel per
 // blockIdx.y, weights straight from global/L1.
-__global__ void __launch_bounds__(CAE_NT) k_conv_up_generic(const ConvArgs a) {
+static __global__ void __launch_bounds__(CAE_NT) k_conv_up_generic(const ConvArgs a) {
     const int co = blockIdx.y;
     const CaeView& iv = a.in.t0;
     const long long in_base = src_cursor_offset(a.in);
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(CAE_NT) k_conv_down(const ConvArgs a) {
     if (epi_reduces(a.epi.mode)) epi_reduce_tail<COT>(a.epi, a.out, co0, s1, s2);
 }
 
-__global__ void __launch_bounds__(CAE_NT) k_conv_down_generic(const ConvArgs a) {
+static __global__ void __launch_bounds__(CAE_NT) k_conv_down_generic(const ConvArgs a) {
     const int co = blockIdx.y;
     const CaeView& iv = a.in.t0;
     const long long in_base = src_cursor_offset(a.in);
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(CAE_NT) k_conv_down_generic(const ConvArgs a) 
 }
 
 // elementwise member: out = epilogue(in); grid.y = channel
-__global__ void __launch_bounds__(CAE_NT) k_ew_epilogue(const ConvArgs a) {
+static __global__ void __launch_bounds__(CAE_NT) k_ew_epilogue(const ConvArgs a) {
     const int co = blockIdx.y;
     const CaeView& iv = a.in.t0;
     const long long in_base = src_cursor_offset(a.in);
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(CAE_NT) k_conv_wgrad(const WgradArgs a) {
 }
 
 // generic geometry: one warp per output element (cs, cb, ky, kx)
-__global__ void __launch_bounds__(CAE_NT) k_conv_wgrad_generic(const WgradArgs a) {
+static __global__ void __launch_bounds__(CAE_NT) k_conv_wgrad_generic(const WgradArgs a) {
     const int KK = a.kh * a.kw;
     const int nelem = a.Cs * a.Cb * KK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

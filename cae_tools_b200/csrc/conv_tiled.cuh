@@ -643,7 +643,7 @@ struct WgGemmPlan {
     int KK, KW;
 };
 
-__global__ void __launch_bounds__(CAE_NT) k_wgrad2b(const WgradArgs a, const WgGemmPlan p) {
+static __global__ void __launch_bounds__(CAE_NT) k_wgrad2b(const WgradArgs a, const WgGemmPlan p) {
     __shared__ __align__(16) float As[WG_KS][WG_BM + 4];
     __shared__ __align__(16) float Bs[WG_KS][WG_BN + 4];
     const int tid = threadIdx.x;

@@ -6,7 +6,7 @@
 // C[m,n] = epi( sum_k A(m,k) B(k,n) ) with arbitrary strides; 32x32 tile, 2x2 per thread.
 // ---------------------------------------------------------------------------------------
 #define GT 32
-__global__ void __launch_bounds__(CAE_NT) k_gemm(const CaeGemm g) {
+static __global__ void __launch_bounds__(CAE_NT) k_gemm(const CaeGemm g) {
     __shared__ float As[GT][GT + 1];  // [m][k]
     __shared__ float Bs[GT][GT + 1];  // [k][n]
     __shared__ float rs[GT];
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(CAE_NT) k_gemm(const CaeGemm g) {
 
 // Skinny problems (few outputs, long K): one thread per output element, K unrolled so the (L1/L2 resident)
 // operand loads overlap.  No on-load transforms, no row sums - those stay with the tiled kernel.
-__global__ void __launch_bounds__(CAE_NT) k_gemm_skinny(const CaeGemm g) {
+static __global__ void __launch_bounds__(CAE_NT) k_gemm_skinny(const CaeGemm g) {
     const int idx = blockIdx.x * CAE_NT + threadIdx.x;
     if (idx >= g.M * g.N) return;
     const int m = idx / g.N, n = idx - m * g.N;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(CAE_NT) k_gemm_skinny(const CaeGemm g) {
 // ---------------------------------------------------------------------------------------
 // eval-mode BatchNorm: scale/shift from the running statistics; one CTA per layer
 // ---------------------------------------------------------------------------------------
-__global__ void k_bn_eval_prepare(const CaeBN* table, int count) {
+static __global__ void k_bn_eval_prepare(const CaeBN* table, int count) {
     const CaeBN bn = table[blockIdx.x];
     for (int c = threadIdx.x; c < bn.C; c += blockDim.x) {
         float invstd = 1.f / sqrtf(bn.running_var[c] + bn.eps);
@@ -133,7 +133,7 @@ __global__ void k_bn_eval_prepare(const CaeBN* table, int count) {
 // ---------------------------------------------------------------------------------------
 // MSE over flat arrays, deterministic
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAE_NT) k_mse(const float* __restrict__ a, const float* __restrict__ b, long long n,
+static __global__ void __launch_bounds__(CAE_NT) k_mse(const float* __restrict__ a, const float* __restrict__ b, long long n,
                                                 double* partials, unsigned int* ticket, float* loss_out,
                                                 const int* cursor) {
     float s = 0.f;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(CAE_NT) k_mse(const float* __restrict__ a, con
 // fused multi-tensor Adam / AdamW over the flat parameter arena
 // (update order follows torch.optim.adam._single_tensor_adam)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAE_NT) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+static __global__ void __launch_bounds__(CAE_NT) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                  float* __restrict__ v, long long n, float lr, float beta1, float beta2,
                                                  float eps, float wd, int decoupled, float gscale,
                                                  const int* step_count) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(CAE_NT) k_adam(float* __restrict__ p, const fl
     }
 }
 
-__global__ void k_step_advance(int* step_count, int* cursor, int n_batches) {
+static __global__ void k_step_advance(int* step_count, int* cursor, int n_batches) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (step_count) step_count[0] += 1;
         if (cursor) {
@@ -214,7 +214,7 @@ __global__ void k_step_advance(int* step_count, int* cursor, int n_batches) {
 // variational bottleneck: z = mu + eps * exp(logvar/2) ; KL = -1/2 sum(1 + logvar - mu^2 - exp(logvar)) / N
 // (single CTA: the latent block is N x L with L <= a few thousand)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAE_NT) k_vae_reparam_fwd(const float* __restrict__ mu, const float* __restrict__ logvar,
+static __global__ void __launch_bounds__(CAE_NT) k_vae_reparam_fwd(const float* __restrict__ mu, const float* __restrict__ logvar,
                                                             const float* __restrict__ eps, long long eps_stride,
                                                             const int* cursor, float* __restrict__ z, int n, int sample,
                                                             float inv_n, float* kl_out) {
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(CAE_NT) k_vae_reparam_fwd(const float* __restr
 }
 
 // dmu = dz + kl_w * mu ; dlogvar = dz * eps * exp(logvar/2) / 2 + kl_w * (exp(logvar) - 1) / 2,  kl_w = lambda_kl / N
-__global__ void __launch_bounds__(CAE_NT) k_vae_reparam_bwd(const float* __restrict__ dz, const float* __restrict__ mu,
+static __global__ void __launch_bounds__(CAE_NT) k_vae_reparam_bwd(const float* __restrict__ dz, const float* __restrict__ mu,
                                                             const float* __restrict__ logvar, const float* __restrict__ eps,
                                                             long long eps_stride, const int* cursor,
                                                             float* __restrict__ dmu, float* __restrict__ dlogvar, int n,
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(CAE_NT) k_vae_reparam_bwd(const float* __restr
 }
 
 // out[i] = a[i] + b[i]   (gradient fan-in of the two latent heads)
-__global__ void __launch_bounds__(CAE_NT) k_add2(const float* __restrict__ a, const float* __restrict__ b,
+static __global__ void __launch_bounds__(CAE_NT) k_add2(const float* __restrict__ a, const float* __restrict__ b,
                                                  float* __restrict__ out, long long n) {
     for (long long i = (long long)blockIdx.x * CAE_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CAE_NT)
         out[i] = a[i] + b[i];
@@ -271,7 +271,7 @@ __device__ __forceinline__ unsigned long long cae_mix64(unsigned long long x) {
     return x ^ (x >> 31);
 }
 
-__global__ void __launch_bounds__(CAE_NT) k_randn(float* __restrict__ out, long long n, unsigned long long seed,
+static __global__ void __launch_bounds__(CAE_NT) k_randn(float* __restrict__ out, long long n, unsigned long long seed,
                                                   const int* step_count) {
     const unsigned long long step = step_count ? (unsigned long long)__ldg(step_count) : 0ull;
     const unsigned long long key = cae_mix64(seed ^ cae_mix64(step + 0x51ED270B5ull));

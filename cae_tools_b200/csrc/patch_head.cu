@@ -1,0 +1,545 @@
+// "Patch head": the last layer of the UNET spec is a transposed convolution whose kernel equals its stride
+// (k32 s32 p0: 16x8x8 -> 1x256x256; reference unet.py:138-140 with torch.sigmoid unet.py:162 and the loss
+// unet.py:314-320,635-678).  Output patches do not overlap, so every output pixel has exactly one tap per input
+// channel:
+//   yhat[n,co,K*i+ky,K*j+kx] = sigmoid(b[co] + sum_ci a(n,ci,i,j) * W[ci,co,ky,kx])
+// The layer produces 99 % of the bytes of the model, so it is fused end to end:
+//   k_ph_fwd    : recomputable forward; optionally writes yhat (apply / score), optionally reads the target (+mask)
+//                 and accumulates the seven masked moments per patch row that the loss needs.  In training yhat is
+//                 never written: HBM traffic = one read of the target.
+//   k_ph_finalize: moments -> masked MSE, 1 - mean Pearson, per-plane gradient coefficients (one small CTA)
+//   k_ph_bwd    : recomputes yhat, forms dL/d(pre-sigmoid) in registers and feeds all three consumers at once -
+//                 weight gradient (register accumulators, one partial row per CTA), bias gradient and the input
+//                 gradient (warp-shuffle transpose reduction) with the ReLU-mask / BatchNorm-backward epilogue of
+//                 the previous layer.  HBM traffic = one more read of the target.
+//   k_ph_wgrad_reduce: fixed-order sum of the partial rows.
+// Thread layout: thread = one group of 4 consecutive taps (ky, kx..kx+3) of the patch; its Cin x 4 weights live in
+// registers for the whole kernel; a warp reads/writes 128-byte row segments.  K in {16, 32}, Cin <= 16.
+#include "capi_host.h"
+#include "conv_family.cuh"
+
+#define PH_CIN 16
+
+struct PhArgs {
+    CaeSrc in;
+    const float* w;
+    const float* bias;
+    int Cin, Cout, N, Hin, Win;
+    CaeView yhat;              // p == NULL: do not write
+    CaeSrc target, mask;       // target.t0.p == NULL: no loss; mask.t0.p == NULL: ones
+    int mask_channels;
+    double* moments;           // [N*Cout][Hin][7]
+    float* coef;               // [N*Cout][3]
+    float* scalars;            // [0] mse gradient factor, [1] masked mse, [2] pearson term
+    float* loss_out;
+    float* pearson_out;
+    float lambda_pearson, count_scale;
+    // backward
+    CaeView dout;              // [N, Cin, Hin, Win]
+    CaeEpilogue epi;
+    float* partials;           // [rows][Cin*Cout*K*K]
+    float* dbpart;             // [rows][Cout]
+    float* grad_w;
+    float* grad_b;
+    int rows;
+};
+
+__device__ __forceinline__ float4 ph_ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ph_sigmoid(float v) { return 1.f / (1.f + expf(-v)); }
+
+// stage the activated inputs of patch row (n, i) for one slot: s[j*PH_CIN + ci], zero for ci >= Cin
+__device__ __forceinline__ void ph_stage(const PhArgs& a, float* s, int n, int i, long long in_base, int tl, int TG) {
+    const CaeView& iv = a.in.t0;
+    for (int e = tl; e < a.Win * PH_CIN; e += TG) {
+        const int j = e / PH_CIN, ci = e - j * PH_CIN;
+        float v = 0.f;
+        if (ci < a.Cin) {
+            const ChanCoef kc = load_coef(a.in, ci);
+            v = src_value(a.in, in_base + (long long)n * iv.sN + (long long)ci * iv.sC + (long long)i * iv.ld + j, kc);
+        }
+        s[e] = v;
+    }
+}
+
+__device__ __forceinline__ void ph_preact(const float4 (&w)[PH_CIN], const float* sa, float b, float (&av)[PH_CIN],
+                                          float (&acc)[4]) {
+#pragma unroll
+    for (int q = 0; q < PH_CIN / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(sa + 4 * q);
+        av[4 * q] = t.x; av[4 * q + 1] = t.y; av[4 * q + 2] = t.z; av[4 * q + 3] = t.w;
+    }
+    acc[0] = acc[1] = acc[2] = acc[3] = b;
+#pragma unroll
+    for (int ci = 0; ci < PH_CIN; ++ci) {
+        acc[0] = fmaf(av[ci], w[ci].x, acc[0]);
+        acc[1] = fmaf(av[ci], w[ci].y, acc[1]);
+        acc[2] = fmaf(av[ci], w[ci].z, acc[2]);
+        acc[3] = fmaf(av[ci], w[ci].w, acc[3]);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
+    constexpr int TG = K * K / 4, SLOTS = CAE_NT / TG, WPS = TG / 32, TPR = K / 4;
+    extern __shared__ __align__(16) float s_a[];               // [SLOTS][Win][PH_CIN]
+    __shared__ double s_mom[SLOTS][WPS][8];
+    const int tid = threadIdx.x, slot = tid / TG, tl = tid - slot * TG, lane = tid & 31, wis = tl >> 5;
+    const int ky = tl / TPR, kx = (tl - ky * TPR) * 4;
+    const int co = blockIdx.y;
+    float4 w[PH_CIN];
+#pragma unroll
+    for (int ci = 0; ci < PH_CIN; ++ci)
+        w[ci] = ci < a.Cin ? ph_ld4(a.w + (((size_t)ci * a.Cout + co) * K + ky) * K + kx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float b = a.bias ? __ldg(a.bias + co) : 0.f;
+    const bool loss = a.target.t0.p != nullptr, has_mask = a.mask.t0.p != nullptr;
+    const long long in_base = src_cursor_offset(a.in);
+    const long long tbase = loss ? src_cursor_offset(a.target) : 0ll;
+    const long long mbase = has_mask ? src_cursor_offset(a.mask) : 0ll;
+    const CaeView& tv = a.target.t0;
+    const CaeView& mv = a.mask.t0;
+    const int mc = a.mask_channels == 1 ? 0 : co;
+    const int units = a.N * a.Hin;
+    float* sa = s_a + slot * a.Win * PH_CIN;
+    for (int u0 = blockIdx.x * SLOTS; u0 < units; u0 += gridDim.x * SLOTS) {
+        const int u = u0 + slot;
+        const bool valid = u < units;
+        const int n = valid ? u / a.Hin : 0, i = valid ? u - n * a.Hin : 0;
+        __syncthreads();
+        if (valid) ph_stage(a, sa, n, i, in_base, tl, TG);
+        __syncthreads();
+        float mo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+            const int oy = i * K + ky;
+            for (int j = 0; j < a.Win; ++j) {
+                const int ox = j * K + kx;
+                float av[PH_CIN], acc[4];
+                ph_preact(w, sa + j * PH_CIN, b, av, acc);
+                float d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = ph_sigmoid(acc[k]);
+                if (a.yhat.p)
+                    *reinterpret_cast<float4*>(a.yhat.p + (long long)n * a.yhat.sN + (long long)co * a.yhat.sC +
+                                               (long long)oy * a.yhat.ld + ox) = make_float4(d[0], d[1], d[2], d[3]);
+                if (loss) {
+                    const float4 t4 = ph_ld4(tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + ox);
+                    float4 m4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (has_mask)
+                        m4 = ph_ld4(mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + ox);
+                    const float t[4] = {t4.x, t4.y, t4.z, t4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float md = m[k] * d[k], mt = m[k] * t[k], e = (d[k] - t[k]) * m[k];
+                        mo[0] += m[k]; mo[1] += md; mo[2] += mt;
+                        mo[3] = fmaf(md, d[k], mo[3]); mo[4] = fmaf(mt, t[k], mo[4]); mo[5] = fmaf(md, t[k], mo[5]);
+                        mo[6] = fmaf(e, e, mo[6]);
+                    }
+                }
+            }
+        }
+        if (loss) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const double s = warp_sum_d((double)mo[k]);
+                if (lane == 0) s_mom[slot][wis][k] = s;
+            }
+            __syncthreads();
+            if (valid && tl < 7) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < WPS; ++q) s += s_mom[slot][q][tl];
+                a.moments[(((size_t)n * a.Cout + co) * a.Hin + i) * 7 + tl] = s;
+            }
+        }
+    }
+}
+
+// single CTA: per-plane moments (sum of the patch-row partials, in row order) -> losses + gradient coefficients.
+// Same algebra as k_mp_finalize (unet_ops.cuh).
+__global__ void __launch_bounds__(CAE_NT) k_ph_finalize(const PhArgs a) {
+    __shared__ double red[CAE_NWARP];
+    const int C = a.Cout, NC = a.N * C;
+    double sq = 0.0, cnt = 0.0, corr_sum = 0.0;
+    for (int p = threadIdx.x; p < NC; p += CAE_NT) {
+        double mo[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int r = 0; r < a.Hin; ++r)
+#pragma unroll
+            for (int k = 0; k < 7; ++k) mo[k] += a.moments[((size_t)p * a.Hin + r) * 7 + k];
+        const double M = mo[0], Md = mo[1], Mt = mo[2], Mdd = mo[3], Mtt = mo[4], Mdt = mo[5];
+        sq += mo[6];
+        if (a.mask_channels != 1 || (p % C) == 0) cnt += M;
+        const double Mp = M + 1e-8;
+        const double mu_d = Md / Mp, mu_t = Mt / Mp;
+        const double vdd = Mdd - 2.0 * mu_d * Md + mu_d * mu_d * M;
+        const double vtt = Mtt - 2.0 * mu_t * Mt + mu_t * mu_t * M;
+        const double sd = sqrt(vdd / Mp + 1e-8), st = sqrt(vtt / Mp + 1e-8);
+        const double S = (Mdt - mu_t * Md - mu_d * Mt + mu_d * mu_t * M) / st;
+        const double T = (Mt - mu_t * M) / st;
+        const double D = Md - mu_d * M;
+        const double corr = M > 0.0 ? S / (M * sd) : 0.0;
+        corr_sum += corr;
+        const double wgt = M > 0.0 ? -(double)a.lambda_pearson / ((double)NC * M * sd) : 0.0;
+        const double kk = S / (sd * sd * Mp);
+        a.coef[p * 3 + 0] = (float)(wgt / st);
+        a.coef[p * 3 + 1] = (float)(-wgt * kk);
+        a.coef[p * 3 + 2] = (float)(wgt * (-mu_t / st - T / Mp + kk * (mu_d + D / Mp)));
+    }
+    auto block_sum = [&](double v) {
+        v = warp_sum_d(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double s = 0.0;
+        for (int q = 0; q < CAE_NWARP; ++q) s += red[q];
+        return s;
+    };
+    const double SQ = block_sum(sq), CNT = block_sum(cnt), CS = block_sum(corr_sum);
+    if (threadIdx.x == 0) {
+        const double cs = a.count_scale > 0.f ? (double)a.count_scale : 1.0;
+        const double mse = SQ / CNT;
+        a.scalars[0] = (float)(2.0 / CNT * cs);
+        a.scalars[1] = (float)mse;
+        a.scalars[2] = (float)(1.0 - CS / NC);
+        const int slot = a.target.cursor ? __ldg(a.target.cursor) : 0;
+        if (a.loss_out) a.loss_out[slot] = (float)(mse * cs);
+        if (a.pearson_out) a.pearson_out[slot] = (float)((1.0 - CS / NC) * cs);
+    }
+}
+
+// 16 per-lane values -> warp sums, one channel per lane pair: lane l ends up with the sum of v[(l >> 1) & 15]
+__device__ __forceinline__ float ph_warp_transpose_sum(float (&v)[PH_CIN], int lane) {
+    float r8[8], r4[4], r2[2];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float send = hi ? v[k] : v[k + 8], keep = hi ? v[k + 8] : v[k];
+            r8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float send = hi ? r8[k] : r8[k + 4], keep = hi ? r8[k + 4] : r8[k];
+            r4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float send = hi ? r4[k] : r4[k + 2], keep = hi ? r4[k + 2] : r4[k];
+            r2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    const bool hi = lane & 2;
+    const float send = hi ? r2[0] : r2[1], keep = hi ? r2[1] : r2[0];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+template <int K>
+__global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
+    constexpr int TG = K * K / 4, SLOTS = CAE_NT / TG, WPS = TG / 32, TPR = K / 4, KK = K * K;
+    extern __shared__ __align__(16) float smem[];
+    float* s_a = smem;                                         // [SLOTS][Win][PH_CIN]
+    float* s_red = smem + SLOTS * a.Win * PH_CIN;              // [SLOTS][WPS][Win][PH_CIN]
+    __shared__ double s_db[CAE_NWARP];
+    __shared__ float s_st[CAE_NT][2];
+    const int tid = threadIdx.x, slot = tid / TG, tl = tid - slot * TG, lane = tid & 31, wis = tl >> 5;
+    const int ky = tl / TPR, kx = (tl - ky * TPR) * 4;
+    const bool has_mask = a.mask.t0.p != nullptr;
+    const long long in_base = src_cursor_offset(a.in);
+    const long long tbase = src_cursor_offset(a.target);
+    const long long mbase = has_mask ? src_cursor_offset(a.mask) : 0ll;
+    const CaeView& tv = a.target.t0;
+    const CaeView& mv = a.mask.t0;
+    const int units = a.N * a.Hin;
+    const float c0 = a.scalars[0];
+    const float cs = a.count_scale > 0.f ? a.count_scale : 1.f;
+    float* sa = s_a + slot * a.Win * PH_CIN;
+    float* sr = s_red + (size_t)slot * WPS * a.Win * PH_CIN;
+    const int my_ci = tl & (PH_CIN - 1);                       // channel this thread finishes in the input-gradient tail
+    const EpiCh ech = epi_load_channel(a.epi, min(my_ci, a.Cin - 1), my_ci < a.Cin);
+    float s1 = 0.f, s2 = 0.f;
+    const size_t nelem = (size_t)a.Cin * a.Cout * KK;
+    const int row = blockIdx.x * SLOTS + slot;
+    for (int co = 0; co < a.Cout; ++co) {
+        float4 w[PH_CIN], gw[PH_CIN];
+#pragma unroll
+        for (int ci = 0; ci < PH_CIN; ++ci) {
+            w[ci] = ci < a.Cin ? ph_ld4(a.w + (((size_t)ci * a.Cout + co) * K + ky) * K + kx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gw[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float b = a.bias ? __ldg(a.bias + co) : 0.f;
+        const int mc = a.mask_channels == 1 ? 0 : co;
+        const bool last_co = co == a.Cout - 1;
+        float dbs = 0.f;
+        for (int u0 = blockIdx.x * SLOTS; u0 < units; u0 += gridDim.x * SLOTS) {
+            const int u = u0 + slot;
+            const bool valid = u < units;
+            const int n = valid ? u / a.Hin : 0, i = valid ? u - n * a.Hin : 0;
+            __syncthreads();
+            if (valid) ph_stage(a, sa, n, i, in_base, tl, TG);
+            __syncthreads();
+            if (valid) {
+                const int plane = n * a.Cout + co;
+                const float ca = a.coef[plane * 3 + 0] * cs, cb = a.coef[plane * 3 + 1] * cs, ce = a.coef[plane * 3 + 2] * cs;
+                const int oy = i * K + ky;
+                const float* tp = tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + kx;
+                const float* mp = has_mask ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx
+                                           : nullptr;
+                float4 t_next = ph_ld4(tp);
+                float4 m_next = has_mask ? ph_ld4(mp) : make_float4(1.f, 1.f, 1.f, 1.f);
+                for (int j = 0; j < a.Win; ++j) {
+                    const float4 t4 = t_next, m4 = m_next;
+                    if (j + 1 < a.Win) {                       // prefetch the next patch's strip
+                        t_next = ph_ld4(tp + (j + 1) * K);
+                        if (has_mask) m_next = ph_ld4(mp + (j + 1) * K);
+                    }
+                    float av[PH_CIN], acc[4];
+                    ph_preact(w, sa + j * PH_CIN, b, av, acc);
+                    const float t[4] = {t4.x, t4.y, t4.z, t4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+                    float dz[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float d = ph_sigmoid(acc[k]);
+                        const float g = c0 * m[k] * m[k] * (d - t[k]) + m[k] * (ca * t[k] + cb * d + ce);
+                        dz[k] = g * d * (1.f - d);
+                        dbs += dz[k];
+                    }
+                    float part[PH_CIN];
+#pragma unroll
+                    for (int ci = 0; ci < PH_CIN; ++ci) {
+                        gw[ci].x = fmaf(av[ci], dz[0], gw[ci].x);
+                        gw[ci].y = fmaf(av[ci], dz[1], gw[ci].y);
+                        gw[ci].z = fmaf(av[ci], dz[2], gw[ci].z);
+                        gw[ci].w = fmaf(av[ci], dz[3], gw[ci].w);
+                        part[ci] = fmaf(dz[0], w[ci].x, fmaf(dz[1], w[ci].y, fmaf(dz[2], w[ci].z, dz[3] * w[ci].w)));
+                    }
+                    const float r = ph_warp_transpose_sum(part, lane);
+                    if (!(lane & 1)) sr[(wis * a.Win + j) * PH_CIN + ((lane >> 1) & 15)] = r;
+                }
+            }
+            __syncthreads();
+            if (valid) {
+                for (int e = tl; e < a.Win * PH_CIN; e += TG) {
+                    const int j = e / PH_CIN, ci = e - j * PH_CIN;      // ci == my_ci
+                    if (ci < a.Cin) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int q = 0; q < WPS; ++q) v += sr[(q * a.Win + j) * PH_CIN + ci];
+                        const long long off = (long long)n * a.dout.sN + (long long)ci * a.dout.sC + (long long)i * a.dout.ld + j;
+                        if (co > 0) v += a.dout.p[off];
+                        if (!last_co) a.dout.p[off] = v;
+                        else epi_element(a.epi, a.dout, ech, n, ci, i, j, v, 0ll, 0.f, s1, s2);
+                    }
+                }
+            }
+        }
+        // this slot's weight-gradient row
+        if (row < a.rows) {
+#pragma unroll
+            for (int ci = 0; ci < PH_CIN; ++ci)
+                if (ci < a.Cin)
+                    *reinterpret_cast<float4*>(a.partials + (size_t)row * nelem + ((size_t)ci * a.Cout + co) * KK + tl * 4) = gw[ci];
+        }
+        const double dbw = warp_sum_d((double)dbs);
+        __syncthreads();
+        if (lane == 0) s_db[tid >> 5] = dbw;
+        __syncthreads();
+        if (tl == 0 && row < a.rows) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < WPS; ++q) s += s_db[slot * WPS + q];
+            a.dbpart[(size_t)row * a.Cout + co] = (float)s;
+        }
+    }
+    if (epi_reduces(a.epi.mode)) {
+        s_st[tid][0] = s1; s_st[tid][1] = s2;
+        __syncthreads();
+        const int C = a.dout.C;
+        if (tid < 2 * PH_CIN) {
+            const int c = tid >> 1, st = tid & 1;
+            if (c < C) {
+                double s = 0.0;
+                for (int q = c; q < CAE_NT; q += PH_CIN) s += (double)s_st[q][st];
+                a.epi.partials[((size_t)blockIdx.x * C + c) * 2 + st] = s;
+            }
+        }
+        if (cae_last_block(a.epi.ticket)) {
+            const double count = (double)a.dout.N * a.dout.H * a.dout.W;
+            if (a.epi.mode == CAE_EPI_STATS) finalize_bn_forward(a.epi.bn, a.epi.partials, gridDim.x, count);
+            else if (a.epi.mode == CAE_EPI_MASKSTATS) finalize_bn_backward(a.epi.bn, a.epi.partials, gridDim.x, count);
+        }
+    }
+}
+
+// grad_w[e] = sum_rows partials[row][e] (fixed order); CTA = 64 float4 columns x 4 row groups.  CTA 0 also sums the bias rows.
+__global__ void __launch_bounds__(CAE_NT) k_ph_wgrad_reduce(const PhArgs a, long long nelem4) {
+    __shared__ float4 s_p[4][64];
+    const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const long long e4 = (long long)blockIdx.x * 64 + col;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e4 < nelem4) {
+        const float4* base = reinterpret_cast<const float4*>(a.partials) + e4;
+        int r = grp;
+        for (; r + 12 < a.rows; r += 16) {
+            const float4 v0 = __ldcg(base + (size_t)r * nelem4), v1 = __ldcg(base + (size_t)(r + 4) * nelem4);
+            const float4 v2 = __ldcg(base + (size_t)(r + 8) * nelem4), v3 = __ldcg(base + (size_t)(r + 12) * nelem4);
+            s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+            s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+            s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
+            s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+        }
+        for (; r < a.rows; r += 4) {
+            const float4 v = __ldcg(base + (size_t)r * nelem4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    s_p[grp][col] = s;
+    __syncthreads();
+    if (grp == 0 && e4 < nelem4) {
+        float4 t = s_p[0][col];
+#pragma unroll
+        for (int g = 1; g < 4; ++g) { t.x += s_p[g][col].x; t.y += s_p[g][col].y; t.z += s_p[g][col].z; t.w += s_p[g][col].w; }
+        reinterpret_cast<float4*>(a.grad_w)[e4] = t;
+    }
+    if (blockIdx.x == 0 && a.grad_b && threadIdx.x < a.Cout) {
+        double t = 0.0;
+        for (int r = 0; r < a.rows; ++r) t += (double)a.dbpart[(size_t)r * a.Cout + threadIdx.x];
+        a.grad_b[threadIdx.x] = (float)t;
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+static bool ph_plain_src(const CaeSrc& s) { return !s.t1 && !s.k0 && !s.k1 && !s.k2 && !s.relu && !s.kn; }
+
+static int ph_fill(PhArgs& a, const CaePatchHead* h) {
+    CAE_REQUIRE(h && h->weight, "patch_head: null argument");
+    int rc;
+    if ((rc = check_view(h->in.t0, "patch_head input"))) return rc;
+    memset(&a, 0, sizeof(a));
+    a.in = h->in; a.w = h->weight; a.bias = h->bias;
+    a.Cin = h->in.t0.C; a.Cout = h->Cout; a.N = h->in.t0.N; a.Hin = h->in.t0.H; a.Win = h->in.t0.W;
+    CAE_REQUIRE(h->K == 16 || h->K == 32, "patch_head: kernel %d not supported (16 or 32)", h->K);
+    CAE_REQUIRE(a.Cin <= PH_CIN && a.Cout >= 1 && a.Win <= 64, "patch_head: Cin %d (<= %d) / Cout %d / Win %d (<= 64) not supported",
+                a.Cin, PH_CIN, a.Cout, a.Win);
+    CAE_REQUIRE(h->in.kn == nullptr, "patch_head: per-(n,c) multipliers are not supported on the input");
+    CAE_REQUIRE((uintptr_t)h->weight % 16 == 0, "patch_head: weight must be 16-byte aligned");
+    a.target = h->target; a.mask = h->mask; a.mask_channels = h->mask_channels;
+    a.moments = h->moments; a.coef = h->coef; a.scalars = h->scalars;
+    a.loss_out = h->loss_out; a.pearson_out = h->pearson_out;
+    a.lambda_pearson = h->lambda_pearson; a.count_scale = h->count_scale;
+    const int Ho = h->K * a.Hin, Wo = h->K * a.Win;
+    if (a.target.t0.p) {
+        const CaeView& t = a.target.t0;
+        CAE_REQUIRE(t.N == a.N && t.C == a.Cout && t.H == Ho && t.W == Wo, "patch_head: target geometry %dx%dx%dx%d != %dx%dx%dx%d",
+                    t.N, t.C, t.H, t.W, a.N, a.Cout, Ho, Wo);
+        CAE_REQUIRE(ph_plain_src(a.target) && src_aligned(a.target), "patch_head: target must be a plain, 16-byte aligned tensor");
+        CAE_REQUIRE(a.moments && a.coef && a.scalars, "patch_head: loss workspace missing");
+        if (a.mask.t0.p) {
+            const CaeView& m = a.mask.t0;
+            CAE_REQUIRE((a.mask_channels == 1 || a.mask_channels == a.Cout) && m.C == a.mask_channels && m.N == a.N &&
+                            m.H == Ho && m.W == Wo, "patch_head: mask must be [N, 1 or C, H, W]");
+            CAE_REQUIRE(ph_plain_src(a.mask) && src_aligned(a.mask), "patch_head: mask must be a plain, 16-byte aligned tensor");
+        } else {
+            a.mask_channels = a.Cout;
+        }
+    }
+    return CAE_OK;
+}
+
+static int ph_grid(const PhArgs& a, int K, int per_sm) {
+    const int slots = CAE_NT / (K * K / 4);
+    const int units = a.N * a.Hin;
+    int gx = ceil_div(units, slots);
+    const int cap = CAE_NUM_SMS * per_sm;
+    if (gx > cap) {
+        // equal number of passes for every CTA
+        const int passes = ceil_div(gx, cap);
+        gx = ceil_div(gx, passes);
+    }
+    return gx;
+}
+
+extern "C" int cae_patch_head_supported(int K, int stride, int pad, int Cin, int Win) {
+    return (K == stride && pad == 0 && (K == 16 || K == 32) && Cin <= PH_CIN && Win <= 64) ? 1 : 0;
+}
+
+extern "C" int cae_patch_head_fwd(const CaePatchHead* h, const CaeView* yhat, void* stream) {
+    PhArgs a;
+    int rc = ph_fill(a, h);
+    if (rc) return rc;
+    const int K = h->K;
+    if (yhat && yhat->p) {
+        CAE_REQUIRE(yhat->N == a.N && yhat->C == a.Cout && yhat->H == K * a.Hin && yhat->W == K * a.Win && view_aligned(*yhat),
+                    "patch_head_fwd: yhat geometry / alignment");
+        a.yhat = *yhat;
+    }
+    CAE_REQUIRE(a.yhat.p || a.target.t0.p, "patch_head_fwd: nothing to do (no yhat, no target)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slots = CAE_NT / (K * K / 4);
+    const size_t smem = (size_t)slots * a.Win * PH_CIN * 4;
+    dim3 grid(ph_grid(a, K, 2), a.Cout);
+    if (K == 32) k_ph_fwd<32><<<grid, CAE_NT, smem, st>>>(a);
+    else k_ph_fwd<16><<<grid, CAE_NT, smem, st>>>(a);
+    if (a.target.t0.p) k_ph_finalize<<<1, CAE_NT, 0, st>>>(a);
+    return cae_check_launch("cae_patch_head_fwd");
+}
+
+extern "C" long long cae_patch_head_partials_len(const CaePatchHead* h) {
+    PhArgs a;
+    if (ph_fill(a, h)) return -1;
+    const int slots = CAE_NT / (h->K * h->K / 4);
+    const long long rows = (long long)CAE_NUM_SMS * slots;
+    return rows * ((long long)a.Cin * a.Cout * h->K * h->K + a.Cout);
+}
+
+extern "C" int cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, const CaeEpilogue* epi, float* grad_w,
+                                  float* grad_b, float* partials, void* stream) {
+    PhArgs a;
+    int rc = ph_fill(a, h);
+    if (rc) return rc;
+    CAE_REQUIRE(a.target.t0.p, "patch_head_bwd: needs the target");
+    CAE_REQUIRE(din && epi && grad_w && partials, "patch_head_bwd: null argument");
+    CAE_REQUIRE(din->p && din->N == a.N && din->C == a.Cin && din->H == a.Hin && din->W == a.Win,
+                "patch_head_bwd: input-gradient geometry differs from the input");
+    CAE_REQUIRE((uintptr_t)grad_w % 16 == 0 && (uintptr_t)partials % 16 == 0, "patch_head_bwd: grad / partials must be 16-byte aligned");
+    a.dout = *din;
+    a.epi = *epi;
+    if (a.epi.mode == CAE_EPI_MASKSTATS && a.epi.act.p == nullptr) a.epi.mode = CAE_EPI_PLAIN;
+    CAE_REQUIRE(a.epi.mode == CAE_EPI_PLAIN || a.epi.mode == CAE_EPI_MASK || a.epi.mode == CAE_EPI_MASKSTATS,
+                "patch_head_bwd: epilogue mode %d not supported", a.epi.mode);
+    CAE_REQUIRE(a.epi.addend.t0.p == nullptr && a.epi.bias == nullptr, "patch_head_bwd: addend / bias not supported");
+    if (a.epi.mode != CAE_EPI_PLAIN) {
+        const CaeView& v = a.epi.act;
+        CAE_REQUIRE(v.p && v.N == a.N && v.C == a.Cin && v.H == a.Hin && v.W == a.Win, "patch_head_bwd: act geometry");
+    }
+    if (a.epi.mode == CAE_EPI_MASKSTATS) {
+        CAE_REQUIRE(a.epi.partials && a.epi.ticket && a.epi.bn.C == a.Cin && a.epi.bn.scale && a.epi.bn.shift && a.epi.bn.mean &&
+                        a.epi.bn.invstd && a.epi.bn.bwdA && a.epi.bn.bwdB && a.epi.bn.bwdC, "patch_head_bwd: BN block incomplete");
+    }
+    const int K = h->K;
+    const int slots = CAE_NT / (K * K / 4), wps = K * K / 128;
+    const int gx = ph_grid(a, K, 1);
+    a.rows = gx * slots;
+    const long long nelem = (long long)a.Cin * a.Cout * K * K;
+    a.partials = partials;
+    a.dbpart = partials + (long long)CAE_NUM_SMS * slots * nelem;
+    a.grad_w = grad_w; a.grad_b = grad_b;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)slots * a.Win * PH_CIN * 4 * (1 + wps);
+    if (K == 32) {
+        ensure_smem(k_ph_bwd<32>);
+        k_ph_bwd<32><<<gx, CAE_NT, smem, st>>>(a);
+    } else {
+        ensure_smem(k_ph_bwd<16>);
+        k_ph_bwd<16><<<gx, CAE_NT, smem, st>>>(a);
+    }
+    k_ph_wgrad_reduce<<<ceil_div(nelem / 4, 64), CAE_NT, 0, st>>>(a, nelem / 4);
+    return cae_check_launch("cae_patch_head_bwd");
+}

@@ -20,7 +20,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
 // per-plane statistics of y: out[(n*C+c)*4 + {0,1,2,3}] = sum, sum of squares, max, argmax (pixel index as float)
 // grid = N*C planes, one CTA each.  (AdaptiveAvgPool2d(1) / AdaptiveMaxPool2d(1) of unet.py:26-27)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAE_NT) k_plane_stats(const CaeView y, float* __restrict__ out) {
+static __global__ void __launch_bounds__(CAE_NT) k_plane_stats(const CaeView y, float* __restrict__ out) {
     __shared__ double red[CAE_NWARP];
     __shared__ float smax[CAE_NWARP];
     __shared__ int sarg[CAE_NWARP];
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(CAE_NT) k_plane_stats(const CaeView y, float* 
 //   att = sigmoid( W2 relu(W1 avg) + W2 relu(W1 max) ),  W1 [Cr][C], W2 [C][Cr]   (1x1 convs without bias)
 // hid[n][0][r] = relu(W1 avg)_r, hid[n][1][r] = relu(W1 max)_r are kept for the backward pass.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAE_NT) k_ca_fwd(const float* __restrict__ stats, const float* __restrict__ W1,
+static __global__ void __launch_bounds__(CAE_NT) k_ca_fwd(const float* __restrict__ stats, const float* __restrict__ W1,
                                                     const float* __restrict__ W2, int C, int Cr, float inv_hw,
                                                     float* __restrict__ att, float* __restrict__ hid) {
     extern __shared__ float sm[];                 // avg[C], mx[C], h[2*Cr]
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(CAE_NT) k_ca_fwd(const float* __restrict__ sta
 //   in : datt[N][C] (dL/d att), att, hid, stats (avg/max), W1, W2
 //   out: dW1[Cr][C], dW2[C][Cr], davg[N][C] (already divided by H*W: gradient per pixel), dmax[N][C]
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAE_NT) k_ca_bwd(const float* __restrict__ datt, const float* __restrict__ att,
+static __global__ void __launch_bounds__(CAE_NT) k_ca_bwd(const float* __restrict__ datt, const float* __restrict__ att,
                                                     const float* __restrict__ hid, const float* __restrict__ stats,
                                                     const float* __restrict__ W1, const float* __restrict__ W2, int N, int C,
                                                     int Cr, float inv_hw, float* __restrict__ dW1, float* __restrict__ dW2,
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(CAE_NT) k_ca_bwd(const float* __restrict__ dat
 // per-plane dot product: out[n*C+c] = sum_hw g(n,c,hw) * y(n,c,hw), g read through an on-load transform
 // (dL/d att of the gate g = att * y)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAE_NT) k_plane_dot(const CaeSrc g, const CaeView y, float* __restrict__ out) {
+static __global__ void __launch_bounds__(CAE_NT) k_plane_dot(const CaeSrc g, const CaeView y, float* __restrict__ out) {
     __shared__ double red[CAE_NWARP];
     const CaeView& gv = g.t0;
     const int plane = blockIdx.x, n = plane / y.C, c = plane - n * y.C;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(CAE_NT) k_plane_dot(const CaeSrc g, const CaeV
 // dL/dy of a gated transposed-conv output: dy = att * g + davg + dmax * [pixel == argmax]
 // (g = dL/d(att*y) through an on-load transform); also the plane sums of dy (bias gradient pieces).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CAE_NT) k_gate_bwd(const CaeSrc g, const float* __restrict__ att,
+static __global__ void __launch_bounds__(CAE_NT) k_gate_bwd(const CaeSrc g, const float* __restrict__ att,
                                                       const float* __restrict__ davg, const float* __restrict__ dmax,
                                                       const float* __restrict__ stats, const CaeView dy,
                                                       float* __restrict__ plane_sum) {
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(CAE_NT) k_gate_bwd(const CaeSrc g, const float
 }
 
 // out[c] = sum_n in[n*C + c]  (fixed order)
-__global__ void k_sum_over_n(const float* __restrict__ in, int N, int C, float* __restrict__ out) {
+static __global__ void k_sum_over_n(const float* __restrict__ in, int N, int C, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
         float s = 0.f;
@@ -238,7 +238,7 @@ __device__ __forceinline__ float mp_mask(const MaskedPearsonArgs& a, long long m
     return __ldg(mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)r * mv.ld + x);
 }
 
-__global__ void __launch_bounds__(CAE_NT) k_mp_moments(const MaskedPearsonArgs a) {
+static __global__ void __launch_bounds__(CAE_NT) k_mp_moments(const MaskedPearsonArgs a) {
     __shared__ double red[CAE_NWARP];
     const CaeView& pv = a.pred;
     const CaeView& tv = a.target.t0;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(CAE_NT) k_mp_moments(const MaskedPearsonArgs a
 }
 
 // single CTA
-__global__ void __launch_bounds__(CAE_NT) k_mp_finalize(const MaskedPearsonArgs a) {
+static __global__ void __launch_bounds__(CAE_NT) k_mp_finalize(const MaskedPearsonArgs a) {
     __shared__ double red[CAE_NWARP];
     const int NC = a.pred.N * a.pred.C, C = a.pred.C;
     double sq = 0.0, cnt = 0.0, corr_sum = 0.0;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(CAE_NT) k_mp_finalize(const MaskedPearsonArgs 
     }
 }
 
-__global__ void __launch_bounds__(CAE_NT) k_mp_grad(const MaskedPearsonArgs a, const CaeView dz, float* __restrict__ plane_sum) {
+static __global__ void __launch_bounds__(CAE_NT) k_mp_grad(const MaskedPearsonArgs a, const CaeView dz, float* __restrict__ plane_sum) {
     __shared__ double red[CAE_NWARP];
     const CaeView& pv = a.pred;
     const CaeView& tv = a.target.t0;

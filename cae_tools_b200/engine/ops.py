@@ -10,7 +10,7 @@ import ctypes as C
 
 import torch
 
-from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeGemm, CaeSrc, CaeView, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
+from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeGemm, CaePatchHead, CaeSrc, CaeView, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
                     EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
 
 __all__ = ["view4", "make_src", "make_bn", "make_epilogue", "geom", "conv_up", "conv_down", "conv_wgrad",
@@ -222,3 +222,46 @@ def masked_pearson_loss(pred: CaeView, target: CaeSrc, mask, mask_channels, lamb
                                         _ptr(coef), _ptr(scalars), _ptr(loss_out), _ptr(pearson_out),
                                         C.byref(dz) if dz is not None else None, _ptr(plane_sum), _stream()),
           "cae_masked_pearson_loss")
+
+
+# ---- patch head (kernel == stride transposed conv + sigmoid + masked MSE / Pearson loss) -------------------------
+def patch_head_supported(K, stride, pad, Cin, Win) -> bool:
+    return bool(lib().cae_patch_head_supported(int(K), int(stride), int(pad), int(Cin), int(Win)))
+
+
+def make_patch_head(src: CaeSrc, weight, bias, K, Cout, target=None, mask=None, mask_channels=0, lambda_pearson=0.0,
+                    count_scale=1.0, moments=None, coef=None, scalars=None, loss_out=None, pearson_out=None) -> CaePatchHead:
+    h = CaePatchHead()
+    h.inp = src
+    h.weight = _ptr(weight)
+    h.bias = _ptr(bias)
+    h.K = int(K)
+    h.Cout = int(Cout)
+    if target is not None:
+        h.target = target
+    if mask is not None:
+        h.mask = mask
+    h.mask_channels = int(mask_channels)
+    h.lambda_pearson = float(lambda_pearson)
+    h.count_scale = float(count_scale)
+    h.moments, h.coef, h.scalars = _ptr(moments), _ptr(coef), _ptr(scalars)
+    h.loss_out, h.pearson_out = _ptr(loss_out), _ptr(pearson_out)
+    h._keep = (src, weight, bias, target, mask, moments, coef, scalars, loss_out, pearson_out)
+    return h
+
+
+def patch_head_fwd(h: CaePatchHead, yhat: CaeView = None):
+    check(lib().cae_patch_head_fwd(C.byref(h), C.byref(yhat) if yhat is not None else None, _stream()),
+          "cae_patch_head_fwd")
+
+
+def patch_head_partials_len(h: CaePatchHead) -> int:
+    n = int(lib().cae_patch_head_partials_len(C.byref(h)))
+    if n < 0:
+        check(-1, "cae_patch_head_partials_len")
+    return n
+
+
+def patch_head_bwd(h: CaePatchHead, din: CaeView, epi: CaeEpilogue, grad_w, grad_b, partials):
+    check(lib().cae_patch_head_bwd(C.byref(h), C.byref(din), C.byref(epi), _ptr(grad_w), _ptr(grad_b), _ptr(partials),
+                                   _stream()), "cae_patch_head_bwd")

@@ -127,6 +127,29 @@ class UNetEngine(ConvAEEngine):
             return ops.make_epilogue(ops.EPI_STATS, bias=bias, partials=self._partials(Cn), ticket=self._ticket(), bn=blk)
         return ops.make_epilogue(ops.EPI_PLAIN, bias=bias)
 
+    use_patch_head = True       # fused kernel==stride last layer (patch_head.cu); False = generic conv + loss kernels
+
+    def _patch_head(self, b, N, data, src, conv, sp, final):
+        """descriptor of the fused last layer when its geometry allows it (kernel == stride, pad 0), else None"""
+        k, st, pad = sp.get_kernel_size(), sp.get_stride(), sp.get_output_padding()
+        cin, hin, win = sp.get_input_dimensions()
+        if not self.use_patch_head or isinstance(k, (tuple, list)) or \
+                not ops.patch_head_supported(k, st, pad, cin, win):
+            return None
+        co = sp.get_output_dimensions()[0]
+        if final == "yhat":
+            return ops.make_patch_head(src, conv.weight, conv.bias, k, co)
+        if "ph_moments" not in b:
+            b["ph_moments"] = torch.zeros(b["yhat"].shape[0] * co * hin * 7, dtype=torch.float64, device=self.device)
+            self._keep.append(b["ph_moments"])
+        tgt = self._cursor_src(data.Y, data, N)
+        msk = self._cursor_src(data.M, data, N) if data.M is not None else None
+        mch = data.M.shape[1] if data.M is not None else co
+        return ops.make_patch_head(src, conv.weight, conv.bias, k, co, target=tgt, mask=msk, mask_channels=mch,
+                                   lambda_pearson=self.lambda_pearson, count_scale=self.count_scale,
+                                   moments=b["ph_moments"], coef=b["coef"], scalars=b["scalars"], loss_out=data.losses,
+                                   pearson_out=data.pearson)
+
     # ------------------------------------------------------------------ forward
     def _forward_ops(self, b, N, data, train, final):
         if train and self.dropout_rate > 0:
@@ -194,6 +217,15 @@ class UNetEngine(ConvAEEngine):
                 s2 = self._bn_scratch[("d", j)]
                 src = ops.make_src(cat, k0=s2[0], k2=s2[1], relu=True, n=N)
             else:
+                head = self._patch_head(b, N, data, src, conv, sp, final)
+                if head is not None:
+                    if final == "yhat":
+                        S.append((f"fwd.head{j}+sigmoid", lambda h=head, o=ops.view4(b["yhat"], N): ops.patch_head_fwd(h, o)))
+                    else:
+                        S.append((f"fwd.head{j}+sigmoid+loss", lambda h=head: ops.patch_head_fwd(h)))
+                    self._head = head if final == "loss_grad" else None
+                    return S
+                self._head = None
                 S.append((f"fwd.convT{j}+sigmoid", lambda src=src, w=conv.weight, g=g, o=ops.view4(b["yhat"], N),
                           e=ops.make_epilogue(ops.EPI_SIGMOID, bias=conv.bias): ops.conv_up(src, w, g, o, e)))
         if final != "yhat":
@@ -214,11 +246,29 @@ class UNetEngine(ConvAEEngine):
         skip_grad = {}      # encoder layer index -> CaeSrc of the gradient arriving through the skip connection
         co = self.dec_specs[-1].get_output_dimensions()[0]
         last_conv = self.dec3[-1][0]
-        S.append(("bwd.convT_last.db", lambda: ops.sum_over_n(b["psL"], N, co, G(last_conv.bias))))
+        head = getattr(self, "_head", None)
+        if head is None:
+            S.append(("bwd.convT_last.db", lambda: ops.sum_over_n(b["psL"], N, co, G(last_conv.bias))))
         for j in range(nd - 1, -1, -1):
             conv, bn, att = self.dec3[j]
             sp = self.dec_specs[j]
             g = self._geom(sp)
+            if j == nd - 1 and head is not None:
+                # fused: recompute yhat, dL/dz in registers -> weight, bias and input gradients in one pass
+                if j > 0:
+                    pbn = self.dec3[j - 1][1]
+                    blk, _ = self._bn(("d", j - 1), pbn)
+                    epi = ops.make_epilogue(ops.EPI_MASKSTATS, partials=self._partials(pbn.num_features),
+                                            ticket=self._ticket(), bn=blk, act=b["catg"][j - 1], n=N)
+                    out = ops.view4(b["dz_catg"][j - 1], N)
+                else:
+                    epi = ops.make_epilogue(ops.EPI_MASK, act=b["u"], n=N)
+                    out = ops.view4(b["du"], N)
+                part = torch.zeros(ops.patch_head_partials_len(head), dtype=torch.float32, device=self.device)
+                self._keep.append(part)
+                S.append((f"bwd.head{j}", lambda h=head, o=out, e=epi, cv=conv, part=part:
+                          ops.patch_head_bwd(h, o, e, G(cv.weight), G(cv.bias), part)))
+                continue
             if j == nd - 1:
                 dy = ops.make_src(b["dzL"], n=N)
             else:

@@ -212,6 +212,42 @@ int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target, const Cae
                             float lambda_pearson, float count_scale, double* moments, float* coef, float* scalars,
                             float* loss_out, float* pearson_out, const CaeView* dz, float* plane_sum, void* stream);
 
+/* ---- patch head: transposed convolution with kernel == stride, pad 0 (the last layer of the UNET spec, e.g. k32 s32
+ * 16x8x8 -> 1x256x256: nn.ConvTranspose2d unet.py:138-140), fused with torch.sigmoid (unet.py:162) and with
+ * masked_mse_loss + lambda * pearson (unet.py:314-320,635-678).  Non-overlapping output patches: one tap per input
+ * channel and output pixel.
+ *   cae_patch_head_fwd : yhat (written only if `yhat` is given: apply / score) and, if target.t0.p is set, the loss:
+ *                        loss_out[slot] = masked MSE, pearson_out[slot] = 1 - mean corr, gradient coefficients in
+ *                        coef / scalars for the backward call.  Training never writes yhat.
+ *   cae_patch_head_bwd : recomputes yhat, forms dL/d(pre-sigmoid) in registers and produces, in one pass over the
+ *                        target, grad_w [Cin][Cout][K][K], grad_b [Cout] and the input gradient `din` (through the
+ *                        PLAIN / MASK / MASKSTATS epilogue of the producing layer).
+ * Workspaces: moments N*Cout*Hin*7 doubles, coef N*Cout*3 floats, scalars 4 floats, partials
+ * cae_patch_head_partials_len() floats.  Supported: K in {16, 32}, Cin <= 16, Win <= 64
+ * (cae_patch_head_supported); other geometries use cae_conv_up / cae_conv_down / cae_conv_wgrad. */
+typedef struct CaePatchHead {
+    CaeSrc        in;             /* layer input [N, Cin, Hin, Win] (BatchNorm+ReLU of the producer applied on load) */
+    const float*  weight;         /* [Cin][Cout][K][K] */
+    const float*  bias;           /* [Cout] or NULL */
+    int           K;              /* kernel size == stride */
+    int           Cout;
+    CaeSrc        target;         /* [N, Cout, K*Hin, K*Win]; t0.p NULL = no loss */
+    CaeSrc        mask;           /* [N, 1 or Cout, K*Hin, K*Win]; t0.p NULL = all ones */
+    int           mask_channels;
+    float         lambda_pearson;
+    float         count_scale;    /* as CaeEpilogue.count_scale */
+    double*       moments;
+    float*        coef;
+    float*        scalars;
+    float*        loss_out;
+    float*        pearson_out;
+} CaePatchHead;
+int       cae_patch_head_supported(int K, int stride, int pad, int Cin, int Win);
+int       cae_patch_head_fwd(const CaePatchHead* h, const CaeView* yhat, void* stream);
+int       cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, const CaeEpilogue* din_epilogue, float* grad_w,
+                             float* grad_b, float* partials, void* stream);
+long long cae_patch_head_partials_len(const CaePatchHead* h);
+
 /* ---- variational bottleneck (VarAEModel; the reference names the variant - cli/train_cae.py:32-33,42,
  * model_evaluator.py:35 - but ships no implementation: parity unpinned) --------------------------
  * forward : z = mu + eps*exp(logvar/2) (sample != 0) or z = mu ; kl_out[slot] = kl_scale * KL,

@@ -175,20 +175,30 @@ UNET_SPEC = {
 }
 
 
-def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lambda_pearson=1.0):
+def unet_spec_with_head(k):
+    """UNET_SPEC with the last transposed conv replaced by a kernel == stride == k head (16x8x8 -> 1 x 8k x 8k);
+    k = 32 is the shipped 16x16 -> 256x256 spec (cae_tools_b200/specs/unet_16x16_256x256.json)"""
+    spec = json.loads(json.dumps(UNET_SPEC))
+    spec["output_layers"][-1].update(kernel_size=k, stride=k, output_dimensions=[1, 8 * k, 8 * k])
+    return spec
+
+
+def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lambda_pearson=1.0, spec_dict=None):
     """the reference's unet Encoder / Decoder / masked_mse_loss / pearson_corr_torch + AdamW, dropout 0
     (UNET() itself cannot be constructed offline: its constructor downloads VGG weights - SURVEY section 0)"""
     from cae_tools.models import unet as ru
     from cae_tools.models.model_sizer import ModelSpec
+    spec_dict = spec_dict or UNET_SPEC
+    oh, ow = spec_dict["output_layers"][-1]["output_dimensions"][1:]
     spec = ModelSpec()
-    spec.load(UNET_SPEC)
+    spec.load(spec_dict)
     torch.manual_seed(seed)
     enc = ru.Encoder(spec.get_input_layers(), encoded_space_dim=latent, fc_size=fc, dropout_rate=0.0)
     dec = ru.Decoder(spec.get_output_layers(), encoded_space_dim=latent, fc_size=fc, dropout_rate=0.0)
     g = torch.Generator().manual_seed(seed + 1)
     x = torch.rand(batch, 1, 16, 16, generator=g)
-    y = torch.rand(batch, 1, 64, 64, generator=g)
-    mask = (torch.rand(batch, 1, 64, 64, generator=g) > 0.3).float() if with_mask else torch.ones(batch, 1, 64, 64)
+    y = torch.rand(batch, 1, oh, ow, generator=g)
+    mask = (torch.rand(batch, 1, oh, ow, generator=g) > 0.3).float() if with_mask else torch.ones(batch, 1, oh, ow)
     out = {"x": x.numpy(), "y": y.numpy(), "mask": mask.numpy()}
     out.update(sd_np(enc.state_dict(), "init.enc."))
     out.update(sd_np(dec.state_dict(), "init.dec."))
@@ -227,7 +237,7 @@ def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lamb
     with torch.no_grad():
         z, skip = enc(x)
         out["eval_yhat"] = dec(z, skip).numpy().copy()
-    out["spec_json"] = np.array(json.dumps(UNET_SPEC))
+    out["spec_json"] = np.array(json.dumps(spec_dict))
     path = os.path.join(GOLD, f"unet_{name}.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path) // 1024, "KB", "mse", mses, "pearson", pls)
@@ -276,6 +286,10 @@ def gen_chaos_envelope(seed=1234, nr_epochs=50, batch_size=10):
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "unet_head":
+        # the fused kernel == stride head (patch_head.cu): k16 -> 128x128 output, masked, batch 3
+        gen_unet("head16_mask", with_mask=True, batch=3, spec_dict=unet_spec_with_head(16))
+        sys.exit(0)
     gen_specs()
     gen_layers("mini", (16, 16), (64, 64), 1, 1, batch=6)
     gen_layers("nonsquare", (12, 10), (40, 36), 1, 1, batch=5)
@@ -285,3 +299,4 @@ if __name__ == "__main__":
     gen_chaos_envelope()
     gen_unet("nomask", with_mask=False)
     gen_unet("mask", with_mask=True)
+    gen_unet("head16_mask", with_mask=True, batch=3, spec_dict=unet_spec_with_head(16))

@@ -33,14 +33,15 @@ def _dead(k):
 
 
 @pytest.mark.parametrize("use_graphs", [False, True])
-@pytest.mark.parametrize("name", ["nomask", "mask"])
+@pytest.mark.parametrize("name", ["nomask", "mask", "head16_mask"])
 def test_unet_train_steps_vs_reference(name, use_graphs):
     from cae_tools_b200.engine.unet import UNetEngine
     g = load_npz(f"unet_{name}.npz")
     spec, enc, dec = _build(g)
     eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5, use_graphs=use_graphs)
     x, y, mask = (torch.from_numpy(g[k]) for k in ("x", "y", "mask"))
-    data = eng.bind(x, y, x.shape[0], mask=mask if name == "mask" else None)
+    data = eng.bind(x, y, x.shape[0], mask=mask if name.endswith("mask") and name != "nomask" else None)
+    fused_head = name.startswith("head")       # kernel == stride last layer: patch_head.cu (never writes yhat in training)
     mses, pls = [], []
     for step in range(3):
         l = eng.train_epoch(data)
@@ -52,7 +53,10 @@ def test_unet_train_steps_vs_reference(name, use_graphs):
                 assert rel_err(t.cpu().numpy(), g[f"act.enc.{4 * i}"]) < 1e-4, f"enc conv {i}"
             for j, t in enumerate(b["y_d"]):
                 assert rel_err(t.cpu().numpy(), g[f"act.dec.{4 * j}"]) < 1e-4, f"dec convT {j}"
-            assert rel_err(b["yhat"].cpu().numpy(), g["yhat"]) < 1e-4
+            if fused_head:
+                assert eng._head is not None and float(b["yhat"].abs().max()) == 0.0
+            else:
+                assert rel_err(b["yhat"].cpu().numpy(), g["yhat"]) < 1e-4
             for prefix, mod in (("enc.", enc), ("dec.", dec)):
                 for k, p in mod.named_parameters():
                     ref = g["grad." + prefix + k]
@@ -121,3 +125,95 @@ def test_unet_model_api_train_save_load_apply(tmp_path):
     m3.spec = spec
     with pytest.raises(NotImplementedError):
         m3.train(["lowres"], "hires", tr, te)
+
+
+def _shipped_spec():
+    from cae_tools_b200.models.model_sizer import ModelSpec
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cae_tools_b200", "specs",
+                        "unet_16x16_256x256.json")
+    spec = ModelSpec()
+    spec.load(json.load(open(path)))
+    return spec, json.load(open(path))
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+@pytest.mark.parametrize("batch", [5, 64])
+def test_patch_head_k32_vs_oracle_and_generic(batch, with_mask):
+    """the shipped 16x16 -> 256x256 spec (k32 s32 head): fused head == oracle port (torch CPU) == generic kernels:
+    losses, every gradient, 2 AdamW steps, eval prediction"""
+    from cae_tools_b200.engine.unet import UNetEngine
+    from cae_tools_b200.models.unet_modules import UNetDecoder, UNetEncoder
+    from oracle.torch_port import OracleUNet
+    spec, spec_json = _shipped_spec()
+    torch.manual_seed(3)
+    gen = torch.Generator().manual_seed(17)
+    x, y = torch.rand(batch, 1, 16, 16, generator=gen), torch.rand(batch, 1, 256, 256, generator=gen)
+    mask = (torch.rand(batch, 1, 256, 256, generator=gen) > 0.25).float() if with_mask else None
+    engines = []
+    for fused in (True, False):
+        torch.manual_seed(3)
+        enc = UNetEncoder(spec.get_input_layers(), 8, 32, 0.0)
+        dec = UNetDecoder(spec.get_output_layers(), 8, 32, 0.0)
+        if fused:
+            oracle = OracleUNet(enc.state_dict(), dec.state_dict(), spec_json, lambda_pearson=0.7,
+                                zero_dead_bias_grads=True)
+        eng = UNetEngine(enc, dec, lambda_pearson=0.7, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5)
+        eng.use_patch_head = fused
+        engines.append((eng, enc, dec, eng.bind(x, y, batch, mask=mask)))
+    ones = torch.ones_like(y)
+    for step in range(2):
+        want = oracle.train_step(x, y, mask if with_mask else ones)
+        for eng, enc, dec, data in engines:
+            mse = float(eng.train_epoch(data).cpu()[0])
+            pl = float(data.pearson.cpu()[0])
+            assert abs(mse - want[0]) <= 2e-5 * want[0] and abs(pl - want[1]) <= 2e-5 * abs(want[1]), (step, mse, pl, want)
+        if step == 0:
+            assert engines[0][0]._head is not None and engines[1][0]._head is None
+            for prefix, sd in (("enc", oracle.enc), ("dec", oracle.dec)):
+                mods = [dict(e[1 if prefix == "enc" else 2].named_parameters()) for e in engines]
+                for k, ref in sd.items():
+                    if not ref.requires_grad:
+                        continue
+                    r = ref.grad.numpy()
+                    scale = max(np.abs(r).max(), 1e-7)
+                    for m in mods:
+                        got = m[k].grad.detach().cpu().numpy()
+                        assert np.abs(got - r).max() <= 2e-4 * scale + 1e-9, (prefix, k, np.abs(got - r).max(), scale)
+    ref = oracle.score(x).numpy()
+    for eng, enc, dec, data in engines:
+        out = []
+        eng.score_batches(eng.bind(x, None, batch), lambda i, yh: out.append(yh.cpu().numpy().copy()))
+        assert rel_err(out[0], ref) < 1e-3
+    # test epoch (eval-mode loss) through the fused head == through the generic kernels
+    l0 = float(engines[0][0].test_epoch(engines[0][3]).cpu()[0])
+    l1 = float(engines[1][0].test_epoch(engines[1][3]).cpu()[0])
+    assert abs(l0 - l1) <= 1e-5 * abs(l1)
+
+
+def test_patch_head_ragged_tail_and_multichannel():
+    """kernel == stride head with 2 output channels, a per-channel mask and a ragged last batch (7 = 4 + 3)"""
+    from cae_tools_b200.engine.unet import UNetEngine
+    from cae_tools_b200.models.model_sizer import ModelSpec
+    from cae_tools_b200.models.unet_modules import UNetDecoder, UNetEncoder
+    from oracle.torch_port import OracleUNet
+    _, spec_json = _shipped_spec()
+    spec_json["output_layers"][-1].update(kernel_size=16, stride=16, output_dimensions=[2, 128, 128])
+    spec = ModelSpec()
+    spec.load(spec_json)
+    gen = torch.Generator().manual_seed(5)
+    x, y = torch.rand(7, 1, 16, 16, generator=gen), torch.rand(7, 2, 128, 128, generator=gen)
+    mask = (torch.rand(7, 2, 128, 128, generator=gen) > 0.4).float()
+    torch.manual_seed(9)
+    enc = UNetEncoder(spec.get_input_layers(), 8, 32, 0.0)
+    dec = UNetDecoder(spec.get_output_layers(), 8, 32, 0.0)
+    oracle = OracleUNet(enc.state_dict(), dec.state_dict(), spec_json, lambda_pearson=1.0, zero_dead_bias_grads=True)
+    eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5)
+    data = eng.bind(x, y, 4, mask=mask)
+    for epoch in range(2):
+        got = eng.train_epoch(data).cpu().numpy()
+        want = [oracle.train_step(x[:4], y[:4], mask[:4])[0], oracle.train_step(x[4:], y[4:], mask[4:])[0]]
+        np.testing.assert_allclose(got, want, rtol=5e-5)
+    assert eng._head is not None
+    out = []
+    eng.score_batches(eng.bind(x, None, 4), lambda i, yh: out.append(yh.cpu().numpy().copy()))
+    assert rel_err(np.concatenate(out), oracle.score(x).numpy()) < 1e-3

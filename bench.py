@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--method", default="unet", choices=["unet", "conv"])
+    ap.add_argument("--n-batches", type=int, default=N_BATCHES,
+                    help="device-resident batches the steps cycle through (small values only for runs under ncu, whose "
+                         "kernel replay saves / restores all device memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
     ap.add_argument("--train-only", action="store_true", help="skip the e2e / apply legs (short runs under ncu)")
@@ -282,8 +285,9 @@ def run_b200(args):
         eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=dev, grad_hook=hook, grad_scale=1.0 / world)
 
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    X = torch.rand(N_BATCHES * B, *IN_SHAPE, device=dev, generator=gen)
-    Y = torch.rand(N_BATCHES * B, *OUT_SHAPE, device=dev, generator=gen)
+    NB = args.n_batches
+    X = torch.rand(NB * B, *IN_SHAPE, device=dev, generator=gen)
+    Y = torch.rand(NB * B, *OUT_SHAPE, device=dev, generator=gen)
     data = eng.bind(X, Y, B)
     prog = eng._program("train", data, B)
 

@@ -59,7 +59,7 @@ class CaePatchHead(C.Structure):
     _fields_ = [("inp", CaeSrc), ("weight", C.c_void_p), ("bias", C.c_void_p), ("K", C.c_int), ("Cout", C.c_int),
                 ("target", CaeSrc), ("mask", CaeSrc), ("mask_channels", C.c_int), ("lambda_pearson", C.c_float),
                 ("count_scale", C.c_float), ("moments", C.c_void_p), ("coef", C.c_void_p), ("scalars", C.c_void_p),
-                ("loss_out", C.c_void_p), ("pearson_out", C.c_void_p)]
+                ("loss_out", C.c_void_p), ("pearson_out", C.c_void_p), ("ticket", C.c_void_p)]
 
 
 EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_MASK = 0, 1, 2, 3, 4, 5
@@ -101,10 +101,18 @@ EXPORTS = {
     "cae_masked_pearson_loss": (C.c_int, [C.POINTER(CaeView), C.POINTER(CaeSrc), C.POINTER(CaeSrc), C.c_int, C.c_float,
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(CaeView), C.c_void_p, C.c_void_p]),
+    "cae_attention_block_supported": (C.c_int, [C.c_int] * 4),
+    "cae_attention_block_partials_len": (C.c_longlong, [C.c_int, C.c_int]),
+    "cae_attention_block_fwd": (C.c_int, [C.POINTER(CaeView), C.POINTER(CaeSrc), C.c_void_p, C.c_void_p, C.c_int,
+                                          C.POINTER(CaeView), C.POINTER(CaeEpilogue), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "cae_attention_block_bwd": (C.c_int, [C.POINTER(CaeSrc), C.POINTER(CaeView)] + [C.c_void_p] * 5 + [C.c_int] +
+                                [C.POINTER(CaeView)] + [C.c_void_p] * 6),
     "cae_patch_head_supported": (C.c_int, [C.c_int] * 5),
     "cae_patch_head_fwd": (C.c_int, [C.POINTER(CaePatchHead), C.POINTER(CaeView), C.c_void_p]),
     "cae_patch_head_bwd": (C.c_int, [C.POINTER(CaePatchHead), C.POINTER(CaeView), C.POINTER(CaeEpilogue), C.c_void_p,
-                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+                                     C.c_void_p]),
+    "cae_patch_head_wgrad_reduce": (C.c_int, [C.POINTER(CaePatchHead), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cae_patch_head_partials_len": (C.c_longlong, [C.POINTER(CaePatchHead)]),
     "cae_randn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
 }

@@ -7,7 +7,7 @@
 //   k_ph_fwd    : recomputable forward; optionally writes yhat (apply / score), optionally reads the target (+mask)
 //                 and accumulates the seven masked moments per patch row that the loss needs.  In training yhat is
 //                 never written: HBM traffic = one read of the target.
-//   k_ph_finalize: moments -> masked MSE, 1 - mean Pearson, per-plane gradient coefficients (one small CTA)
+//   ph_finalize : moments -> masked MSE, 1 - mean Pearson, per-plane gradient coefficients (last CTA of k_ph_fwd)
 //   k_ph_bwd    : recomputes yhat, forms dL/d(pre-sigmoid) in registers and feeds all three consumers at once -
 //                 weight gradient (register accumulators, one partial row per CTA), bias gradient and the input
 //                 gradient (warp-shuffle transpose reduction) with the ReLU-mask / BatchNorm-backward epilogue of
@@ -33,6 +33,7 @@ struct PhArgs {
     float* scalars;            // [0] mse gradient factor, [1] masked mse, [2] pearson term
     float* loss_out;
     float* pearson_out;
+    unsigned int* ticket;
     float lambda_pearson, count_scale;
     // backward
     CaeView dout;              // [N, Cin, Hin, Win]
@@ -45,7 +46,9 @@ struct PhArgs {
 };
 
 __device__ __forceinline__ float4 ph_ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float ph_sigmoid(float v) { return 1.f / (1.f + expf(-v)); }
+// sigmoid through the SFU: ex2.approx + rcp (relative error ~2e-7 for |v| < 30, far inside the 1e-4 parity bar); the
+// IEEE expf + division pair costs ~25 instructions per pixel, which made these kernels issue-bound
+__device__ __forceinline__ float ph_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
 
 // stage the activated inputs of patch row (n, i) for one slot: s[j*PH_CIN + ci], zero for ci >= Cin
 __device__ __forceinline__ void ph_stage(const PhArgs& a, float* s, int n, int i, long long in_base, int tl, int TG) {
@@ -78,92 +81,35 @@ __device__ __forceinline__ void ph_preact(const float4 (&w)[PH_CIN], const float
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
-    constexpr int TG = K * K / 4, SLOTS = CAE_NT / TG, WPS = TG / 32, TPR = K / 4;
-    extern __shared__ __align__(16) float s_a[];               // [SLOTS][Win][PH_CIN]
-    __shared__ double s_mom[SLOTS][WPS][8];
-    const int tid = threadIdx.x, slot = tid / TG, tl = tid - slot * TG, lane = tid & 31, wis = tl >> 5;
-    const int ky = tl / TPR, kx = (tl - ky * TPR) * 4;
-    const int co = blockIdx.y;
-    float4 w[PH_CIN];
-#pragma unroll
-    for (int ci = 0; ci < PH_CIN; ++ci)
-        w[ci] = ci < a.Cin ? ph_ld4(a.w + (((size_t)ci * a.Cout + co) * K + ky) * K + kx) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float b = a.bias ? __ldg(a.bias + co) : 0.f;
-    const bool loss = a.target.t0.p != nullptr, has_mask = a.mask.t0.p != nullptr;
-    const long long in_base = src_cursor_offset(a.in);
-    const long long tbase = loss ? src_cursor_offset(a.target) : 0ll;
-    const long long mbase = has_mask ? src_cursor_offset(a.mask) : 0ll;
-    const CaeView& tv = a.target.t0;
-    const CaeView& mv = a.mask.t0;
-    const int mc = a.mask_channels == 1 ? 0 : co;
-    const int units = a.N * a.Hin;
-    float* sa = s_a + slot * a.Win * PH_CIN;
-    for (int u0 = blockIdx.x * SLOTS; u0 < units; u0 += gridDim.x * SLOTS) {
-        const int u = u0 + slot;
-        const bool valid = u < units;
-        const int n = valid ? u / a.Hin : 0, i = valid ? u - n * a.Hin : 0;
-        __syncthreads();
-        if (valid) ph_stage(a, sa, n, i, in_base, tl, TG);
-        __syncthreads();
-        float mo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (valid) {
-            const int oy = i * K + ky;
-            for (int j = 0; j < a.Win; ++j) {
-                const int ox = j * K + kx;
-                float av[PH_CIN], acc[4];
-                ph_preact(w, sa + j * PH_CIN, b, av, acc);
-                float d[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) d[k] = ph_sigmoid(acc[k]);
-                if (a.yhat.p)
-                    *reinterpret_cast<float4*>(a.yhat.p + (long long)n * a.yhat.sN + (long long)co * a.yhat.sC +
-                                               (long long)oy * a.yhat.ld + ox) = make_float4(d[0], d[1], d[2], d[3]);
-                if (loss) {
-                    const float4 t4 = ph_ld4(tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + ox);
-                    float4 m4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (has_mask)
-                        m4 = ph_ld4(mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + ox);
-                    const float t[4] = {t4.x, t4.y, t4.z, t4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float md = m[k] * d[k], mt = m[k] * t[k], e = (d[k] - t[k]) * m[k];
-                        mo[0] += m[k]; mo[1] += md; mo[2] += mt;
-                        mo[3] = fmaf(md, d[k], mo[3]); mo[4] = fmaf(mt, t[k], mo[4]); mo[5] = fmaf(md, t[k], mo[5]);
-                        mo[6] = fmaf(e, e, mo[6]);
-                    }
-                }
-            }
-        }
-        if (loss) {
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const double s = warp_sum_d((double)mo[k]);
-                if (lane == 0) s_mom[slot][wis][k] = s;
-            }
-            __syncthreads();
-            if (valid && tl < 7) {
-                double s = 0.0;
-#pragma unroll
-                for (int q = 0; q < WPS; ++q) s += s_mom[slot][q][tl];
-                a.moments[(((size_t)n * a.Cout + co) * a.Hin + i) * 7 + tl] = s;
-            }
-        }
-    }
-}
-
-// single CTA: per-plane moments (sum of the patch-row partials, in row order) -> losses + gradient coefficients.
-// Same algebra as k_mp_finalize (unet_ops.cuh).
-__global__ void __launch_bounds__(CAE_NT) k_ph_finalize(const PhArgs a) {
+// one CTA (the last of k_ph_fwd to finish): per-plane moments (sum of the patch-row partials, in row order) -> losses +
+// gradient coefficients.  Same algebra as k_mp_finalize (unet_ops.cuh).
+__device__ __forceinline__ void ph_finalize(const PhArgs& a, int rows_per_plane) {
     __shared__ double red[CAE_NWARP];
+    __shared__ double s_mo[CAE_NT][7];
     const int C = a.Cout, NC = a.N * C;
     double sq = 0.0, cnt = 0.0, corr_sum = 0.0;
-    for (int p = threadIdx.x; p < NC; p += CAE_NT) {
-        double mo[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int r = 0; r < a.Hin; ++r)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p0 = 0; p0 < NC; p0 += CAE_NT) {
+        const int pn = min(CAE_NT, NC - p0);
+        // phase 1 - one warp per plane: lanes take the partial rows r = lane, lane + 32, ... (loads in flight together),
+        // fixed-order butterfly
+        __syncthreads();
+        for (int q = warp; q < pn; q += CAE_NWARP) {
+            double mo[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (int r = lane; r < rows_per_plane; r += 32)
 #pragma unroll
-            for (int k = 0; k < 7; ++k) mo[k] += a.moments[((size_t)p * a.Hin + r) * 7 + k];
+                for (int k = 0; k < 7; ++k) mo[k] += __ldcg(a.moments + ((size_t)(p0 + q) * rows_per_plane + r) * 7 + k);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const double t = warp_sum_d(mo[k]);
+                if (lane == 0) s_mo[q][k] = t;
+            }
+        }
+        __syncthreads();
+        // phase 2 - one thread per plane: the (double precision, division / sqrt heavy) algebra runs in parallel
+        if ((int)threadIdx.x >= pn) continue;
+        const int p = p0 + threadIdx.x;
+        const double* mo = s_mo[threadIdx.x];
         const double M = mo[0], Md = mo[1], Mt = mo[2], Mdd = mo[3], Mtt = mo[4], Mdt = mo[5];
         sq += mo[6];
         if (a.mask_channels != 1 || (p % C) == 0) cnt += M;
@@ -205,6 +151,108 @@ __global__ void __launch_bounds__(CAE_NT) k_ph_finalize(const PhArgs a) {
     }
 }
 
+#define PH_UC 4          // patch rows staged per slot and pass (one exposure of the input-load latency per pass)
+#define PH_PF 4          // target strips in flight per thread (bytes in flight per SM = 256 thr x PF x 16 B)
+
+// unit (patch row) u of this CTA's contiguous share [ub, ue): slot s takes ub + s, ub + s + SLOTS, ...
+struct PhRange { int ub, ue; };
+__device__ __forceinline__ PhRange ph_range(int units, int slots) {
+    int upc = (units + gridDim.x - 1) / gridDim.x;
+    upc = (upc + slots - 1) / slots * slots;
+    PhRange r;
+    r.ub = blockIdx.x * upc;
+    r.ue = min(units, r.ub + upc);
+    return r;
+}
+
+template <int K>
+__global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
+    constexpr int PF = 2;                                       // 16 warps / SM x 2 strips in flight
+    constexpr int TG = K * K / 4, SLOTS = CAE_NT / TG, WPS = TG / 32, TPR = K / 4;
+    extern __shared__ __align__(16) float s_a[];               // [SLOTS][PH_UC][Win][PH_CIN]
+    const int tid = threadIdx.x, slot = tid / TG, tl = tid - slot * TG, lane = tid & 31, wis = tl >> 5;
+    const int ky = tl / TPR, kx = (tl - ky * TPR) * 4;
+    const int co = blockIdx.y;
+    float4 w[PH_CIN];
+#pragma unroll
+    for (int ci = 0; ci < PH_CIN; ++ci)
+        w[ci] = ci < a.Cin ? ph_ld4(a.w + (((size_t)ci * a.Cout + co) * K + ky) * K + kx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float b = a.bias ? __ldg(a.bias + co) : 0.f;
+    const bool loss = a.target.t0.p != nullptr, has_mask = a.mask.t0.p != nullptr;
+    const long long in_base = src_cursor_offset(a.in);
+    const long long tbase = loss ? src_cursor_offset(a.target) : 0ll;
+    const long long mbase = has_mask ? src_cursor_offset(a.mask) : 0ll;
+    const CaeView& tv = a.target.t0;
+    const CaeView& mv = a.mask.t0;
+    const int mc = a.mask_channels == 1 ? 0 : co;
+    const PhRange rg = ph_range(a.N * a.Hin, SLOTS);
+    const int usz = a.Win * PH_CIN;
+    float* sa0 = s_a + slot * PH_UC * usz;
+    for (int cb = rg.ub; cb < rg.ue; cb += PH_UC * SLOTS) {
+        __syncthreads();
+        for (int uu = 0; uu < PH_UC; ++uu) {
+            const int u = cb + uu * SLOTS + slot;
+            if (u < rg.ue) ph_stage(a, sa0 + uu * usz, u / a.Hin, u % a.Hin, in_base, tl, TG);
+        }
+        __syncthreads();
+        for (int uu = 0; uu < PH_UC; ++uu) {
+            const int u = cb + uu * SLOTS + slot;
+            if (u >= rg.ue) break;
+            const int n = u / a.Hin, i = u - n * a.Hin;
+            const float* sa = sa0 + uu * usz;
+            const int oy = i * K + ky;
+            const float* tp = loss ? tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + kx : nullptr;
+            const float* mp = has_mask ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx : nullptr;
+            float* yp = a.yhat.p ? a.yhat.p + (long long)n * a.yhat.sN + (long long)co * a.yhat.sC + (long long)oy * a.yhat.ld + kx : nullptr;
+            float mo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int j0 = 0; j0 < a.Win; j0 += PF) {
+                float4 t4[PF], m4[PF];
+#pragma unroll
+                for (int q = 0; q < PF; ++q) {
+                    t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    m4[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (j0 + q < a.Win) {
+                        if (loss) t4[q] = ph_ld4(tp + (j0 + q) * K);
+                        if (has_mask) m4[q] = ph_ld4(mp + (j0 + q) * K);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < PF; ++q) {
+                    const int j = j0 + q;
+                    if (j < a.Win) {
+                        float av[PH_CIN], acc[4];
+                        ph_preact(w, sa + j * PH_CIN, b, av, acc);
+                        float d[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) d[k] = ph_sigmoid(acc[k]);
+                        if (yp) __stcs(reinterpret_cast<float4*>(yp + j * K), make_float4(d[0], d[1], d[2], d[3]));
+                        if (loss) {
+                            const float t[4] = {t4[q].x, t4[q].y, t4[q].z, t4[q].w}, m[4] = {m4[q].x, m4[q].y, m4[q].z, m4[q].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float md = m[k] * d[k], mt = m[k] * t[k], e = (d[k] - t[k]) * m[k];
+                                mo[0] += m[k]; mo[1] += md; mo[2] += mt;
+                                mo[3] = fmaf(md, d[k], mo[3]); mo[4] = fmaf(mt, t[k], mo[4]); mo[5] = fmaf(md, t[k], mo[5]);
+                                mo[6] = fmaf(e, e, mo[6]);
+                            }
+                        }
+                    }
+                }
+            }
+            if (loss) {
+                // one partial row per (plane, patch row, warp): no block-level synchronisation in the streaming loop
+                double* row = a.moments + ((((size_t)n * a.Cout + co) * a.Hin + i) * WPS + wis) * 7;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const double sk = warp_sum_d((double)mo[k]);
+                    if (lane == 0) row[k] = sk;
+                }
+            }
+        }
+    }
+    if (loss && cae_last_block(a.ticket)) ph_finalize(a, a.Hin * WPS);
+}
+
 // 16 per-lane values -> warp sums, one channel per lane pair: lane l ends up with the sum of v[(l >> 1) & 15]
 __device__ __forceinline__ float ph_warp_transpose_sum(float (&v)[PH_CIN], int lane) {
     float r8[8], r4[4], r2[2];
@@ -243,8 +291,9 @@ template <int K>
 __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
     constexpr int TG = K * K / 4, SLOTS = CAE_NT / TG, WPS = TG / 32, TPR = K / 4, KK = K * K;
     extern __shared__ __align__(16) float smem[];
-    float* s_a = smem;                                         // [SLOTS][Win][PH_CIN]
-    float* s_red = smem + SLOTS * a.Win * PH_CIN;              // [SLOTS][WPS][Win][PH_CIN]
+    const int usz = a.Win * PH_CIN;
+    float* s_a = smem;                                         // [SLOTS][PH_UC][Win][PH_CIN]
+    float* s_red = smem + SLOTS * PH_UC * usz;                 // [SLOTS][PH_UC][WPS][Win][PH_CIN]
     __shared__ double s_db[CAE_NWARP];
     __shared__ float s_st[CAE_NT][2];
     const int tid = threadIdx.x, slot = tid / TG, tl = tid - slot * TG, lane = tid & 31, wis = tl >> 5;
@@ -255,16 +304,16 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
     const long long mbase = has_mask ? src_cursor_offset(a.mask) : 0ll;
     const CaeView& tv = a.target.t0;
     const CaeView& mv = a.mask.t0;
-    const int units = a.N * a.Hin;
     const float c0 = a.scalars[0];
     const float cs = a.count_scale > 0.f ? a.count_scale : 1.f;
-    float* sa = s_a + slot * a.Win * PH_CIN;
-    float* sr = s_red + (size_t)slot * WPS * a.Win * PH_CIN;
+    float* sa0 = s_a + slot * PH_UC * usz;
+    float* sr0 = s_red + (size_t)slot * PH_UC * WPS * usz;
     const int my_ci = tl & (PH_CIN - 1);                       // channel this thread finishes in the input-gradient tail
     const EpiCh ech = epi_load_channel(a.epi, min(my_ci, a.Cin - 1), my_ci < a.Cin);
     float s1 = 0.f, s2 = 0.f;
     const size_t nelem = (size_t)a.Cin * a.Cout * KK;
     const int row = blockIdx.x * SLOTS + slot;
+    const PhRange rg = ph_range(a.N * a.Hin, SLOTS);
     for (int co = 0; co < a.Cout; ++co) {
         float4 w[PH_CIN], gw[PH_CIN];
 #pragma unroll
@@ -276,65 +325,80 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
         const int mc = a.mask_channels == 1 ? 0 : co;
         const bool last_co = co == a.Cout - 1;
         float dbs = 0.f;
-        for (int u0 = blockIdx.x * SLOTS; u0 < units; u0 += gridDim.x * SLOTS) {
-            const int u = u0 + slot;
-            const bool valid = u < units;
-            const int n = valid ? u / a.Hin : 0, i = valid ? u - n * a.Hin : 0;
+        for (int cb = rg.ub; cb < rg.ue; cb += PH_UC * SLOTS) {
             __syncthreads();
-            if (valid) ph_stage(a, sa, n, i, in_base, tl, TG);
+            for (int uu = 0; uu < PH_UC; ++uu) {
+                const int u = cb + uu * SLOTS + slot;
+                if (u < rg.ue) ph_stage(a, sa0 + uu * usz, u / a.Hin, u % a.Hin, in_base, tl, TG);
+            }
             __syncthreads();
-            if (valid) {
+            for (int uu = 0; uu < PH_UC; ++uu) {
+                const int u = cb + uu * SLOTS + slot;
+                if (u >= rg.ue) break;
+                const int n = u / a.Hin, i = u - n * a.Hin;
+                const float* sa = sa0 + uu * usz;
+                float* sr = sr0 + (size_t)(uu * WPS + wis) * usz;
                 const int plane = n * a.Cout + co;
-                const float ca = a.coef[plane * 3 + 0] * cs, cb = a.coef[plane * 3 + 1] * cs, ce = a.coef[plane * 3 + 2] * cs;
+                const float ca = a.coef[plane * 3 + 0] * cs, cb2 = a.coef[plane * 3 + 1] * cs, ce = a.coef[plane * 3 + 2] * cs;
                 const int oy = i * K + ky;
                 const float* tp = tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + kx;
                 const float* mp = has_mask ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx
                                            : nullptr;
-                float4 t_next = ph_ld4(tp);
-                float4 m_next = has_mask ? ph_ld4(mp) : make_float4(1.f, 1.f, 1.f, 1.f);
-                for (int j = 0; j < a.Win; ++j) {
-                    const float4 t4 = t_next, m4 = m_next;
-                    if (j + 1 < a.Win) {                       // prefetch the next patch's strip
-                        t_next = ph_ld4(tp + (j + 1) * K);
-                        if (has_mask) m_next = ph_ld4(mp + (j + 1) * K);
-                    }
-                    float av[PH_CIN], acc[4];
-                    ph_preact(w, sa + j * PH_CIN, b, av, acc);
-                    const float t[4] = {t4.x, t4.y, t4.z, t4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
-                    float dz[4];
+                for (int j0 = 0; j0 < a.Win; j0 += PH_PF) {
+                    float4 t4[PH_PF], m4[PH_PF];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float d = ph_sigmoid(acc[k]);
-                        const float g = c0 * m[k] * m[k] * (d - t[k]) + m[k] * (ca * t[k] + cb * d + ce);
-                        dz[k] = g * d * (1.f - d);
-                        dbs += dz[k];
+                    for (int q = 0; q < PH_PF; ++q) {
+                        t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        m4[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (j0 + q < a.Win) {
+                            t4[q] = ph_ld4(tp + (j0 + q) * K);
+                            if (has_mask) m4[q] = ph_ld4(mp + (j0 + q) * K);
+                        }
                     }
-                    float part[PH_CIN];
 #pragma unroll
-                    for (int ci = 0; ci < PH_CIN; ++ci) {
-                        gw[ci].x = fmaf(av[ci], dz[0], gw[ci].x);
-                        gw[ci].y = fmaf(av[ci], dz[1], gw[ci].y);
-                        gw[ci].z = fmaf(av[ci], dz[2], gw[ci].z);
-                        gw[ci].w = fmaf(av[ci], dz[3], gw[ci].w);
-                        part[ci] = fmaf(dz[0], w[ci].x, fmaf(dz[1], w[ci].y, fmaf(dz[2], w[ci].z, dz[3] * w[ci].w)));
+                    for (int q = 0; q < PH_PF; ++q) {
+                        const int j = j0 + q;
+                        if (j < a.Win) {                                  // uniform over the slot (whole warps)
+                            float av[PH_CIN], acc[4];
+                            ph_preact(w, sa + j * PH_CIN, b, av, acc);
+                            const float t[4] = {t4[q].x, t4[q].y, t4[q].z, t4[q].w}, m[4] = {m4[q].x, m4[q].y, m4[q].z, m4[q].w};
+                            float dz[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float d = ph_sigmoid(acc[k]);
+                                const float g = c0 * m[k] * m[k] * (d - t[k]) + m[k] * (ca * t[k] + cb2 * d + ce);
+                                dz[k] = g * d * (1.f - d);
+                                dbs += dz[k];
+                            }
+                            float part[PH_CIN];
+#pragma unroll
+                            for (int ci = 0; ci < PH_CIN; ++ci) {
+                                gw[ci].x = fmaf(av[ci], dz[0], gw[ci].x);
+                                gw[ci].y = fmaf(av[ci], dz[1], gw[ci].y);
+                                gw[ci].z = fmaf(av[ci], dz[2], gw[ci].z);
+                                gw[ci].w = fmaf(av[ci], dz[3], gw[ci].w);
+                                part[ci] = fmaf(dz[0], w[ci].x, fmaf(dz[1], w[ci].y, fmaf(dz[2], w[ci].z, dz[3] * w[ci].w)));
+                            }
+                            const float r = ph_warp_transpose_sum(part, lane);
+                            if (!(lane & 1)) sr[j * PH_CIN + ((lane >> 1) & 15)] = r;
+                        }
                     }
-                    const float r = ph_warp_transpose_sum(part, lane);
-                    if (!(lane & 1)) sr[(wis * a.Win + j) * PH_CIN + ((lane >> 1) & 15)] = r;
                 }
             }
             __syncthreads();
-            if (valid) {
-                for (int e = tl; e < a.Win * PH_CIN; e += TG) {
-                    const int j = e / PH_CIN, ci = e - j * PH_CIN;      // ci == my_ci
-                    if (ci < a.Cin) {
-                        float v = 0.f;
+            // input gradient of this pass: sum the warps' pieces, then the epilogue of the producing layer
+            for (int e = tl; e < PH_UC * usz; e += TG) {
+                const int uu = e / usz, r2 = e - uu * usz, j = r2 / PH_CIN, ci = r2 - j * PH_CIN;      // ci == my_ci
+                const int u = cb + uu * SLOTS + slot;
+                if (u < rg.ue && ci < a.Cin) {
+                    const int n = u / a.Hin, i = u - n * a.Hin;
+                    float v = 0.f;
 #pragma unroll
-                        for (int q = 0; q < WPS; ++q) v += sr[(q * a.Win + j) * PH_CIN + ci];
-                        const long long off = (long long)n * a.dout.sN + (long long)ci * a.dout.sC + (long long)i * a.dout.ld + j;
-                        if (co > 0) v += a.dout.p[off];
-                        if (!last_co) a.dout.p[off] = v;
-                        else epi_element(a.epi, a.dout, ech, n, ci, i, j, v, 0ll, 0.f, s1, s2);
-                    }
+                    for (int q = 0; q < WPS; ++q) v += sr0[(size_t)(uu * WPS + q) * usz + r2];
+                    const long long off = (long long)n * a.dout.sN + (long long)ci * a.dout.sC + (long long)i * a.dout.ld + j;
+                    if (co > 0) v += a.dout.p[off];
+                    if (!last_co) a.dout.p[off] = v;
+                    else epi_element(a.epi, a.dout, ech, n, ci, i, j, v, 0ll, 0.f, s1, s2);
                 }
             }
         }
@@ -432,7 +496,7 @@ static int ph_fill(PhArgs& a, const CaePatchHead* h) {
     CAE_REQUIRE((uintptr_t)h->weight % 16 == 0, "patch_head: weight must be 16-byte aligned");
     a.target = h->target; a.mask = h->mask; a.mask_channels = h->mask_channels;
     a.moments = h->moments; a.coef = h->coef; a.scalars = h->scalars;
-    a.loss_out = h->loss_out; a.pearson_out = h->pearson_out;
+    a.loss_out = h->loss_out; a.pearson_out = h->pearson_out; a.ticket = h->ticket;
     a.lambda_pearson = h->lambda_pearson; a.count_scale = h->count_scale;
     const int Ho = h->K * a.Hin, Wo = h->K * a.Win;
     if (a.target.t0.p) {
@@ -440,7 +504,7 @@ static int ph_fill(PhArgs& a, const CaePatchHead* h) {
         CAE_REQUIRE(t.N == a.N && t.C == a.Cout && t.H == Ho && t.W == Wo, "patch_head: target geometry %dx%dx%dx%d != %dx%dx%dx%d",
                     t.N, t.C, t.H, t.W, a.N, a.Cout, Ho, Wo);
         CAE_REQUIRE(ph_plain_src(a.target) && src_aligned(a.target), "patch_head: target must be a plain, 16-byte aligned tensor");
-        CAE_REQUIRE(a.moments && a.coef && a.scalars, "patch_head: loss workspace missing");
+        CAE_REQUIRE(a.moments && a.coef && a.scalars && a.ticket, "patch_head: loss workspace missing");
         if (a.mask.t0.p) {
             const CaeView& m = a.mask.t0;
             CAE_REQUIRE((a.mask_channels == 1 || a.mask_channels == a.Cout) && m.C == a.mask_channels && m.N == a.N &&
@@ -453,17 +517,14 @@ static int ph_fill(PhArgs& a, const CaePatchHead* h) {
     return CAE_OK;
 }
 
-static int ph_grid(const PhArgs& a, int K, int per_sm) {
+// CTAs: every CTA gets the same number of patch rows (a multiple of the slot count), at most one CTA per SM
+static int ph_grid(const PhArgs& a, int K, int per_sm = 1) {
     const int slots = CAE_NT / (K * K / 4);
     const int units = a.N * a.Hin;
-    int gx = ceil_div(units, slots);
-    const int cap = CAE_NUM_SMS * per_sm;
-    if (gx > cap) {
-        // equal number of passes for every CTA
-        const int passes = ceil_div(gx, cap);
-        gx = ceil_div(gx, passes);
-    }
-    return gx;
+    int gx = min(ceil_div(units, slots), CAE_NUM_SMS * per_sm);
+    int upc = ceil_div(units, gx);
+    upc = ceil_div(upc, slots) * slots;
+    return ceil_div(units, upc);
 }
 
 extern "C" int cae_patch_head_supported(int K, int stride, int pad, int Cin, int Win) {
@@ -483,11 +544,10 @@ extern "C" int cae_patch_head_fwd(const CaePatchHead* h, const CaeView* yhat, vo
     CAE_REQUIRE(a.yhat.p || a.target.t0.p, "patch_head_fwd: nothing to do (no yhat, no target)");
     cudaStream_t st = (cudaStream_t)stream;
     const int slots = CAE_NT / (K * K / 4);
-    const size_t smem = (size_t)slots * a.Win * PH_CIN * 4;
+    const size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 4;
     dim3 grid(ph_grid(a, K, 2), a.Cout);
     if (K == 32) k_ph_fwd<32><<<grid, CAE_NT, smem, st>>>(a);
     else k_ph_fwd<16><<<grid, CAE_NT, smem, st>>>(a);
-    if (a.target.t0.p) k_ph_finalize<<<1, CAE_NT, 0, st>>>(a);
     return cae_check_launch("cae_patch_head_fwd");
 }
 
@@ -499,16 +559,16 @@ extern "C" long long cae_patch_head_partials_len(const CaePatchHead* h) {
     return rows * ((long long)a.Cin * a.Cout * h->K * h->K + a.Cout);
 }
 
-extern "C" int cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, const CaeEpilogue* epi, float* grad_w,
-                                  float* grad_b, float* partials, void* stream) {
+extern "C" int cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, const CaeEpilogue* epi, float* partials,
+                                  void* stream) {
     PhArgs a;
     int rc = ph_fill(a, h);
     if (rc) return rc;
     CAE_REQUIRE(a.target.t0.p, "patch_head_bwd: needs the target");
-    CAE_REQUIRE(din && epi && grad_w && partials, "patch_head_bwd: null argument");
+    CAE_REQUIRE(din && epi && partials, "patch_head_bwd: null argument");
     CAE_REQUIRE(din->p && din->N == a.N && din->C == a.Cin && din->H == a.Hin && din->W == a.Win,
                 "patch_head_bwd: input-gradient geometry differs from the input");
-    CAE_REQUIRE((uintptr_t)grad_w % 16 == 0 && (uintptr_t)partials % 16 == 0, "patch_head_bwd: grad / partials must be 16-byte aligned");
+    CAE_REQUIRE((uintptr_t)partials % 16 == 0, "patch_head_bwd: partials must be 16-byte aligned");
     a.dout = *din;
     a.epi = *epi;
     if (a.epi.mode == CAE_EPI_MASKSTATS && a.epi.act.p == nullptr) a.epi.mode = CAE_EPI_PLAIN;
@@ -525,14 +585,13 @@ extern "C" int cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, con
     }
     const int K = h->K;
     const int slots = CAE_NT / (K * K / 4), wps = K * K / 128;
-    const int gx = ph_grid(a, K, 1);
+    const int gx = ph_grid(a, K);
     a.rows = gx * slots;
     const long long nelem = (long long)a.Cin * a.Cout * K * K;
     a.partials = partials;
     a.dbpart = partials + (long long)CAE_NUM_SMS * slots * nelem;
-    a.grad_w = grad_w; a.grad_b = grad_b;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)slots * a.Win * PH_CIN * 4 * (1 + wps);
+    const size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 4 * (1 + wps);
     if (K == 32) {
         ensure_smem(k_ph_bwd<32>);
         k_ph_bwd<32><<<gx, CAE_NT, smem, st>>>(a);
@@ -540,6 +599,23 @@ extern "C" int cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, con
         ensure_smem(k_ph_bwd<16>);
         k_ph_bwd<16><<<gx, CAE_NT, smem, st>>>(a);
     }
-    k_ph_wgrad_reduce<<<ceil_div(nelem / 4, 64), CAE_NT, 0, st>>>(a, nelem / 4);
     return cae_check_launch("cae_patch_head_bwd");
+}
+
+extern "C" int cae_patch_head_wgrad_reduce(const CaePatchHead* h, float* grad_w, float* grad_b, const float* partials,
+                                           void* stream) {
+    PhArgs a;
+    int rc = ph_fill(a, h);
+    if (rc) return rc;
+    CAE_REQUIRE(grad_w && partials && (uintptr_t)grad_w % 16 == 0 && (uintptr_t)partials % 16 == 0,
+                "patch_head_wgrad_reduce: null / misaligned argument");
+    const int K = h->K;
+    const int slots = CAE_NT / (K * K / 4);
+    a.rows = ph_grid(a, K) * slots;
+    const long long nelem = (long long)a.Cin * a.Cout * K * K;
+    a.partials = const_cast<float*>(partials);
+    a.dbpart = a.partials + (long long)CAE_NUM_SMS * slots * nelem;
+    a.grad_w = grad_w; a.grad_b = grad_b;
+    k_ph_wgrad_reduce<<<ceil_div(nelem / 4, 64), CAE_NT, 0, (cudaStream_t)stream>>>(a, nelem / 4);
+    return cae_check_launch("cae_patch_head_wgrad_reduce");
 }

@@ -230,7 +230,8 @@ def patch_head_supported(K, stride, pad, Cin, Win) -> bool:
 
 
 def make_patch_head(src: CaeSrc, weight, bias, K, Cout, target=None, mask=None, mask_channels=0, lambda_pearson=0.0,
-                    count_scale=1.0, moments=None, coef=None, scalars=None, loss_out=None, pearson_out=None) -> CaePatchHead:
+                    count_scale=1.0, moments=None, coef=None, scalars=None, loss_out=None, pearson_out=None,
+                    ticket=None) -> CaePatchHead:
     h = CaePatchHead()
     h.inp = src
     h.weight = _ptr(weight)
@@ -246,7 +247,8 @@ def make_patch_head(src: CaeSrc, weight, bias, K, Cout, target=None, mask=None, 
     h.count_scale = float(count_scale)
     h.moments, h.coef, h.scalars = _ptr(moments), _ptr(coef), _ptr(scalars)
     h.loss_out, h.pearson_out = _ptr(loss_out), _ptr(pearson_out)
-    h._keep = (src, weight, bias, target, mask, moments, coef, scalars, loss_out, pearson_out)
+    h.ticket = _ptr(ticket)
+    h._keep = (src, weight, bias, target, mask, moments, coef, scalars, loss_out, pearson_out, ticket)
     return h
 
 
@@ -262,6 +264,33 @@ def patch_head_partials_len(h: CaePatchHead) -> int:
     return n
 
 
-def patch_head_bwd(h: CaePatchHead, din: CaeView, epi: CaeEpilogue, grad_w, grad_b, partials):
-    check(lib().cae_patch_head_bwd(C.byref(h), C.byref(din), C.byref(epi), _ptr(grad_w), _ptr(grad_b), _ptr(partials),
-                                   _stream()), "cae_patch_head_bwd")
+def patch_head_bwd(h: CaePatchHead, din: CaeView, epi: CaeEpilogue, partials):
+    check(lib().cae_patch_head_bwd(C.byref(h), C.byref(din), C.byref(epi), _ptr(partials), _stream()),
+          "cae_patch_head_bwd")
+
+
+def patch_head_wgrad_reduce(h: CaePatchHead, grad_w, grad_b, partials):
+    check(lib().cae_patch_head_wgrad_reduce(C.byref(h), _ptr(grad_w), _ptr(grad_b), _ptr(partials), _stream()),
+          "cae_patch_head_wgrad_reduce")
+
+
+# ---- fused attention block ---------------------------------------------------------------------------------------
+def attention_block_supported(Cn, H, W, Cr) -> bool:
+    return bool(lib().cae_attention_block_supported(int(Cn), int(H), int(W), int(Cr)))
+
+
+def attention_block_partials_len(Cn, Cr) -> int:
+    return int(lib().cae_attention_block_partials_len(int(Cn), int(Cr)))
+
+
+def attention_block_fwd(y: CaeView, skip: CaeSrc, W1, W2, Cr, cat: CaeView, epi: CaeEpilogue, stats, att, hid):
+    check(lib().cae_attention_block_fwd(C.byref(y), C.byref(skip), _ptr(W1), _ptr(W2), int(Cr), C.byref(cat),
+                                        C.byref(epi), _ptr(stats), _ptr(att), _ptr(hid), _stream()),
+          "cae_attention_block_fwd")
+
+
+def attention_block_bwd(g: CaeSrc, y: CaeView, att, hid, stats, W1, W2, Cr, dy: CaeView, dW1, dW2, dbias, partials,
+                        ticket):
+    check(lib().cae_attention_block_bwd(C.byref(g), C.byref(y), _ptr(att), _ptr(hid), _ptr(stats), _ptr(W1), _ptr(W2),
+                                        int(Cr), C.byref(dy), _ptr(dW1), _ptr(dW2), _ptr(dbias), _ptr(partials),
+                                        _ptr(ticket), _stream()), "cae_attention_block_bwd")

@@ -127,6 +127,7 @@ class UNetEngine(ConvAEEngine):
             return ops.make_epilogue(ops.EPI_STATS, bias=bias, partials=self._partials(Cn), ticket=self._ticket(), bn=blk)
         return ops.make_epilogue(ops.EPI_PLAIN, bias=bias)
 
+    use_fused_attention = True  # one launch per decoder block and direction (attention_block.cu); False = unfused chain
     use_patch_head = True       # fused kernel==stride last layer (patch_head.cu); False = generic conv + loss kernels
 
     def _patch_head(self, b, N, data, src, conv, sp, final):
@@ -140,7 +141,8 @@ class UNetEngine(ConvAEEngine):
         if final == "yhat":
             return ops.make_patch_head(src, conv.weight, conv.bias, k, co)
         if "ph_moments" not in b:
-            b["ph_moments"] = torch.zeros(b["yhat"].shape[0] * co * hin * 7, dtype=torch.float64, device=self.device)
+            b["ph_moments"] = torch.zeros(b["yhat"].shape[0] * co * hin * (k * k // 128) * 7, dtype=torch.float64,
+                                          device=self.device)
             self._keep.append(b["ph_moments"])
         tgt = self._cursor_src(data.Y, data, N)
         msk = self._cursor_src(data.M, data, N) if data.M is not None else None
@@ -148,7 +150,7 @@ class UNetEngine(ConvAEEngine):
         return ops.make_patch_head(src, conv.weight, conv.bias, k, co, target=tgt, mask=msk, mask_channels=mch,
                                    lambda_pearson=self.lambda_pearson, count_scale=self.count_scale,
                                    moments=b["ph_moments"], coef=b["coef"], scalars=b["scalars"], loss_out=data.losses,
-                                   pearson_out=data.pearson)
+                                   pearson_out=data.pearson, ticket=self._ticket())
 
     # ------------------------------------------------------------------ forward
     def _forward_ops(self, b, N, data, train, final):
@@ -201,19 +203,25 @@ class UNetEngine(ConvAEEngine):
                 y, cat = b["y_d"][j], b["catg"][j]
                 S.append((f"fwd.convT{j}", lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N),
                           e=ops.make_epilogue(ops.EPI_PLAIN, bias=conv.bias): ops.conv_up(src, w, g, o, e)))
-                S.append((f"fwd.planestats{j}", lambda y=y, st=b["st"][j]: ops.plane_stats(ops.view4(y, N), st)))
                 cr = att.fc1.out_channels
-                S.append((f"fwd.attention{j}", lambda st=b["st"][j], a=att, C=C, cr=cr, hw=H * W, at=b["att"][j],
-                          hd=b["hid"][j]: ops.channel_attention_fwd(st, a.fc1.weight, a.fc2.weight, N, C, cr, hw, at, hd)))
-                half0 = self._bn_half(("d", j), bn, 0, C, True)
-                half1 = self._bn_half(("d", j), bn, C, 2 * C, False)
-                S.append((f"fwd.gate{j}", lambda y=y, at=b["att"][j], o=ops.view4(cat[:, :C], N),
-                          e=self._stats_epi(train, half0, C): ops.ew_epilogue(ops.make_src(y, kn=at, n=N), o, e)))
                 i_skip = ne - 2 - j
                 ss = self._bn_scratch[("e", i_skip)]
-                S.append((f"fwd.skip{j}", lambda ys=b["y_e"][i_skip], ss=ss, o=ops.view4(cat[:, C:], N),
-                          e=self._stats_epi(train, half1, C):
-                          ops.ew_epilogue(ops.make_src(ys, k0=ss[0], k2=ss[1], relu=True, n=N), o, e)))
+                skip_src = ops.make_src(b["y_e"][i_skip], k0=ss[0], k2=ss[1], relu=True, n=N)
+                if self.use_fused_attention and ops.attention_block_supported(C, H, W, cr):
+                    blk_full, _ = self._bn(("d", j), bn)
+                    S.append((f"fwd.attblock{j}", lambda y=y, sk=skip_src, a=att, cr=cr, o=ops.view4(cat, N),
+                              e=self._stats_epi(train, blk_full, 2 * C), st=b["st"][j], at=b["att"][j], hd=b["hid"][j]:
+                              ops.attention_block_fwd(ops.view4(y, N), sk, a.fc1.weight, a.fc2.weight, cr, o, e, st, at, hd)))
+                else:
+                    S.append((f"fwd.planestats{j}", lambda y=y, st=b["st"][j]: ops.plane_stats(ops.view4(y, N), st)))
+                    S.append((f"fwd.attention{j}", lambda st=b["st"][j], a=att, C=C, cr=cr, hw=H * W, at=b["att"][j],
+                              hd=b["hid"][j]: ops.channel_attention_fwd(st, a.fc1.weight, a.fc2.weight, N, C, cr, hw, at, hd)))
+                    half0 = self._bn_half(("d", j), bn, 0, C, True)
+                    half1 = self._bn_half(("d", j), bn, C, 2 * C, False)
+                    S.append((f"fwd.gate{j}", lambda y=y, at=b["att"][j], o=ops.view4(cat[:, :C], N),
+                              e=self._stats_epi(train, half0, C): ops.ew_epilogue(ops.make_src(y, kn=at, n=N), o, e)))
+                    S.append((f"fwd.skip{j}", lambda sk=skip_src, o=ops.view4(cat[:, C:], N),
+                              e=self._stats_epi(train, half1, C): ops.ew_epilogue(sk, o, e)))
                 s2 = self._bn_scratch[("d", j)]
                 src = ops.make_src(cat, k0=s2[0], k2=s2[1], relu=True, n=N)
             else:
@@ -266,8 +274,9 @@ class UNetEngine(ConvAEEngine):
                     out = ops.view4(b["du"], N)
                 part = torch.zeros(ops.patch_head_partials_len(head), dtype=torch.float32, device=self.device)
                 self._keep.append(part)
-                S.append((f"bwd.head{j}", lambda h=head, o=out, e=epi, cv=conv, part=part:
-                          ops.patch_head_bwd(h, o, e, G(cv.weight), G(cv.bias), part)))
+                S.append((f"bwd.head{j}", lambda h=head, o=out, e=epi, part=part: ops.patch_head_bwd(h, o, e, part)))
+                S.append((f"bwd.head{j}.wgrad", lambda h=head, cv=conv, part=part:
+                          ops.patch_head_wgrad_reduce(h, G(cv.weight), G(cv.bias), part)))
                 continue
             if j == nd - 1:
                 dy = ops.make_src(b["dzL"], n=N)
@@ -279,14 +288,22 @@ class UNetEngine(ConvAEEngine):
                 skip_grad[ne - 2 - j] = ops.make_src(dzc[:, C:], t1=cat[:, C:], k0=s2[4][C:], k1=s2[5][C:], k2=s2[6][C:],
                                                      n=N)
                 cr = att.fc1.out_channels
-                S.append((f"bwd.gate{j}.datt", lambda gs=gsrc, y=b["y_d"][j], o=b["datt"][j]:
-                          ops.plane_dot(gs, ops.view4(y, N), o)))
-                S.append((f"bwd.attention{j}", lambda a=att, j=j, C=C, cr=cr, hw=H * W: ops.channel_attention_bwd(
-                    b["datt"][j], b["att"][j], b["hid"][j], b["st"][j], a.fc1.weight, a.fc2.weight, N, C, cr, hw,
-                    G(a.fc1.weight), G(a.fc2.weight), b["davg"][j], b["dmax"][j])))
-                S.append((f"bwd.gate{j}.dy", lambda gs=gsrc, j=j: ops.gate_bwd(
-                    gs, b["att"][j], b["davg"][j], b["dmax"][j], b["st"][j], ops.view4(b["dy_d"][j], N), b["psum"][j])))
-                S.append((f"bwd.convT{j}.db", lambda j=j, C=C, cv=conv: ops.sum_over_n(b["psum"][j], N, C, G(cv.bias))))
+                if self.use_fused_attention and ops.attention_block_supported(C, H, W, cr):
+                    part = torch.zeros(ops.attention_block_partials_len(C, cr), dtype=torch.float32, device=self.device)
+                    self._keep.append(part)
+                    S.append((f"bwd.attblock{j}", lambda gs=gsrc, a=att, j=j, cr=cr, cv=conv, part=part, t=self._ticket():
+                              ops.attention_block_bwd(gs, ops.view4(b["y_d"][j], N), b["att"][j], b["hid"][j], b["st"][j],
+                                                      a.fc1.weight, a.fc2.weight, cr, ops.view4(b["dy_d"][j], N),
+                                                      G(a.fc1.weight), G(a.fc2.weight), G(cv.bias), part, t)))
+                else:
+                    S.append((f"bwd.gate{j}.datt", lambda gs=gsrc, y=b["y_d"][j], o=b["datt"][j]:
+                              ops.plane_dot(gs, ops.view4(y, N), o)))
+                    S.append((f"bwd.attention{j}", lambda a=att, j=j, C=C, cr=cr, hw=H * W: ops.channel_attention_bwd(
+                        b["datt"][j], b["att"][j], b["hid"][j], b["st"][j], a.fc1.weight, a.fc2.weight, N, C, cr, hw,
+                        G(a.fc1.weight), G(a.fc2.weight), b["davg"][j], b["dmax"][j])))
+                    S.append((f"bwd.gate{j}.dy", lambda gs=gsrc, j=j: ops.gate_bwd(
+                        gs, b["att"][j], b["davg"][j], b["dmax"][j], b["st"][j], ops.view4(b["dy_d"][j], N), b["psum"][j])))
+                    S.append((f"bwd.convT{j}.db", lambda j=j, C=C, cv=conv: ops.sum_over_n(b["psum"][j], N, C, G(cv.bias))))
                 dy = ops.make_src(b["dy_d"][j], n=N)
             if j > 0:
                 sp2 = self._bn_scratch[("d", j - 1)]

@@ -212,6 +212,25 @@ int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target, const Cae
                             float lambda_pearson, float count_scale, double* moments, float* coef, float* scalars,
                             float* loss_out, float* pearson_out, const CaeView* dz, float* plane_sum, void* stream);
 
+/* ---- fused attention block of the UNET decoder (unet.py:23-39,149-163): between two transposed convolutions
+ *   forward : plane statistics of y (AdaptiveAvg/MaxPool), att = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max)),
+ *             cat = [att*y ; skip] and - epilogue STATS - the BatchNorm2d(2C) statistics of cat, in ONE launch
+ *             (replaces cae_plane_stats + cae_channel_attention_fwd + two cae_ew_epilogue launches)
+ *   backward: dL/d att, the MLP backward (dW1, dW2), dL/dy = att*g + davg + dmax*[argmax] and dbias = sum dL/dy in ONE
+ *             launch (replaces cae_plane_dot + cae_channel_attention_bwd + cae_gate_bwd + cae_sum_over_n)
+ * One CTA per sample with the sample's planes in shared memory: cae_attention_block_supported() says whether a
+ * geometry fits; larger ones use the unfused entry points above.  stats [N*C*4], att [N*C], hid [N*2*Cr] are saved for
+ * the backward call; partials: cae_attention_block_partials_len() floats. */
+int       cae_attention_block_supported(int C, int H, int W, int Cr);
+long long cae_attention_block_partials_len(int C, int Cr);
+int       cae_attention_block_fwd(const CaeView* y, const CaeSrc* skip, const float* W1, const float* W2, int Cr,
+                                  const CaeView* cat, const CaeEpilogue* epi, float* stats, float* att, float* hid,
+                                  void* stream);
+int       cae_attention_block_bwd(const CaeSrc* g, const CaeView* y, const float* att, const float* hid,
+                                  const float* stats, const float* W1, const float* W2, int Cr, const CaeView* dy,
+                                  float* dW1, float* dW2, float* dbias, float* partials, unsigned int* ticket,
+                                  void* stream);
+
 /* ---- patch head: transposed convolution with kernel == stride, pad 0 (the last layer of the UNET spec, e.g. k32 s32
  * 16x8x8 -> 1x256x256: nn.ConvTranspose2d unet.py:138-140), fused with torch.sigmoid (unet.py:162) and with
  * masked_mse_loss + lambda * pearson (unet.py:314-320,635-678).  Non-overlapping output patches: one tap per input
@@ -220,9 +239,9 @@ int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target, const Cae
  *                        loss_out[slot] = masked MSE, pearson_out[slot] = 1 - mean corr, gradient coefficients in
  *                        coef / scalars for the backward call.  Training never writes yhat.
  *   cae_patch_head_bwd : recomputes yhat, forms dL/d(pre-sigmoid) in registers and produces, in one pass over the
- *                        target, grad_w [Cin][Cout][K][K], grad_b [Cout] and the input gradient `din` (through the
- *                        PLAIN / MASK / MASKSTATS epilogue of the producing layer).
- * Workspaces: moments N*Cout*Hin*7 doubles, coef N*Cout*3 floats, scalars 4 floats, partials
+ *                        target, partial rows of grad_w [Cin][Cout][K][K] / grad_b [Cout] and the input gradient `din`
+ *                        (through the PLAIN / MASK / MASKSTATS epilogue of the producing layer).
+ * Workspaces: moments N*Cout*Hin*(K*K/128)*7 doubles (one row per plane, patch row and warp), coef N*Cout*3 floats, scalars 4 floats, partials
  * cae_patch_head_partials_len() floats.  Supported: K in {16, 32}, Cin <= 16, Win <= 64
  * (cae_patch_head_supported); other geometries use cae_conv_up / cae_conv_down / cae_conv_wgrad. */
 typedef struct CaePatchHead {
@@ -241,11 +260,16 @@ typedef struct CaePatchHead {
     float*        scalars;
     float*        loss_out;
     float*        pearson_out;
+    unsigned int* ticket;         /* 1 x u32, zero before first use (loss only) */
 } CaePatchHead;
 int       cae_patch_head_supported(int K, int stride, int pad, int Cin, int Win);
 int       cae_patch_head_fwd(const CaePatchHead* h, const CaeView* yhat, void* stream);
-int       cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, const CaeEpilogue* din_epilogue, float* grad_w,
-                             float* grad_b, float* partials, void* stream);
+int       cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, const CaeEpilogue* din_epilogue, float* partials,
+                             void* stream);
+/* grad_w / grad_b = fixed-order sum of the partial rows cae_patch_head_bwd left in `partials` (only the optimiser waits
+ * for it: the engine runs it beside the rest of the backward pass) */
+int       cae_patch_head_wgrad_reduce(const CaePatchHead* h, float* grad_w, float* grad_b, const float* partials,
+                                      void* stream);
 long long cae_patch_head_partials_len(const CaePatchHead* h);
 
 /* ---- variational bottleneck (VarAEModel; the reference names the variant - cli/train_cae.py:32-33,42,

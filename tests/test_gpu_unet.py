@@ -83,9 +83,17 @@ def test_unet_train_steps_vs_reference(name, use_graphs):
                 # Adam divides by |g| + 1e-8: a gradient component of ~1e-8 (nearly dead ReLU unit) becomes a step of
                 # rounding-sensitive size (measured: step-0 gradients agree to 2e-5 of the tensor's max-norm, yet two
                 # of eight latent biases move by 0.89*lr instead of 1.0*lr).  Typical element tight, worst < 0.2 lr/step.
+                # Elements that move differently must be exactly those whose gradient sits at rounding-noise level (there
+                # the summation order decides the sign Adam sees), they must be rare, and no element can be off by more
+                # than the 3 steps x lr a sign flip costs.
                 dev = np.abs(got - ref)
                 assert np.median(dev) <= 3e-4 * max(np.abs(ref).max(), 1e-3) + 1e-6, k
-                assert dev.max() <= 0.2 * 1e-3 * 3, k
+                assert dev.max() <= 2.0 * 1e-3 * 3, k
+                loose = dev > 0.2 * 1e-3 * 3
+                if loose.any():
+                    g0 = np.abs(g["grad." + prefix + k])
+                    assert loose.sum() <= max(2, 5e-3 * loose.size), (k, int(loose.sum()), loose.size)
+                    assert g0[loose].max() <= 1e-4 * g0.max(), (k, g0[loose].max(), g0.max())
     out = []
     eng.score_batches(eng.bind(x, None, x.shape[0]), lambda i, yh: out.append(yh.cpu().numpy().copy()))
     assert rel_err(out[0], g["eval_yhat"]) < 1e-3
@@ -159,6 +167,7 @@ def test_patch_head_k32_vs_oracle_and_generic(batch, with_mask):
                                 zero_dead_bias_grads=True)
         eng = UNetEngine(enc, dec, lambda_pearson=0.7, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5)
         eng.use_patch_head = fused
+        eng.use_fused_attention = fused        # second engine: unfused attention chain + generic conv / loss kernels
         engines.append((eng, enc, dec, eng.bind(x, y, batch, mask=mask)))
     ones = torch.ones_like(y)
     for step in range(2):

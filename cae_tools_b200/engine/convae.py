@@ -441,6 +441,54 @@ class ConvAEEngine:
         for _ in range(steps):
             prog.run()
 
+    def train_stream(self, host_batches, batch_size):
+        """Optimiser steps fed from HOST memory: `host_batches` yields (x, y) or (x, y, mask) CPU tensors of one batch
+        each (pinned memory makes the copies asynchronous).  Two device slots: while step i computes on slot i % 2 the
+        copy stream fills slot (i + 1) % 2, so the PCIe transfer of the next batch hides behind the current step; the
+        4-byte loss of every step is copied back asynchronously into pinned memory.  Returns the per-step losses
+        (host tensor) after one final synchronisation.  Every batch must hold exactly `batch_size` samples."""
+        st = getattr(self, "_stream_state", None)
+        if st is None or st["B"] != batch_size:
+            st = {"B": batch_size, "data": None, "copy": torch.cuda.Stream(device=self.device),
+                  "filled": [torch.cuda.Event(), torch.cuda.Event()], "freed": [torch.cuda.Event(), torch.cuda.Event()]}
+            self._stream_state = st
+        main = torch.cuda.current_stream(self.device)
+        B = batch_size
+        losses_host, n = None, 0
+        for i, hb in enumerate(host_batches):
+            xh, yh = hb[0], hb[1]
+            mh = hb[2] if len(hb) > 2 else None
+            if st["data"] is None:
+                X2 = torch.empty(2 * B, *xh.shape[1:], dtype=torch.float32, device=self.device)
+                Y2 = torch.empty(2 * B, *yh.shape[1:], dtype=torch.float32, device=self.device)
+                if mh is not None:
+                    st["data"] = self.bind(X2, Y2, B, mask=torch.empty(2 * B, *mh.shape[1:], dtype=torch.float32, device=self.device))
+                else:
+                    st["data"] = self.bind(X2, Y2, B)
+                st["prog"] = self._program("train", st["data"], B)
+                st["host_losses"] = torch.empty(1 << 16, dtype=torch.float32).pin_memory()
+            data = st["data"]
+            if i == 0:
+                data.cursor.zero_()
+                st["copy"].wait_stream(main)
+            slot = i % 2
+            lo, hi = slot * B, (slot + 1) * B
+            with torch.cuda.stream(st["copy"]):
+                if i >= 2:
+                    st["copy"].wait_event(st["freed"][slot])        # step i-2 no longer reads this slot
+                data.X[lo:hi].copy_(xh, non_blocking=True)
+                data.Y[lo:hi].copy_(yh, non_blocking=True)
+                if mh is not None:
+                    data.M[lo:hi].copy_(mh, non_blocking=True)
+                st["filled"][slot].record(st["copy"])
+            main.wait_event(st["filled"][slot])
+            st["prog"].run()
+            st["freed"][slot].record(main)
+            st["host_losses"][i % (1 << 16):i % (1 << 16) + 1].copy_(self.batch_losses(data)[slot:slot + 1], non_blocking=True)
+            n = i + 1
+        main.synchronize()
+        return st["host_losses"][:min(n, 1 << 16)].clone() if n else torch.empty(0)
+
     def test_epoch(self, data):
         self._eval_prepare_op()()
         data.cursor.zero_()

@@ -233,3 +233,30 @@ def test_cli_train_apply_continue(tmp_path):
         assert hist["nr_epochs"] == 7
     import sqlite3
     assert sqlite3.connect(db).execute("select count(*) from MODEL_TRAINING").fetchone()[0] == 2   # --continue-training builds the model without a database (as the reference does)
+
+
+@pytest.mark.parametrize("method", ["conv", "unet"])
+def test_train_stream_equals_resident_training(method):
+    """host-fed, double-buffered training (ConvAEEngine.train_stream: batch i+1 is copied while step i runs) gives
+    exactly the losses and parameters of training on a device-resident data set - same kernels, same order"""
+    import bench
+    from cae_tools_b200.engine.convae import ConvAEEngine
+    from cae_tools_b200.engine.unet import UNetEngine
+    B, nb = 8, 5
+    gen = torch.Generator().manual_seed(21)
+    X = torch.rand(nb * B, *bench.IN_SHAPE, generator=gen)
+    Y = torch.rand(nb * B, *bench.OUT_SHAPE, generator=gen)
+    results = []
+    for streamed in (False, True):
+        spec, enc, dec = bench.build_modules(method)
+        eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0) if method == "unet" else ConvAEEngine(enc, dec)
+        if streamed:
+            xs, ys = X.pin_memory(), Y.pin_memory()
+            losses = eng.train_stream(((xs[i * B:(i + 1) * B], ys[i * B:(i + 1) * B]) for i in range(nb)), B)
+            losses = torch.cat([losses, eng.train_stream(((xs[i * B:(i + 1) * B], ys[i * B:(i + 1) * B]) for i in range(nb)), B)])
+        else:
+            data = eng.bind(X, Y, B)
+            losses = torch.cat([eng.train_epoch(data).cpu().clone(), eng.train_epoch(data).cpu().clone()])
+        results.append((losses.numpy(), eng.arena.detach().cpu().numpy().copy()))
+    np.testing.assert_array_equal(results[0][0], results[1][0])
+    np.testing.assert_array_equal(results[0][1], results[1][1])

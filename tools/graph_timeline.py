@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--reps", type=int, default=200)
     ap.add_argument("--stride", type=int, default=1, help="time every stride-th prefix")
+    ap.add_argument("--kind", default="train", choices=["train", "score", "test"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -34,10 +35,13 @@ def main():
     else:
         eng = ConvAEEngine(enc, dec, device=dev)
     B = args.batch
-    X = torch.rand(8 * B, *bench.IN_SHAPE, device=dev)
-    Y = torch.rand(8 * B, *bench.OUT_SHAPE, device=dev)
+    nb = 8 if args.kind == "train" else 2
+    X = torch.rand(nb * B, *bench.IN_SHAPE, device=dev)
+    Y = torch.rand(nb * B, *bench.OUT_SHAPE, device=dev)
     data = eng.bind(X, Y, B)
-    full = eng._program("train", data, B)
+    if args.kind != "train":
+        eng._eval_prepare_op()()
+    full = eng._program(args.kind, data, B)
     sched = full.sched
     prev = 0.0
     print(f"{'op':34s} {'cumulative us':>14s} {'adds us':>10s}")

@@ -62,6 +62,28 @@ class CaePatchHead(C.Structure):
                 ("loss_out", C.c_void_p), ("pearson_out", C.c_void_p), ("ticket", C.c_void_p)]
 
 
+STEM_MAX = 4
+
+
+class CaeStemConv(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("Cin", "Hin", "Win", "Cout", "Hout", "Wout", "k", "stride", "pad")] + \
+               [(k, C.c_void_p) for k in ("w", "b", "scale", "shift")]
+
+
+class CaeStemFc(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("inp", "out", "relu")] + [(k, C.c_void_p) for k in ("w", "b", "scale", "shift")]
+
+
+class CaeStemUp(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("Cin", "Hin", "Win", "Cout", "Hout", "Wout", "k", "stride", "pad", "Cr", "skip")] + \
+               [(k, C.c_void_p) for k in ("w", "b", "W1", "W2", "scale", "shift")]
+
+
+class CaeUnetStem(C.Structure):
+    _fields_ = [("n_conv", C.c_int), ("n_fc", C.c_int), ("n_up", C.c_int), ("conv", CaeStemConv * STEM_MAX),
+                ("fc", CaeStemFc * STEM_MAX), ("up", CaeStemUp * STEM_MAX)]
+
+
 EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_MASK = 0, 1, 2, 3, 4, 5
 
 # every symbol include/cae_b200.h declares
@@ -108,6 +130,8 @@ EXPORTS = {
                                           C.c_void_p, C.c_void_p]),
     "cae_attention_block_bwd": (C.c_int, [C.POINTER(CaeSrc), C.POINTER(CaeView)] + [C.c_void_p] * 5 + [C.c_int] +
                                 [C.POINTER(CaeView)] + [C.c_void_p] * 6),
+    "cae_unet_stem_supported": (C.c_int, [C.POINTER(CaeUnetStem)]),
+    "cae_unet_stem_eval": (C.c_int, [C.POINTER(CaeUnetStem), C.POINTER(CaeSrc), C.POINTER(CaeView), C.c_void_p]),
     "cae_patch_head_supported": (C.c_int, [C.c_int] * 5),
     "cae_patch_head_fwd": (C.c_int, [C.POINTER(CaePatchHead), C.POINTER(CaeView), C.c_void_p]),
     "cae_patch_head_bwd": (C.c_int, [C.POINTER(CaePatchHead), C.POINTER(CaeView), C.POINTER(CaeEpilogue), C.c_void_p,

@@ -35,6 +35,7 @@ struct PhArgs {
     float* pearson_out;
     unsigned int* ticket;
     float lambda_pearson, count_scale;
+    int pixels_per_plane;
     // backward
     CaeView dout;              // [N, Cin, Hin, Win]
     CaeEpilogue epi;
@@ -50,7 +51,36 @@ __device__ __forceinline__ float4 ph_ld4(const float* p) { return __ldg(reinterp
 // IEEE expf + division pair costs ~25 instructions per pixel, which made these kernels issue-bound
 __device__ __forceinline__ float ph_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
 
-// stage the activated inputs of patch row (n, i) for one slot: s[j*PH_CIN + ci], zero for ci >= Cin
+// packed fp32 pairs: sm_100 issues two FMAs per FFMA2 instruction (fma.rn.f32x2), which halves the issue slots of the
+// three 16 x 4 FMA blocks these kernels are made of
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+struct W4 { f32x2 lo, hi; };          // four taps of one input channel
+__device__ __forceinline__ W4 ph_ldw(const float* p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    W4 w;
+    w.lo = pk(v.x, v.y);
+    w.hi = pk(v.z, v.w);
+    return w;
+}
+
+// stage the activated inputs of patch row (n, i) for one slot, every value DUPLICATED into a pair so that one
+// 16-byte shared-memory load yields two ready-made FFMA2 operands: s[(j*PH_CIN + ci)*2 + {0,1}], zero for ci >= Cin
 __device__ __forceinline__ void ph_stage(const PhArgs& a, float* s, int n, int i, long long in_base, int tl, int TG) {
     const CaeView& iv = a.in.t0;
     for (int e = tl; e < a.Win * PH_CIN; e += TG) {
@@ -60,24 +90,24 @@ __device__ __forceinline__ void ph_stage(const PhArgs& a, float* s, int n, int i
             const ChanCoef kc = load_coef(a.in, ci);
             v = src_value(a.in, in_base + (long long)n * iv.sN + (long long)ci * iv.sC + (long long)i * iv.ld + j, kc);
         }
-        s[e] = v;
+        reinterpret_cast<float2*>(s)[e] = make_float2(v, v);
     }
 }
 
-__device__ __forceinline__ void ph_preact(const float4 (&w)[PH_CIN], const float* sa, float b, float (&av)[PH_CIN],
-                                          float (&acc)[4]) {
+// pre-activation of 4 pixels: acc = b + sum_ci a[ci] * w[ci][0..3]; av[ci] = {a, a}
+__device__ __forceinline__ void ph_preact(const W4 (&w)[PH_CIN], const float* sa, float b, f32x2 (&av)[PH_CIN], f32x2& acc01,
+                                          f32x2& acc23) {
 #pragma unroll
-    for (int q = 0; q < PH_CIN / 4; ++q) {
-        const float4 t = *reinterpret_cast<const float4*>(sa + 4 * q);
-        av[4 * q] = t.x; av[4 * q + 1] = t.y; av[4 * q + 2] = t.z; av[4 * q + 3] = t.w;
+    for (int q = 0; q < PH_CIN / 2; ++q) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(sa + 4 * q);
+        av[2 * q] = t.x;
+        av[2 * q + 1] = t.y;
     }
-    acc[0] = acc[1] = acc[2] = acc[3] = b;
+    acc01 = acc23 = pk(b, b);
 #pragma unroll
     for (int ci = 0; ci < PH_CIN; ++ci) {
-        acc[0] = fmaf(av[ci], w[ci].x, acc[0]);
-        acc[1] = fmaf(av[ci], w[ci].y, acc[1]);
-        acc[2] = fmaf(av[ci], w[ci].z, acc[2]);
-        acc[3] = fmaf(av[ci], w[ci].w, acc[3]);
+        acc01 = fma2(av[ci], w[ci].lo, acc01);
+        acc23 = fma2(av[ci], w[ci].hi, acc23);
     }
 }
 
@@ -110,7 +140,7 @@ __device__ __forceinline__ void ph_finalize(const PhArgs& a, int rows_per_plane)
         if ((int)threadIdx.x >= pn) continue;
         const int p = p0 + threadIdx.x;
         const double* mo = s_mo[threadIdx.x];
-        const double M = mo[0], Md = mo[1], Mt = mo[2], Mdd = mo[3], Mtt = mo[4], Mdt = mo[5];
+        const double M = a.mask.t0.p ? mo[0] : (double)a.pixels_per_plane, Md = mo[1], Mt = mo[2], Mdd = mo[3], Mtt = mo[4], Mdt = mo[5];
         sq += mo[6];
         if (a.mask_channels != 1 || (p % C) == 0) cnt += M;
         const double Mp = M + 1e-8;
@@ -152,7 +182,6 @@ __device__ __forceinline__ void ph_finalize(const PhArgs& a, int rows_per_plane)
 }
 
 #define PH_UC 4          // patch rows staged per slot and pass (one exposure of the input-load latency per pass)
-#define PH_PF 4          // target strips in flight per thread (bytes in flight per SM = 256 thr x PF x 16 B)
 
 // unit (patch row) u of this CTA's contiguous share [ub, ue): slot s takes ub + s, ub + s + SLOTS, ...
 struct PhRange { int ub, ue; };
@@ -165,29 +194,50 @@ __device__ __forceinline__ PhRange ph_range(int units, int slots) {
     return r;
 }
 
-template <int K>
+// Compile-time variants: LOSS (read the target, accumulate the moments) / MASK (a mask tensor is present) / WRITE (store
+// yhat); PF = strips in flight per thread (Win % PF == 0).  Runtime flags in the streaming loop cost more issue slots
+// than the arithmetic (ncu: 257 instructions per 4-pixel strip, 32 of them the FFMA2 block).
+template <int K, bool LOSS, bool MASK, bool WRITE, int PF>
 __global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
-    constexpr int PF = 2;                                       // 16 warps / SM x 2 strips in flight
     constexpr int TG = K * K / 4, SLOTS = CAE_NT / TG, WPS = TG / 32, TPR = K / 4;
-    extern __shared__ __align__(16) float s_a[];               // [SLOTS][PH_UC][Win][PH_CIN]
+    extern __shared__ __align__(16) float s_a[];               // [SLOTS][PH_UC][Win][PH_CIN][2]
     const int tid = threadIdx.x, slot = tid / TG, tl = tid - slot * TG, lane = tid & 31, wis = tl >> 5;
     const int ky = tl / TPR, kx = (tl - ky * TPR) * 4;
     const int co = blockIdx.y;
-    float4 w[PH_CIN];
+    W4 w[PH_CIN];
 #pragma unroll
-    for (int ci = 0; ci < PH_CIN; ++ci)
-        w[ci] = ci < a.Cin ? ph_ld4(a.w + (((size_t)ci * a.Cout + co) * K + ky) * K + kx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ci = 0; ci < PH_CIN; ++ci) {
+        w[ci].lo = w[ci].hi = 0ull;
+        if (ci < a.Cin) w[ci] = ph_ldw(a.w + (((size_t)ci * a.Cout + co) * K + ky) * K + kx);
+    }
     const float b = a.bias ? __ldg(a.bias + co) : 0.f;
-    const bool loss = a.target.t0.p != nullptr, has_mask = a.mask.t0.p != nullptr;
     const long long in_base = src_cursor_offset(a.in);
-    const long long tbase = loss ? src_cursor_offset(a.target) : 0ll;
-    const long long mbase = has_mask ? src_cursor_offset(a.mask) : 0ll;
+    const long long tbase = LOSS ? src_cursor_offset(a.target) : 0ll;
+    const long long mbase = MASK ? src_cursor_offset(a.mask) : 0ll;
     const CaeView& tv = a.target.t0;
     const CaeView& mv = a.mask.t0;
     const int mc = a.mask_channels == 1 ? 0 : co;
     const PhRange rg = ph_range(a.N * a.Hin, SLOTS);
-    const int usz = a.Win * PH_CIN;
+    const int usz = a.Win * PH_CIN * 2;                         // duplicated pairs
     float* sa0 = s_a + slot * PH_UC * usz;
+    // moments of the current plane, per thread, across all of its patch rows that this slot handles (flushed when the
+    // plane changes): M (mask only), Md, Mt, Mdd, Mtt, Mdt, E
+    float mo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    auto flush = [&](int n, int i, bool real) {
+        // one partial row per (plane, patch row, warp); rows of a run other than its last one are written as zeros
+        double* row = a.moments + ((((size_t)n * a.Cout + co) * a.Hin + i) * WPS + wis) * 7;
+        if (real) {
+            if (!MASK) mo[0] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const double sk = warp_sum_d((double)mo[k]);
+                if (lane == 0) row[k] = sk;
+                mo[k] = 0.f;
+            }
+        } else if (lane < 7) {
+            row[lane] = 0.0;
+        }
+    };
     for (int cb = rg.ub; cb < rg.ue; cb += PH_UC * SLOTS) {
         __syncthreads();
         for (int uu = 0; uu < PH_UC; ++uu) {
@@ -201,33 +251,31 @@ __global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
             const int n = u / a.Hin, i = u - n * a.Hin;
             const float* sa = sa0 + uu * usz;
             const int oy = i * K + ky;
-            const float* tp = loss ? tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + kx : nullptr;
-            const float* mp = has_mask ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx : nullptr;
-            float* yp = a.yhat.p ? a.yhat.p + (long long)n * a.yhat.sN + (long long)co * a.yhat.sC + (long long)oy * a.yhat.ld + kx : nullptr;
-            float mo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const float* tp = LOSS ? tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + kx : nullptr;
+            const float* mp = MASK ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx : nullptr;
+            float* yp = WRITE ? a.yhat.p + (long long)n * a.yhat.sN + (long long)co * a.yhat.sC + (long long)oy * a.yhat.ld + kx : nullptr;
             for (int j0 = 0; j0 < a.Win; j0 += PF) {
                 float4 t4[PF], m4[PF];
 #pragma unroll
                 for (int q = 0; q < PF; ++q) {
-                    t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    m4[q] = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (j0 + q < a.Win) {
-                        if (loss) t4[q] = ph_ld4(tp + (j0 + q) * K);
-                        if (has_mask) m4[q] = ph_ld4(mp + (j0 + q) * K);
-                    }
+                    if (LOSS) t4[q] = ph_ld4(tp + (j0 + q) * K);
+                    if (MASK) m4[q] = ph_ld4(mp + (j0 + q) * K);
                 }
 #pragma unroll
                 for (int q = 0; q < PF; ++q) {
                     const int j = j0 + q;
-                    if (j < a.Win) {
-                        float av[PH_CIN], acc[4];
-                        ph_preact(w, sa + j * PH_CIN, b, av, acc);
-                        float d[4];
+                    f32x2 av[PH_CIN], acc01, acc23;
+                    ph_preact(w, sa + j * PH_CIN * 2, b, av, acc01, acc23);
+                    float acc[4], d[4];
+                    upk(acc01, acc[0], acc[1]);
+                    upk(acc23, acc[2], acc[3]);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) d[k] = ph_sigmoid(acc[k]);
-                        if (yp) __stcs(reinterpret_cast<float4*>(yp + j * K), make_float4(d[0], d[1], d[2], d[3]));
-                        if (loss) {
-                            const float t[4] = {t4[q].x, t4[q].y, t4[q].z, t4[q].w}, m[4] = {m4[q].x, m4[q].y, m4[q].z, m4[q].w};
+                    for (int k = 0; k < 4; ++k) d[k] = ph_sigmoid(acc[k]);
+                    if (WRITE) __stcs(reinterpret_cast<float4*>(yp + j * K), make_float4(d[0], d[1], d[2], d[3]));
+                    if (LOSS) {
+                        const float t[4] = {t4[q].x, t4[q].y, t4[q].z, t4[q].w};
+                        if (MASK) {
+                            const float m[4] = {m4[q].x, m4[q].y, m4[q].z, m4[q].w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float md = m[k] * d[k], mt = m[k] * t[k], e = (d[k] - t[k]) * m[k];
@@ -235,22 +283,27 @@ __global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
                                 mo[3] = fmaf(md, d[k], mo[3]); mo[4] = fmaf(mt, t[k], mo[4]); mo[5] = fmaf(md, t[k], mo[5]);
                                 mo[6] = fmaf(e, e, mo[6]);
                             }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float e = d[k] - t[k];
+                                mo[1] += d[k]; mo[2] += t[k];
+                                mo[3] = fmaf(d[k], d[k], mo[3]); mo[4] = fmaf(t[k], t[k], mo[4]); mo[5] = fmaf(d[k], t[k], mo[5]);
+                                mo[6] = fmaf(e, e, mo[6]);
+                            }
                         }
                     }
                 }
             }
-            if (loss) {
-                // one partial row per (plane, patch row, warp): no block-level synchronisation in the streaming loop
-                double* row = a.moments + ((((size_t)n * a.Cout + co) * a.Hin + i) * WPS + wis) * 7;
-#pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    const double sk = warp_sum_d((double)mo[k]);
-                    if (lane == 0) row[k] = sk;
-                }
+            if (LOSS) {
+                // last patch row of this plane that this slot handles?
+                const int un = u + SLOTS;
+                const bool last = un >= rg.ue || un / a.Hin != n;
+                flush(n, i, last);
             }
         }
     }
-    if (loss && cae_last_block(a.ticket)) ph_finalize(a, a.Hin * WPS);
+    if (LOSS && cae_last_block(a.ticket)) ph_finalize(a, a.Hin * WPS);
 }
 
 // 16 per-lane values -> warp sums, one channel per lane pair: lane l ends up with the sum of v[(l >> 1) & 15]
@@ -287,26 +340,25 @@ __device__ __forceinline__ float ph_warp_transpose_sum(float (&v)[PH_CIN], int l
     return r;
 }
 
-template <int K>
+template <int K, bool MASK, int PF>
 __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
     constexpr int TG = K * K / 4, SLOTS = CAE_NT / TG, WPS = TG / 32, TPR = K / 4, KK = K * K;
     extern __shared__ __align__(16) float smem[];
-    const int usz = a.Win * PH_CIN;
-    float* s_a = smem;                                         // [SLOTS][PH_UC][Win][PH_CIN]
-    float* s_red = smem + SLOTS * PH_UC * usz;                 // [SLOTS][PH_UC][WPS][Win][PH_CIN]
+    const int usz = a.Win * PH_CIN, usz2 = 2 * usz;
+    float* s_a = smem;                                         // [SLOTS][PH_UC][Win][PH_CIN][2] (duplicated pairs)
+    float* s_red = smem + SLOTS * PH_UC * usz2;                // [SLOTS][PH_UC][WPS][Win][PH_CIN]
     __shared__ double s_db[CAE_NWARP];
     __shared__ float s_st[CAE_NT][2];
     const int tid = threadIdx.x, slot = tid / TG, tl = tid - slot * TG, lane = tid & 31, wis = tl >> 5;
     const int ky = tl / TPR, kx = (tl - ky * TPR) * 4;
-    const bool has_mask = a.mask.t0.p != nullptr;
     const long long in_base = src_cursor_offset(a.in);
     const long long tbase = src_cursor_offset(a.target);
-    const long long mbase = has_mask ? src_cursor_offset(a.mask) : 0ll;
+    const long long mbase = MASK ? src_cursor_offset(a.mask) : 0ll;
     const CaeView& tv = a.target.t0;
     const CaeView& mv = a.mask.t0;
     const float c0 = a.scalars[0];
     const float cs = a.count_scale > 0.f ? a.count_scale : 1.f;
-    float* sa0 = s_a + slot * PH_UC * usz;
+    float* sa0 = s_a + slot * PH_UC * usz2;
     float* sr0 = s_red + (size_t)slot * PH_UC * WPS * usz;
     const int my_ci = tl & (PH_CIN - 1);                       // channel this thread finishes in the input-gradient tail
     const EpiCh ech = epi_load_channel(a.epi, min(my_ci, a.Cin - 1), my_ci < a.Cin);
@@ -315,11 +367,12 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
     const int row = blockIdx.x * SLOTS + slot;
     const PhRange rg = ph_range(a.N * a.Hin, SLOTS);
     for (int co = 0; co < a.Cout; ++co) {
-        float4 w[PH_CIN], gw[PH_CIN];
+        W4 w[PH_CIN], gw[PH_CIN];
 #pragma unroll
         for (int ci = 0; ci < PH_CIN; ++ci) {
-            w[ci] = ci < a.Cin ? ph_ld4(a.w + (((size_t)ci * a.Cout + co) * K + ky) * K + kx) : make_float4(0.f, 0.f, 0.f, 0.f);
-            gw[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+            w[ci].lo = w[ci].hi = 0ull;
+            if (ci < a.Cin) w[ci] = ph_ldw(a.w + (((size_t)ci * a.Cout + co) * K + ky) * K + kx);
+            gw[ci].lo = gw[ci].hi = 0ull;                      // bit pattern of {0.f, 0.f}
         }
         const float b = a.bias ? __ldg(a.bias + co) : 0.f;
         const int mc = a.mask_channels == 1 ? 0 : co;
@@ -329,55 +382,63 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
             __syncthreads();
             for (int uu = 0; uu < PH_UC; ++uu) {
                 const int u = cb + uu * SLOTS + slot;
-                if (u < rg.ue) ph_stage(a, sa0 + uu * usz, u / a.Hin, u % a.Hin, in_base, tl, TG);
+                if (u < rg.ue) ph_stage(a, sa0 + uu * usz2, u / a.Hin, u % a.Hin, in_base, tl, TG);
             }
             __syncthreads();
             for (int uu = 0; uu < PH_UC; ++uu) {
                 const int u = cb + uu * SLOTS + slot;
                 if (u >= rg.ue) break;
                 const int n = u / a.Hin, i = u - n * a.Hin;
-                const float* sa = sa0 + uu * usz;
+                const float* sa = sa0 + uu * usz2;
                 float* sr = sr0 + (size_t)(uu * WPS + wis) * usz;
                 const int plane = n * a.Cout + co;
                 const float ca = a.coef[plane * 3 + 0] * cs, cb2 = a.coef[plane * 3 + 1] * cs, ce = a.coef[plane * 3 + 2] * cs;
                 const int oy = i * K + ky;
                 const float* tp = tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + kx;
-                const float* mp = has_mask ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx
-                                           : nullptr;
-                for (int j0 = 0; j0 < a.Win; j0 += PH_PF) {
-                    float4 t4[PH_PF], m4[PH_PF];
+                const float* mp = MASK ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx
+                                       : nullptr;
+                // without a mask: g = c0 (d - t) + ca t + cb d + ce = gd d + gt t + ce
+                const float gd = c0 + cb2, gt = ca - c0;
+                for (int j0 = 0; j0 < a.Win; j0 += PF) {
+                    float4 t4[PF], m4[PF];
 #pragma unroll
-                    for (int q = 0; q < PH_PF; ++q) {
-                        t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        m4[q] = make_float4(1.f, 1.f, 1.f, 1.f);
-                        if (j0 + q < a.Win) {
-                            t4[q] = ph_ld4(tp + (j0 + q) * K);
-                            if (has_mask) m4[q] = ph_ld4(mp + (j0 + q) * K);
-                        }
+                    for (int q = 0; q < PF; ++q) {
+                        t4[q] = ph_ld4(tp + (j0 + q) * K);
+                        if (MASK) m4[q] = ph_ld4(mp + (j0 + q) * K);
                     }
 #pragma unroll
-                    for (int q = 0; q < PH_PF; ++q) {
+                    for (int q = 0; q < PF; ++q) {
                         const int j = j0 + q;
-                        if (j < a.Win) {                                  // uniform over the slot (whole warps)
-                            float av[PH_CIN], acc[4];
-                            ph_preact(w, sa + j * PH_CIN, b, av, acc);
-                            const float t[4] = {t4[q].x, t4[q].y, t4[q].z, t4[q].w}, m[4] = {m4[q].x, m4[q].y, m4[q].z, m4[q].w};
+                        {
+                            f32x2 av[PH_CIN], acc01, acc23;
+                            ph_preact(w, sa + j * PH_CIN * 2, b, av, acc01, acc23);
+                            float acc[4];
+                            upk(acc01, acc[0], acc[1]);
+                            upk(acc23, acc[2], acc[3]);
+                            const float t[4] = {t4[q].x, t4[q].y, t4[q].z, t4[q].w};
                             float dz[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float d = ph_sigmoid(acc[k]);
-                                const float g = c0 * m[k] * m[k] * (d - t[k]) + m[k] * (ca * t[k] + cb2 * d + ce);
-                                dz[k] = g * d * (1.f - d);
+                                float g;
+                                if (MASK) {
+                                    const float m = k == 0 ? m4[q].x : (k == 1 ? m4[q].y : (k == 2 ? m4[q].z : m4[q].w));
+                                    g = m * fmaf(c0 * m, d - t[k], fmaf(ca, t[k], fmaf(cb2, d, ce)));
+                                } else {
+                                    g = fmaf(gd, d, fmaf(gt, t[k], ce));
+                                }
+                                dz[k] = g * fmaf(-d, d, d);
                                 dbs += dz[k];
                             }
+                            const f32x2 dz01 = pk(dz[0], dz[1]), dz23 = pk(dz[2], dz[3]);
                             float part[PH_CIN];
 #pragma unroll
                             for (int ci = 0; ci < PH_CIN; ++ci) {
-                                gw[ci].x = fmaf(av[ci], dz[0], gw[ci].x);
-                                gw[ci].y = fmaf(av[ci], dz[1], gw[ci].y);
-                                gw[ci].z = fmaf(av[ci], dz[2], gw[ci].z);
-                                gw[ci].w = fmaf(av[ci], dz[3], gw[ci].w);
-                                part[ci] = fmaf(dz[0], w[ci].x, fmaf(dz[1], w[ci].y, fmaf(dz[2], w[ci].z, dz[3] * w[ci].w)));
+                                gw[ci].lo = fma2(av[ci], dz01, gw[ci].lo);
+                                gw[ci].hi = fma2(av[ci], dz23, gw[ci].hi);
+                                float p0, p1;
+                                upk(fma2(dz01, w[ci].lo, mul2(dz23, w[ci].hi)), p0, p1);
+                                part[ci] = p0 + p1;
                             }
                             const float r = ph_warp_transpose_sum(part, lane);
                             if (!(lane & 1)) sr[j * PH_CIN + ((lane >> 1) & 15)] = r;
@@ -407,7 +468,8 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
 #pragma unroll
             for (int ci = 0; ci < PH_CIN; ++ci)
                 if (ci < a.Cin)
-                    *reinterpret_cast<float4*>(a.partials + (size_t)row * nelem + ((size_t)ci * a.Cout + co) * KK + tl * 4) = gw[ci];
+                    *reinterpret_cast<ulonglong2*>(a.partials + (size_t)row * nelem + ((size_t)ci * a.Cout + co) * KK + tl * 4) =
+                        make_ulonglong2(gw[ci].lo, gw[ci].hi);
         }
         const double dbw = warp_sum_d((double)dbs);
         __syncthreads();
@@ -499,6 +561,7 @@ static int ph_fill(PhArgs& a, const CaePatchHead* h) {
     a.loss_out = h->loss_out; a.pearson_out = h->pearson_out; a.ticket = h->ticket;
     a.lambda_pearson = h->lambda_pearson; a.count_scale = h->count_scale;
     const int Ho = h->K * a.Hin, Wo = h->K * a.Win;
+    a.pixels_per_plane = Ho * Wo;
     if (a.target.t0.p) {
         const CaeView& t = a.target.t0;
         CAE_REQUIRE(t.N == a.N && t.C == a.Cout && t.H == Ho && t.W == Wo, "patch_head: target geometry %dx%dx%dx%d != %dx%dx%dx%d",
@@ -544,10 +607,27 @@ extern "C" int cae_patch_head_fwd(const CaePatchHead* h, const CaeView* yhat, vo
     CAE_REQUIRE(a.yhat.p || a.target.t0.p, "patch_head_fwd: nothing to do (no yhat, no target)");
     cudaStream_t st = (cudaStream_t)stream;
     const int slots = CAE_NT / (K * K / 4);
-    const size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 4;
+    const size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 2 * 4;
     dim3 grid(ph_grid(a, K, 2), a.Cout);
-    if (K == 32) k_ph_fwd<32><<<grid, CAE_NT, smem, st>>>(a);
-    else k_ph_fwd<16><<<grid, CAE_NT, smem, st>>>(a);
+    const bool loss = a.target.t0.p != nullptr, mask = loss && a.mask.t0.p != nullptr, write = a.yhat.p != nullptr;
+    CAE_REQUIRE(!(loss && write), "patch_head_fwd: writing yhat and computing the loss in one call is not supported "
+                                  "(score writes, train / test reduce)");
+    const bool pf2 = a.Win % 2 == 0;
+#define PH_FWD(K_, L_, M_, W_)                                                                      \
+    do {                                                                                            \
+        if (pf2) k_ph_fwd<K_, L_, M_, W_, 2><<<grid, CAE_NT, smem, st>>>(a);                        \
+        else k_ph_fwd<K_, L_, M_, W_, 1><<<grid, CAE_NT, smem, st>>>(a);                            \
+    } while (0)
+    if (K == 32) {
+        if (write) PH_FWD(32, false, false, true);
+        else if (mask) PH_FWD(32, true, true, false);
+        else PH_FWD(32, true, false, false);
+    } else {
+        if (write) PH_FWD(16, false, false, true);
+        else if (mask) PH_FWD(16, true, true, false);
+        else PH_FWD(16, true, false, false);
+    }
+#undef PH_FWD
     return cae_check_launch("cae_patch_head_fwd");
 }
 
@@ -591,14 +671,21 @@ extern "C" int cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, con
     a.partials = partials;
     a.dbpart = partials + (long long)CAE_NUM_SMS * slots * nelem;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 4 * (1 + wps);
-    if (K == 32) {
-        ensure_smem(k_ph_bwd<32>);
-        k_ph_bwd<32><<<gx, CAE_NT, smem, st>>>(a);
-    } else {
-        ensure_smem(k_ph_bwd<16>);
-        k_ph_bwd<16><<<gx, CAE_NT, smem, st>>>(a);
-    }
+    const size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 4 * (2 + wps);
+    const bool mask = a.mask.t0.p != nullptr, pf4 = a.Win % 2 == 0;     // two strips in flight (four spill at 255 registers)
+#define PH_BWD(K_, M_, P_)                                        \
+    do {                                                          \
+        ensure_smem(k_ph_bwd<K_, M_, P_>);                        \
+        k_ph_bwd<K_, M_, P_><<<gx, CAE_NT, smem, st>>>(a);        \
+    } while (0)
+#define PH_BWD_K(K_)                                              \
+    do {                                                          \
+        if (mask) { if (pf4) PH_BWD(K_, true, 2); else PH_BWD(K_, true, 1); }     \
+        else { if (pf4) PH_BWD(K_, false, 2); else PH_BWD(K_, false, 1); }        \
+    } while (0)
+    if (K == 32) PH_BWD_K(32); else PH_BWD_K(16);
+#undef PH_BWD_K
+#undef PH_BWD
     return cae_check_launch("cae_patch_head_bwd");
 }
 

@@ -10,7 +10,8 @@ import ctypes as C
 
 import torch
 
-from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeGemm, CaePatchHead, CaeSrc, CaeView, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
+from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
+                    CaeUnetStem, CaeView, STEM_MAX, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
                     EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
 
 __all__ = ["view4", "make_src", "make_bn", "make_epilogue", "geom", "conv_up", "conv_down", "conv_wgrad",
@@ -294,3 +295,33 @@ def attention_block_bwd(g: CaeSrc, y: CaeView, att, hid, stats, W1, W2, Cr, dy: 
     check(lib().cae_attention_block_bwd(C.byref(g), C.byref(y), _ptr(att), _ptr(hid), _ptr(stats), _ptr(W1), _ptr(W2),
                                         int(Cr), C.byref(dy), _ptr(dW1), _ptr(dW2), _ptr(dbias), _ptr(partials),
                                         _ptr(ticket), _stream()), "cae_attention_block_bwd")
+
+
+# ---- eval-mode UNET stem ---------------------------------------------------------------------------------------------
+def make_unet_stem(convs, fcs, ups) -> CaeUnetStem:
+    """convs: [(Cin,Hin,Win,Cout,Hout,Wout,k,stride,pad, w,b,scale,shift)], fcs: [(in,out,relu, w,b,scale,shift)],
+    ups: [(Cin,Hin,Win,Cout,Hout,Wout,k,stride,pad,Cr,skip, w,b,W1,W2,scale,shift)]; tensors or None"""
+    if max(len(convs), len(fcs), len(ups)) > STEM_MAX:
+        return None
+    st = CaeUnetStem()
+    st.n_conv, st.n_fc, st.n_up = len(convs), len(fcs), len(ups)
+    keep = []
+    for i, c in enumerate(convs):
+        st.conv[i] = CaeStemConv(*[int(v) for v in c[:9]], *[_ptr(t) for t in c[9:]])
+        keep += list(c[9:])
+    for i, c in enumerate(fcs):
+        st.fc[i] = CaeStemFc(*[int(v) for v in c[:3]], *[_ptr(t) for t in c[3:]])
+        keep += list(c[3:])
+    for i, c in enumerate(ups):
+        st.up[i] = CaeStemUp(*[int(v) for v in c[:11]], *[_ptr(t) for t in c[11:]])
+        keep += list(c[11:])
+    st._keep = keep
+    return st
+
+
+def unet_stem_supported(stem: CaeUnetStem) -> bool:
+    return stem is not None and bool(lib().cae_unet_stem_supported(C.byref(stem)))
+
+
+def unet_stem_eval(stem: CaeUnetStem, x: CaeSrc, out: CaeView):
+    check(lib().cae_unet_stem_eval(C.byref(stem), C.byref(x), C.byref(out), _stream()), "cae_unet_stem_eval")

@@ -127,6 +127,10 @@ class UNetEngine(ConvAEEngine):
             return ops.make_epilogue(ops.EPI_STATS, bias=bias, partials=self._partials(Cn), ticket=self._ticket(), bn=blk)
         return ops.make_epilogue(ops.EPI_PLAIN, bias=bias)
 
+    # eval mode: every layer before the last one in ONE launch (unet_stem_eval.cu).  Correct and tested, but its plain
+    # per-thread loops run at ~3 TFLOP/s: measured 243 us against 218 us for the 11-launch chain at batch 1024, so it is
+    # off by default until its inner loops are register-tiled.
+    use_fused_stem = False
     use_fused_attention = True  # one launch per decoder block and direction (attention_block.cu); False = unfused chain
     use_patch_head = True       # fused kernel==stride last layer (patch_head.cu); False = generic conv + loss kernels
 
@@ -152,6 +156,62 @@ class UNetEngine(ConvAEEngine):
                                    moments=b["ph_moments"], coef=b["coef"], scalars=b["scalars"], loss_out=data.losses,
                                    pearson_out=data.pearson, ticket=self._ticket())
 
+    def _last_layer_ops(self, S, b, N, data, src, conv, sp, j, final):
+        """last transposed conv + sigmoid (+ loss): the fused patch head when the geometry allows it, else generic"""
+        g = self._geom(sp)
+        head = self._patch_head(b, N, data, src, conv, sp, final)
+        if head is not None:
+            if final == "yhat":
+                S.append((f"fwd.head{j}+sigmoid", lambda h=head, o=ops.view4(b["yhat"], N): ops.patch_head_fwd(h, o)))
+            else:
+                S.append((f"fwd.head{j}+sigmoid+loss", lambda h=head: ops.patch_head_fwd(h)))
+            self._head = head if final == "loss_grad" else None
+            return
+        self._head = None
+        S.append((f"fwd.convT{j}+sigmoid", lambda src=src, w=conv.weight, g=g, o=ops.view4(b["yhat"], N),
+                  e=ops.make_epilogue(ops.EPI_SIGMOID, bias=conv.bias): ops.conv_up(src, w, g, o, e)))
+        if final != "yhat":
+            tgt = self._cursor_src(data.Y, data, N)
+            msk = self._cursor_src(data.M, data, N) if data.M is not None else None
+            mch = data.M.shape[1] if data.M is not None else b["yhat"].shape[1]
+            dz = ops.view4(b["dzL"], N) if final == "loss_grad" else None
+            S.append(("loss.masked_mse+pearson", lambda tgt=tgt, msk=msk, mch=mch, dz=dz: ops.masked_pearson_loss(
+                ops.view4(b["yhat"], N), tgt, msk, mch, self.lambda_pearson, self.count_scale, b["moments"], b["coef"],
+                b["scalars"], data.losses, data.pearson, dz, b["psL"] if dz is not None else None)))
+
+    def _eval_stem(self):
+        """descriptor of the fused eval-mode stem (cached), or None when the geometry does not fit the kernel"""
+        if hasattr(self, "_stem"):
+            return self._stem
+        self._stem = None
+        ks = lambda sp: sp.get_kernel_size()
+        if any(isinstance(ks(sp), (tuple, list)) for sp in list(self.enc_specs) + list(self.dec_specs)):
+            return None
+        convs, fcs, ups = [], [], []
+        for i, ((conv, bn), sp) in enumerate(zip(self.enc_layers, self.enc_specs)):
+            _, s = self._bn(("e", i), bn)
+            convs.append((*sp.get_input_dimensions(), *sp.get_output_dimensions(), ks(sp), sp.get_stride(),
+                          sp.get_output_padding(), conv.weight, conv.bias, s[0], s[1]))
+        lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
+        _, s1 = self._bn(("l", 0), lin[1])
+        _, s3 = self._bn(("l", 1), dlin[1])
+        fcs.append((lin[0].in_features, lin[0].out_features, 1, lin[0].weight, lin[0].bias, s1[0], s1[1]))
+        fcs.append((lin[4].in_features, lin[4].out_features, 1, lin[4].weight, lin[4].bias, None, None))
+        fcs.append((dlin[0].in_features, dlin[0].out_features, 1, dlin[0].weight, dlin[0].bias, s3[0], s3[1]))
+        fcs.append((dlin[4].in_features, dlin[4].out_features, 1, dlin[4].weight, dlin[4].bias, None, None))
+        ne = len(self.enc_layers)
+        for j, ((conv, bn, att), sp) in enumerate(zip(self.dec3[:-1], self.dec_specs[:-1])):
+            _, s2 = self._bn(("d", j), bn)
+            ups.append((*sp.get_input_dimensions(), *sp.get_output_dimensions(), ks(sp), sp.get_stride(),
+                        sp.get_output_padding(), att.fc1.out_channels, ne - 2 - j, conv.weight, conv.bias,
+                        att.fc1.weight, att.fc2.weight, s2[0], s2[1]))
+        if not ups:
+            return None
+        stem = ops.make_unet_stem(convs, fcs, ups)
+        if ops.unet_stem_supported(stem):
+            self._stem = stem
+        return self._stem
+
     # ------------------------------------------------------------------ forward
     def _forward_ops(self, b, N, data, train, final):
         if train and self.dropout_rate > 0:
@@ -159,6 +219,17 @@ class UNetEngine(ConvAEEngine):
                                       "(use dropout_rate=0; inference is unaffected)")
         S = []
         src = self._x_src(data, N)
+        if not train and self.use_fused_stem:
+            stem = self._eval_stem()
+            if stem is not None:
+                nd = len(self.dec3)
+                C2, H, W = self.dec_specs[nd - 1].get_input_dimensions()
+                if "stem_out" not in b:
+                    b["stem_out"] = self._f32(b["yhat"].shape[0], C2, H, W)
+                S.append(("fwd.stem", lambda st=stem, x=src, o=ops.view4(b["stem_out"], N): ops.unet_stem_eval(st, x, o)))
+                conv, sp = self.dec3[-1][0], self.dec_specs[-1]
+                self._last_layer_ops(S, b, N, data, ops.make_src(b["stem_out"], n=N), conv, sp, nd - 1, final)
+                return S
         for i, ((conv, bn), sp) in enumerate(zip(self.enc_layers, self.enc_specs)):
             y = b["y_e"][i]
             blk, s = self._bn(("e", i), bn, self.g(conv.bias))
@@ -225,25 +296,7 @@ class UNetEngine(ConvAEEngine):
                 s2 = self._bn_scratch[("d", j)]
                 src = ops.make_src(cat, k0=s2[0], k2=s2[1], relu=True, n=N)
             else:
-                head = self._patch_head(b, N, data, src, conv, sp, final)
-                if head is not None:
-                    if final == "yhat":
-                        S.append((f"fwd.head{j}+sigmoid", lambda h=head, o=ops.view4(b["yhat"], N): ops.patch_head_fwd(h, o)))
-                    else:
-                        S.append((f"fwd.head{j}+sigmoid+loss", lambda h=head: ops.patch_head_fwd(h)))
-                    self._head = head if final == "loss_grad" else None
-                    return S
-                self._head = None
-                S.append((f"fwd.convT{j}+sigmoid", lambda src=src, w=conv.weight, g=g, o=ops.view4(b["yhat"], N),
-                          e=ops.make_epilogue(ops.EPI_SIGMOID, bias=conv.bias): ops.conv_up(src, w, g, o, e)))
-        if final != "yhat":
-            tgt = self._cursor_src(data.Y, data, N)
-            msk = self._cursor_src(data.M, data, N) if data.M is not None else None
-            mch = data.M.shape[1] if data.M is not None else b["yhat"].shape[1]
-            dz = ops.view4(b["dzL"], N) if final == "loss_grad" else None
-            S.append(("loss.masked_mse+pearson", lambda tgt=tgt, msk=msk, mch=mch, dz=dz: ops.masked_pearson_loss(
-                ops.view4(b["yhat"], N), tgt, msk, mch, self.lambda_pearson, self.count_scale, b["moments"], b["coef"],
-                b["scalars"], data.losses, data.pearson, dz, b["psL"] if dz is not None else None)))
+                self._last_layer_ops(S, b, N, data, src, conv, sp, j, final)
         return S
 
     # ------------------------------------------------------------------ backward

@@ -231,6 +231,37 @@ int       cae_attention_block_bwd(const CaeSrc* g, const CaeView* y, const float
                                   float* dW1, float* dW2, float* dbias, float* partials, unsigned int* ticket,
                                   void* stream);
 
+/* ---- eval-mode UNET stem: every layer before the last transposed convolution in ONE launch (BatchNorm in eval mode
+ * is a per-channel affine, so samples are independent: a CTA carries a few samples through the whole stem in shared
+ * memory).  Used by apply() / score() / the test epoch.  scale / shift are the eval-mode BatchNorm coefficients
+ * written by cae_bn_eval_prepare (NULL = no BatchNorm).  Reference: unet.py:73-163 in eval mode.
+ *   conv[l] : Conv2d(k, stride, pad) + BN + ReLU                                   weights [Cout][Cin][k][k]
+ *   fc[l]   : y = act((W x + b) * scale + shift)                                   weights [out][in]
+ *   up[j]   : ConvTranspose2d(k, stride, pad), ChannelAttention (W1 [Cr][C], W2 [C][Cr]), concat with the activated
+ *             output of encoder layer `skip`, BN(2C) + ReLU                        weights [Cin][Cout][k][k]
+ * out: [N, 2*C_last, H_last, W_last] - the ACTIVATED input of the last layer. */
+#define CAE_STEM_MAX 4
+typedef struct CaeStemConv {
+    int Cin, Hin, Win, Cout, Hout, Wout, k, stride, pad;
+    const float *w, *b, *scale, *shift;
+} CaeStemConv;
+typedef struct CaeStemFc {
+    int in, out, relu;
+    const float *w, *b, *scale, *shift;
+} CaeStemFc;
+typedef struct CaeStemUp {
+    int Cin, Hin, Win, Cout, Hout, Wout, k, stride, pad, Cr, skip;
+    const float *w, *b, *W1, *W2, *scale, *shift;
+} CaeStemUp;
+typedef struct CaeUnetStem {
+    int n_conv, n_fc, n_up;
+    CaeStemConv conv[CAE_STEM_MAX];
+    CaeStemFc   fc[CAE_STEM_MAX];
+    CaeStemUp   up[CAE_STEM_MAX];
+} CaeUnetStem;
+int cae_unet_stem_supported(const CaeUnetStem* s);
+int cae_unet_stem_eval(const CaeUnetStem* s, const CaeSrc* x, const CaeView* out, void* stream);
+
 /* ---- patch head: transposed convolution with kernel == stride, pad 0 (the last layer of the UNET spec, e.g. k32 s32
  * 16x8x8 -> 1x256x256: nn.ConvTranspose2d unet.py:138-140), fused with torch.sigmoid (unet.py:162) and with
  * masked_mse_loss + lambda * pearson (unet.py:314-320,635-678).  Non-overlapping output patches: one tap per input

@@ -406,6 +406,36 @@ def run_b200(args):
                 "apply_step": {"bytes_per_image": b_apply, "achieved": b_apply * AB / (ms_apply / Ka / 1e3) / 1e9,
                                "frac": b_apply * AB / (ms_apply / Ka / 1e3) / 1e9 / hbm_peak}}
 
+    # ncu --set full (profiles/r01_head_ncu.md): DRAM bytes of one launch of the fused head kernels at batch 64
+    NCU_TRAFFIC = {"bwd.head2": 17172480, "fwd.head2+sigmoid+loss": 17160704}
+    if B == 64 and method == "unet" and top[0] in NCU_TRAFFIC:
+        roofline["traffic"] = NCU_TRAFFIC[top[0]]
+        roofline["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_head_ncu.md"
+
+    # ---- the ConvAEModel geometry of BASELINE configs[0] at the same batch, short run (secondary numbers)
+    also = None
+    if method == "unet" and world == 1:
+        spec_c, enc_c, dec_c = build_modules("conv")
+        eng_c = ConvAEEngine(enc_c, dec_c, lr=1e-3, weight_decay=1e-5, device=dev)
+        data_c = eng_c.bind(X[:16 * B], Y[:16 * B], B)
+        prog_c = eng_c._program("train", data_c, B)
+        for _ in range(W):
+            prog_c.run()
+        kc = max(20, K // 4)
+        ms_c = timed(prog_c.run, kc)
+        adata_c = eng_c.bind(XA, None, AB)
+        eng_c._eval_prepare_op()()
+        aprog_c = eng_c._program("score", adata_c, AB)
+        for _ in range(3):
+            aprog_c.run()
+        ms_ca = timed(aprog_c.run, 10)
+        bt_c, ba_c = bytes_per_sample(spec_c, FC, LATENT)
+        also = {"workload": workload_config("conv", B, 1)["workload"],
+                "train_samples_per_sec": B * kc / (ms_c / 1e3), "ms_per_step": ms_c / kc,
+                "apply_images_per_sec": AB * 10 / (ms_ca / 1e3), "launches_per_step": prog_c.n_launches,
+                "step_frac_of_hbm_roofline": bt_c * B / (ms_c / kc / 1e3) / 1e9 / hbm_peak,
+                "apply_frac_of_hbm_roofline": ba_c * AB / (ms_ca / 10 / 1e3) / 1e9 / hbm_peak}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cms, cores, arate = cpu_train_rate(method, B, 40, 3)
@@ -428,6 +458,7 @@ def run_b200(args):
                               "d2h_bytes_per_step": AB * numel(OUT_SHAPE) * 4}},
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "conv": also,
             "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)

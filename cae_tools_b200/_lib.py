@@ -62,6 +62,15 @@ class CaePatchHead(C.Structure):
                 ("loss_out", C.c_void_p), ("pearson_out", C.c_void_p), ("ticket", C.c_void_p)]
 
 
+class CaeFcStack(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("N", "in1", "fc1", "lat", "fc2", "out4")] + \
+               [("A", C.c_void_p), ("a_k0", C.c_void_p), ("a_k2", C.c_void_p), ("a_hw", C.c_int), ("a_relu", C.c_int)] + \
+               [(k, C.c_void_p) for k in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4")] + \
+               [("bn1", CaeBN), ("bn3", CaeBN), ("train", C.c_int), ("relu_mid", C.c_int)] + \
+               [(k, C.c_void_p) for k in ("t1", "z", "t3", "u", "du", "dW1", "db1", "dW2", "db2", "dW3", "db3", "dW4",
+                                          "db4", "dA")]
+
+
 STEM_MAX = 4
 
 
@@ -130,6 +139,9 @@ EXPORTS = {
                                           C.c_void_p, C.c_void_p]),
     "cae_attention_block_bwd": (C.c_int, [C.POINTER(CaeSrc), C.POINTER(CaeView)] + [C.c_void_p] * 5 + [C.c_int] +
                                 [C.POINTER(CaeView)] + [C.c_void_p] * 6),
+    "cae_fc_stack_supported": (C.c_int, [C.c_int] * 6),
+    "cae_fc_stack_fwd": (C.c_int, [C.POINTER(CaeFcStack), C.c_void_p]),
+    "cae_fc_stack_bwd": (C.c_int, [C.POINTER(CaeFcStack), C.c_void_p]),
     "cae_unet_stem_supported": (C.c_int, [C.POINTER(CaeUnetStem)]),
     "cae_unet_stem_eval": (C.c_int, [C.POINTER(CaeUnetStem), C.POINTER(CaeSrc), C.POINTER(CaeView), C.c_void_p]),
     "cae_patch_head_supported": (C.c_int, [C.c_int] * 5),

@@ -26,6 +26,7 @@ static const int kTileSmemMax = 100 * 1024;
 #define CAE_V2_WGRAD_B 4
 #define CAE_V2_UPDOWN_WIDE 8   // tiled up/down also for wide layers (register tile of 2/4 positions)
 #define CAE_V3_DIRECT 16       // vectorised direct kernels for wide thin layers (k_up3 / k_down3)
+#define CAE_WGRAD_SMALL 32     // warp-per-element weight gradient for layers with few positions (k_wgrad_small)
 extern int g_cae_mask;                 // defined in capi.cu
 #define g_mask g_cae_mask
 #define g_use_v2 (g_mask & CAE_V2_UPDOWN)
@@ -53,4 +54,14 @@ static bool src_aligned(const CaeSrc& s) {
     if (s.t1 && (uintptr_t)s.t1 % 16 != 0) return false;
     if (s.cursor && s.cursor_stride % 4 != 0) return false;
     return true;
+}
+
+// opt in to `bytes` of dynamic shared memory for one kernel (once per kernel)
+template <typename K>
+static void ensure_smem_limit(K kernel, int bytes) {
+    static std::mutex mu;
+    static std::unordered_set<const void*> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    if (seen.insert((const void*)kernel).second)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }

@@ -598,3 +598,52 @@ static __global__ void __launch_bounds__(CAE_NT) k_conv_wgrad_generic(const Wgra
     if (active && lane == 0) a.partials[(size_t)pc * nelem + e] = acc;
     wgrad_final_sum(a, nelem);
 }
+
+// small problems (few positions, many weight elements - the deep 2x2 ... 8x8 layers): one warp per output element, lanes
+// over ALL positions, fixed-order butterfly, direct store.  No partial rows, no ticket, no last-CTA pass: the templated
+// kernels above spend 20-35 us on their staging / reduction machinery for < 10 MFLOP of work.
+static __global__ void __launch_bounds__(CAE_NT) k_wgrad_small(const WgradArgs a) {
+    const int KK = a.kh * a.kw;
+    const int nelem = a.Cs * a.Cb * KK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * CAE_NWARP + warp;
+    if (e >= nelem) return;
+    const CaeView& sv = a.sm.t0;
+    const CaeView& bv = a.bg.t0;
+    const long long sbase = src_cursor_offset(a.sm), bbase = src_cursor_offset(a.bg);
+    const int t = e % KK, cb = (e / KK) % a.Cb, cs = e / (KK * a.Cb);
+    const int ky = t / a.kw, kx = t - ky * a.kw;
+    const ChanCoef ks = load_coef(a.sm, cs), kb = load_coef(a.bg, cb);
+    const int HW = sv.H * sv.W;
+    float acc0 = 0.f, acc1 = 0.f;
+    int g = lane;
+    for (; g + 32 < a.total; g += 64) {                      // two independent positions in flight per lane
+        const int g1 = g + 32;
+        const int n0 = g / HW, r0 = g - n0 * HW, i0 = r0 / sv.W, j0 = r0 - i0 * sv.W;
+        const int n1 = g1 / HW, r1 = g1 - n1 * HW, i1 = r1 / sv.W, j1 = r1 - i1 * sv.W;
+        const int y0 = i0 * a.s + ky - a.p, x0 = j0 * a.s + kx - a.p, y1 = i1 * a.s + ky - a.p, x1 = j1 * a.s + kx - a.p;
+        const bool ok0 = y0 >= 0 && y0 < bv.H && x0 >= 0 && x0 < bv.W, ok1 = y1 >= 0 && y1 < bv.H && x1 >= 0 && x1 < bv.W;
+        float s0 = 0.f, b0 = 0.f, s1 = 0.f, b1 = 0.f;
+        if (ok0) {
+            s0 = src_value(a.sm, sbase + (long long)n0 * sv.sN + (long long)cs * sv.sC + (long long)i0 * sv.ld + j0, ks);
+            b0 = src_value(a.bg, bbase + (long long)n0 * bv.sN + (long long)cb * bv.sC + (long long)y0 * bv.ld + x0, kb);
+        }
+        if (ok1) {
+            s1 = src_value(a.sm, sbase + (long long)n1 * sv.sN + (long long)cs * sv.sC + (long long)i1 * sv.ld + j1, ks);
+            b1 = src_value(a.bg, bbase + (long long)n1 * bv.sN + (long long)cb * bv.sC + (long long)y1 * bv.ld + x1, kb);
+        }
+        acc0 = fmaf(s0, b0, acc0);
+        acc1 = fmaf(s1, b1, acc1);
+    }
+    for (; g < a.total; g += 32) {
+        const int n0 = g / HW, r0 = g - n0 * HW, i0 = r0 / sv.W, j0 = r0 - i0 * sv.W;
+        const int y0 = i0 * a.s + ky - a.p, x0 = j0 * a.s + kx - a.p;
+        if (y0 >= 0 && y0 < bv.H && x0 >= 0 && x0 < bv.W) {
+            const float s0 = src_value(a.sm, sbase + (long long)n0 * sv.sN + (long long)cs * sv.sC + (long long)i0 * sv.ld + j0, ks);
+            const float b0 = src_value(a.bg, bbase + (long long)n0 * bv.sN + (long long)cb * bv.sC + (long long)y0 * bv.ld + x0, kb);
+            acc0 = fmaf(s0, b0, acc0);
+        }
+    }
+    const float acc = warp_sum(acc0 + acc1);
+    if (lane == 0) a.grad[e] = acc;
+}

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
         const float b = a.bias ? __ldg(a.bias + co) : 0.f;
         const int mc = a.mask_channels == 1 ? 0 : co;
         const bool last_co = co == a.Cout - 1;
-        float dbs = 0.f;
+        double dbs = 0.0;          // the bias gradient is a heavily cancelling sum: fp64 per thread
         for (int cb = rg.ub; cb < rg.ue; cb += PH_UC * SLOTS) {
             __syncthreads();
             for (int uu = 0; uu < PH_UC; ++uu) {
@@ -428,8 +428,8 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
                                     g = fmaf(gd, d, fmaf(gt, t[k], ce));
                                 }
                                 dz[k] = g * fmaf(-d, d, d);
-                                dbs += dz[k];
                             }
+                            dbs += (double)((dz[0] + dz[1]) + (dz[2] + dz[3]));
                             const f32x2 dz01 = pk(dz[0], dz[1]), dz23 = pk(dz[2], dz[3]);
                             float part[PH_CIN];
 #pragma unroll
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
                     *reinterpret_cast<ulonglong2*>(a.partials + (size_t)row * nelem + ((size_t)ci * a.Cout + co) * KK + tl * 4) =
                         make_ulonglong2(gw[ci].lo, gw[ci].hi);
         }
-        const double dbw = warp_sum_d((double)dbs);
+        const double dbw = warp_sum_d(dbs);
         __syncthreads();
         if (lane == 0) s_db[tid >> 5] = dbw;
         __syncthreads();

@@ -60,6 +60,11 @@ def _align(n, a=4):
 
 class ConvAEEngine:
 
+    # fc bottleneck as one launch per direction (fc_stack.cu).  Correct and tested, but measured no faster than the
+    # cae_gemm chain on B200 (unet batch 64: 25 + 40 us fused against 31 + 35 us; conv: 30 + 41 against 14 + 20): a
+    # dependent launch costs only ~1 us inside a graph, while a single CTA pays every phase's latency serially.
+    use_fused_fc = False
+
     def __init__(self, encoder, decoder, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, decoupled=False,
                  device="cuda", use_graphs=True, grad_hook=None, grad_scale=1.0, count_scale=1.0):
         require_cuda()
@@ -243,6 +248,11 @@ class ConvAEEngine:
         fc, lat = lin[0].out_features, lin[2].out_features
         fc2 = dlin[0].out_features
         out4 = dlin[2].out_features
+        if self._fc_fused(N, flat, fc, lat, fc2, out4):
+            # h1 / h3 hold the PRE-activations here (the fused backward differentiates the ReLU from them)
+            p = ops.make_fc_stack(N, ylast, (lin[0], lin[2], dlin[0], dlin[2]), b["h1"], b["z"], b["h3"], b["u"],
+                                  a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True)
+            return [("fwd.fcstack", lambda p=p: ops.fc_stack_fwd(p))]
         sched.append(("fwd.fc1", lambda: ops.gemm(N, fc, flat, ylast, flat, 1, lin[0].weight, 1, flat, b["h1"], fc, 1,
                                                   a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True,
                                                   bias=lin[0].bias, relu_out=True)))
@@ -253,6 +263,9 @@ class ConvAEEngine:
         sched.append(("fwd.fc4", lambda: ops.gemm(N, out4, fc2, b["h3"], fc2, 1, dlin[2].weight, 1, fc2, b["u"], out4,
                                                   1, bias=dlin[2].bias)))
         return sched
+
+    def _fc_fused(self, N, *dims):
+        return self.use_fused_fc and ops.fc_stack_supported(N, *dims)
 
     def _fc_backward_ops(self, b, N, data):
         """du -> gradients of the four Linear layers -> da (wrt the last encoder activation)"""
@@ -266,6 +279,11 @@ class ConvAEEngine:
         le = len(self.enc_layers) - 1
         s_last = self._bn_scratch[("e", le)]
         ylast = b["y_e"][-1]
+        if self._fc_fused(N, flat, fc, lat, fc2, out4):
+            p = ops.make_fc_stack(N, ylast, (lin[0], lin[2], dlin[0], dlin[2]), b["h1"], b["z"], b["h3"], b["u"],
+                                  a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True, du=b["du"], grads=G,
+                                  dA=b["da"])
+            return [("bwd.fcstack", lambda p=p: ops.fc_stack_bwd(p))]
         # Linear 4: u = h3 W4^T + b4
         sched.append(("bwd.fc4.dW", lambda: ops.gemm(out4, fc2, N, b["du"], 1, out4, b["h3"], fc2, 1, G(dlin[2].weight), fc2, 1,
                                       rowsum_A=G(dlin[2].bias))))
@@ -590,12 +608,24 @@ class _Program:
             with torch.no_grad():
                 for t, c in zip(self.state, saved):
                     t.copy_(c)
-            g = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                with torch.cuda.graph(g, stream=s):
-                    self.run_forked()
+            # Nothing may free CUDA objects while the capture is open: a garbage-collection pass that destroys the
+            # CUDAGraph / events of an engine that went out of scope earlier invalidates it (seen as a rare
+            # cudaErrorStreamCaptureInvalidated in long test sessions).  Collect now, keep the collector off during
+            # the capture, and do not let calls of other threads count against this capture.
+            import gc
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                g = torch.cuda.CUDAGraph()
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+                        self.run_forked()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             torch.cuda.current_stream().wait_stream(s)
             self.graph = g
         self.graph.replay()

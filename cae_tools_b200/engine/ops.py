@@ -10,7 +10,7 @@ import ctypes as C
 
 import torch
 
-from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
+from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
                     CaeUnetStem, CaeView, STEM_MAX, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
                     EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
 
@@ -325,3 +325,40 @@ def unet_stem_supported(stem: CaeUnetStem) -> bool:
 
 def unet_stem_eval(stem: CaeUnetStem, x: CaeSrc, out: CaeView):
     check(lib().cae_unet_stem_eval(C.byref(stem), C.byref(x), C.byref(out), _stream()), "cae_unet_stem_eval")
+
+
+# ---- fc bottleneck in one launch -----------------------------------------------------------------------------------------
+def fc_stack_supported(N, in1, fc1, lat, fc2, out4) -> bool:
+    return bool(lib().cae_fc_stack_supported(int(N), int(in1), int(fc1), int(lat), int(fc2), int(out4)))
+
+
+def make_fc_stack(N, A, lins, t1, z, t3, u, a_k0=None, a_k2=None, a_hw=1, a_relu=False, bn1=None, bn3=None, train=False,
+                  relu_mid=False, du=None, grads=None, dA=None) -> CaeFcStack:
+    """lins: the four nn.Linear modules; grads: callable parameter -> gradient view (backward descriptor only)"""
+    p = CaeFcStack()
+    l1, l2, l3, l4 = lins
+    p.N, p.in1, p.fc1, p.lat, p.fc2, p.out4 = int(N), l1.in_features, l1.out_features, l2.out_features, \
+        l3.out_features, l4.out_features
+    p.A, p.a_k0, p.a_k2, p.a_hw, p.a_relu = _ptr(A), _ptr(a_k0), _ptr(a_k2), int(a_hw), int(bool(a_relu))
+    for i, l in enumerate(lins, 1):
+        setattr(p, f"W{i}", _ptr(l.weight))
+        setattr(p, f"b{i}", _ptr(l.bias))
+    if bn1 is not None:
+        p.bn1, p.bn3 = bn1, bn3
+    p.train, p.relu_mid = int(bool(train)), int(bool(relu_mid))
+    p.t1, p.z, p.t3, p.u = _ptr(t1), _ptr(z), _ptr(t3), _ptr(u)
+    if grads is not None:
+        p.du, p.dA = _ptr(du), _ptr(dA)
+        for i, l in enumerate(lins, 1):
+            setattr(p, f"dW{i}", _ptr(grads(l.weight)))
+            setattr(p, f"db{i}", _ptr(grads(l.bias)))
+    p._keep = (A, a_k0, a_k2, lins, bn1, bn3, t1, z, t3, u, du, dA)
+    return p
+
+
+def fc_stack_fwd(p: CaeFcStack):
+    check(lib().cae_fc_stack_fwd(C.byref(p), _stream()), "cae_fc_stack_fwd")
+
+
+def fc_stack_bwd(p: CaeFcStack):
+    check(lib().cae_fc_stack_bwd(C.byref(p), _stream()), "cae_fc_stack_bwd")

@@ -212,6 +212,29 @@ int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target, const Cae
                             float lambda_pearson, float count_scale, double* moments, float* coef, float* scalars,
                             float* loss_out, float* pearson_out, const CaeView* dz, float* plane_sum, void* stream);
 
+/* ---- fc bottleneck in one launch per direction (replaces the cae_gemm / cae_ew_epilogue chain when it fits one CTA) --
+ * ConvAEModel (encoder.py:52-58, decoder.py:29-35):  Linear ReLU Linear | Linear ReLU Linear           (bn*.C == 0, relu_mid 0)
+ * UNET (unet.py:92-100,121-129): Linear BatchNorm1d ReLU Linear ReLU | Linear BatchNorm1d ReLU Linear ReLU   (relu_mid 1)
+ * A [N][in1] is read through an optional per-channel affine + ReLU (BatchNorm2d + ReLU + Flatten of the last encoder
+ * layer: channel = k / a_hw).  Saved for the backward pass: t1 / t3 (pre-activations of Linear 1 / 3), z, u.
+ * Backward: du [N][out4] must already carry the mask of the last activation; writes every weight / bias gradient,
+ * the BatchNorm gradients (bn*.dgamma / dbeta) and dA [N][in1]; biases that feed a BatchNorm get no gradient written
+ * (identically zero). */
+typedef struct CaeFcStack {
+    int          N, in1, fc1, lat, fc2, out4;
+    const float* A; const float* a_k0; const float* a_k2; int a_hw; int a_relu;
+    const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4;       /* nn.Linear layout [out][in] */
+    CaeBN        bn1, bn3;
+    int          train;        /* BatchNorm: batch statistics (1) or the eval coefficients already in bn.scale / shift (0) */
+    int          relu_mid;
+    float        *t1, *z, *t3, *u;
+    const float* du;
+    float        *dW1, *db1, *dW2, *db2, *dW3, *db3, *dW4, *db4, *dA;
+} CaeFcStack;
+int cae_fc_stack_supported(int N, int in1, int fc1, int lat, int fc2, int out4);
+int cae_fc_stack_fwd(const CaeFcStack* p, void* stream);
+int cae_fc_stack_bwd(const CaeFcStack* p, void* stream);
+
 /* ---- fused attention block of the UNET decoder (unet.py:23-39,149-163): between two transposed convolutions
  *   forward : plane statistics of y (AdaptiveAvg/MaxPool), att = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max)),
  *             cat = [att*y ; skip] and - epilogue STATS - the BatchNorm2d(2C) statistics of cat, in ONE launch

@@ -170,6 +170,7 @@ def test_patch_head_k32_vs_oracle_and_generic(batch, with_mask):
         eng = UNetEngine(enc, dec, lambda_pearson=0.7, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5)
         eng.use_patch_head = fused
         eng.use_fused_attention = fused        # second engine: unfused attention chain + generic conv / loss kernels
+        eng.use_fused_fc = fused               # one-launch fc bottleneck (off by default) against the cae_gemm chain
         eng.use_fused_stem = fused             # one-launch eval stem (off by default) against the layer-by-layer forward
         engines.append((eng, enc, dec, eng.bind(x, y, batch, mask=mask)))
     ones = torch.ones_like(y)

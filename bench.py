@@ -35,8 +35,8 @@ OUT_SHAPE = (1, 256, 256)
 LATENT, FC = 4, 16         # train_cae defaults (--latent-size 4 --fc-size 16)
 UNET_SPEC = os.path.join(ROOT, "cae_tools_b200", "specs", "unet_16x16_256x256.json")
 N_BATCHES = 64             # device-resident batches that the steps cycle through (1.1 GB > 126 MB L2)
-APPLY_BATCH = 1024
-APPLY_BATCHES = 16
+APPLY_BATCH = 4096         # micro-batch >= 4096 for the apply sweep
+APPLY_BATCHES = 4
 
 
 def parse():

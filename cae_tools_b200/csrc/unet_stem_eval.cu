@@ -13,7 +13,7 @@
 #define STEM_NT 256
 
 struct StemSmem {            // offsets in floats, per CTA (all STEM_S samples)
-    int in0, enc[CAE_STEM_MAX], va, vb, y, cat, small;
+    int in0, enc[CAE_STEM_MAX], va, vb, y, cat, small, wbuf;
     int total;
 };
 
@@ -30,7 +30,8 @@ __device__ __forceinline__ float stem_bn_relu(float v, const float* scale, const
 }
 
 // y[s][e] for e = (co, oy, ox): strided convolution with padding, BN(eval) + ReLU
-__device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* in, float* outp, int in_pitch, int out_pitch) {
+__device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* wsm, const float* in, float* outp, int in_pitch,
+                                          int out_pitch) {
     const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, KK = L.k * L.k;
     for (int e = threadIdx.x; e < total; e += STEM_NT) {
         const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
@@ -40,7 +41,7 @@ __device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* in,
         for (int s = 0; s < STEM_S; ++s) acc[s] = b;
         const int iy0 = oy * L.stride - L.pad, ix0 = ox * L.stride - L.pad;
         for (int ci = 0; ci < L.Cin; ++ci) {
-            const float* wp = L.w + ((size_t)co * L.Cin + ci) * KK;
+            const float* wp = wsm + (co * L.Cin + ci) * KK;
             const float* ip = in + ci * L.Hin * L.Win;
             for (int ky = 0; ky < L.k; ++ky) {
                 const int iy = iy0 + ky;
@@ -48,7 +49,7 @@ __device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* in,
                 for (int kx = 0; kx < L.k; ++kx) {
                     const int ix = ix0 + kx;
                     if (ix < 0 || ix >= L.Win) continue;
-                    const float wv = __ldg(wp + ky * L.k + kx);
+                    const float wv = wp[ky * L.k + kx];
                     const float* q = ip + iy * L.Win + ix;
 #pragma unroll
                     for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(q[s * in_pitch], wv, acc[s]);
@@ -61,7 +62,8 @@ __device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* in,
 }
 
 // v_out[s][o] = act((W v_in[s] + b) * scale + shift)
-__device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* in, float* outp, int in_pitch, int out_pitch) {
+__device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* wsm, const float* in, float* outp, int in_pitch,
+                                        int out_pitch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (L.in >= 64) {                                   // long rows: one warp per output, lanes over k
         for (int o = warp; o < L.out; o += STEM_NT / 32) {
@@ -69,7 +71,7 @@ __device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* in, flo
 #pragma unroll
             for (int s = 0; s < STEM_S; ++s) acc[s] = 0.f;
             for (int k = lane; k < L.in; k += 32) {
-                const float wv = __ldg(L.w + (size_t)o * L.in + k);
+                const float wv = wsm[o * L.in + k];
 #pragma unroll
                 for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(in[s * in_pitch + k], wv, acc[s]);
             }
@@ -91,7 +93,7 @@ __device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* in, flo
 #pragma unroll
             for (int s = 0; s < STEM_S; ++s) acc[s] = b;
             for (int k = 0; k < L.in; ++k) {
-                const float wv = __ldg(L.w + (size_t)o * L.in + k);
+                const float wv = wsm[o * L.in + k];
 #pragma unroll
                 for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(in[s * in_pitch + k], wv, acc[s]);
             }
@@ -106,7 +108,8 @@ __device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* in, flo
 }
 
 // transposed convolution (gather form, padding), raw output + bias
-__device__ __forceinline__ void stem_up(const CaeStemUp& L, const float* in, float* outp, int in_pitch, int out_pitch) {
+__device__ __forceinline__ void stem_up(const CaeStemUp& L, const float* wsm, const float* in, float* outp, int in_pitch,
+                                        int out_pitch) {
     const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, KK = L.k * L.k;
     for (int e = threadIdx.x; e < total; e += STEM_NT) {
         const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
@@ -124,10 +127,11 @@ __device__ __forceinline__ void stem_up(const CaeStemUp& L, const float* in, flo
                 if (tx < 0 || tx % L.stride) continue;
                 const int ix = tx / L.stride;
                 if (ix >= L.Win) continue;
-                const float* wp = L.w + (size_t)co * KK + ky * L.k + kx;            // + ci * Cout * KK
+                const float* wp = wsm + co * KK + ky * L.k + kx;                    // + ci * Cout * KK
                 const float* q = in + iy * L.Win + ix;                              // + ci * Hin * Win
+#pragma unroll 4
                 for (int ci = 0; ci < L.Cin; ++ci) {
-                    const float wv = __ldg(wp + (size_t)ci * L.Cout * KK);
+                    const float wv = wp[ci * L.Cout * KK];
 #pragma unroll
                     for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(q[s * in_pitch + ci * L.Hin * L.Win], wv, acc[s]);
                 }
@@ -148,6 +152,12 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
     const CaeView& xv = a.x.t0;
     const long long xbase = src_cursor_offset(a.x);
     const int N = xv.N;
+    float* wsm = sm + m.wbuf;
+    // layer weights go through shared memory: with ~190 KB of the SM carved out for activations the L1 keeps almost
+    // nothing, and weight loads that miss it cost an L2 round trip per tap (first version: 747 us per 4096 samples)
+    auto stage_w = [&](const float* w, int n) {
+        for (int e = tid; e < n; e += STEM_NT) wsm[e] = __ldg(w + e);
+    };
     for (int n0 = blockIdx.x * STEM_S; n0 < N; n0 += gridDim.x * STEM_S) {
         __syncthreads();
         // ---- input (samples beyond N are zero-filled; their results are never written)
@@ -168,7 +178,9 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
         for (int l = 0; l < S.n_conv; ++l) {
             const CaeStemConv& L = S.conv[l];
             const int op = L.Cout * L.Hout * L.Wout;
-            stem_conv(L, cur, sm + m.enc[l], cur_pitch, op);
+            stage_w(L.w, L.Cout * L.Cin * L.k * L.k);
+            __syncthreads();
+            stem_conv(L, wsm, cur, sm + m.enc[l], cur_pitch, op);
             __syncthreads();
             cur = sm + m.enc[l];
             cur_pitch = op;
@@ -179,7 +191,9 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
         for (int l = 0; l < S.n_fc; ++l) {
             const CaeStemFc& L = S.fc[l];
             float* dst = (l & 1) ? vb : va;
-            stem_fc(L, cur, dst, cur_pitch, L.out);
+            stage_w(L.w, L.in * L.out);
+            __syncthreads();
+            stem_fc(L, wsm, cur, dst, cur_pitch, L.out);
             __syncthreads();
             cur = dst;
             cur_pitch = L.out;
@@ -190,7 +204,9 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
             const int C = L.Cout, HW = L.Hout * L.Wout, yp = C * HW, cp = 2 * yp;
             float* y = sm + m.y;
             float* cat = sm + m.cat;
-            stem_up(L, cur, y, cur_pitch, yp);
+            stage_w(L.w, L.Cin * L.Cout * L.k * L.k);
+            __syncthreads();
+            stem_up(L, wsm, cur, y, cur_pitch, yp);
             __syncthreads();
             float* avg = sm + m.small;                     // [S][C]
             float* mx = avg + STEM_S * C;                  // [S][C]
@@ -281,6 +297,11 @@ static int stem_plan(const CaeUnetStem& s, StemSmem& m, char* why, size_t why_le
     m.y = take(STEM_S * ymax);
     m.cat = take(STEM_S * 2 * ymax);
     m.small = take(STEM_S * smallmax);
+    int wmax = 0;
+    for (int l = 0; l < s.n_conv; ++l) wmax = max(wmax, s.conv[l].Cout * s.conv[l].Cin * s.conv[l].k * s.conv[l].k);
+    for (int l = 0; l < s.n_fc; ++l) wmax = max(wmax, s.fc[l].in * s.fc[l].out);
+    for (int j = 0; j < s.n_up; ++j) wmax = max(wmax, s.up[j].Cin * s.up[j].Cout * s.up[j].k * s.up[j].k);
+    m.wbuf = take(wmax);
     m.total = off;
     if ((size_t)off * 4 > 160 * 1024) STEM_FAIL("activations of %d samples need %d KB of shared memory (> 160)", STEM_S, off * 4 / 1024);
     return 1;

@@ -127,10 +127,11 @@ class UNetEngine(ConvAEEngine):
             return ops.make_epilogue(ops.EPI_STATS, bias=bias, partials=self._partials(Cn), ticket=self._ticket(), bn=blk)
         return ops.make_epilogue(ops.EPI_PLAIN, bias=bias)
 
-    # eval mode: every layer before the last one in ONE launch (unet_stem_eval.cu).  Correct and tested, but its plain
-    # per-thread loops run at ~3 TFLOP/s: measured 243 us against 218 us for the 11-launch chain at batch 1024, so it is
-    # off by default until its inner loops are register-tiled.
-    use_fused_stem = False
+    # eval mode: every layer before the last one in ONE launch (unet_stem_eval.cu), used up to `fused_stem_max_batch`
+    # samples per batch.  Measured (B200, shipped spec): batch 1024 - 150 us against 218 us for the 11-launch chain;
+    # batch 4096 - 577 us against 537 us (its plain per-thread loops run at ~1 TFLOP/s, the chain's tiled kernels at ~3).
+    use_fused_stem = True
+    fused_stem_max_batch = 2048
     use_fused_attention = True  # one launch per decoder block and direction (attention_block.cu); False = unfused chain
     use_patch_head = True       # fused kernel==stride last layer (patch_head.cu); False = generic conv + loss kernels
 
@@ -219,7 +220,7 @@ class UNetEngine(ConvAEEngine):
                                       "(use dropout_rate=0; inference is unaffected)")
         S = []
         src = self._x_src(data, N)
-        if not train and self.use_fused_stem:
+        if not train and self.use_fused_stem and N <= self.fused_stem_max_batch:
             stem = self._eval_stem()
             if stem is not None:
                 nd = len(self.dec3)

@@ -26,7 +26,10 @@ static const int kTileSmemMax = 100 * 1024;
 #define CAE_V2_WGRAD_B 4
 #define CAE_V2_UPDOWN_WIDE 8   // tiled up/down also for wide layers (register tile of 2/4 positions)
 #define CAE_V3_DIRECT 16       // vectorised direct kernels for wide thin layers (k_up3 / k_down3)
-#define CAE_WGRAD_SMALL 32     // warp-per-element weight gradient for layers with few positions (k_wgrad_small)
+// warp-per-element weight gradient for layers with few positions (k_wgrad_small).  OFF by default: alone it is 2x faster
+// than the tiled kernels (33 -> 14 us), but its 1000+ CTAs take the SMs away from the input-gradient chain that runs
+// beside it on the main stream - the whole step got slower (unet 341 -> 350 us, conv 492 -> 528 us).
+#define CAE_WGRAD_SMALL 32
 extern int g_cae_mask;                 // defined in capi.cu
 #define g_mask g_cae_mask
 #define g_use_v2 (g_mask & CAE_V2_UPDOWN)

@@ -48,6 +48,16 @@ __device__ __forceinline__ float src_value(const CaeSrc& s, long long off, const
     return v;
 }
 
+// sigmoid in four SFU / FMA-pipe instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP); relative error ~2e-7 for |v| < 80.
+// Used by the HBM-streaming last-layer kernels, where the IEEE expf + division pair (~25 instructions per pixel) or even
+// __expf + __frcp_rn (~16) dominate the issue slots.
+__device__ __forceinline__ float cae_fast_sigmoid(float v) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

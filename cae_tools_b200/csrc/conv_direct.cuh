@@ -78,7 +78,7 @@ __device__ __forceinline__ void epi_strip(const CaeEpilogue& e, const CaeView& o
         } break;
         case CAE_EPI_SIGMOID:
 #pragma unroll
-            for (int i = 0; i < NE; ++i) res[i] = __fdividef(1.f, 1.f + __expf(-(acc[i] + ch.bias)));
+            for (int i = 0; i < NE; ++i) res[i] = cae_fast_sigmoid(acc[i] + ch.bias);
             break;
         case CAE_EPI_SIGMOID_MSE: {
             const CaeView& t = e.target.t0;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void epi_strip(const CaeEpilogue& e, const CaeView& o
                 const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float yh = __fdividef(1.f, 1.f + __expf(-(acc[4 * q + i] + ch.bias)));
+                    float yh = cae_fast_sigmoid(acc[4 * q + i] + ch.bias);
                     float d = yh - fmaf(tv[i], ch.tk.k0, ch.tk.k2);
                     float dz = 2.f * d * inv_count * yh * (1.f - yh);
                     if (ox0 + 4 * q + i < Wout) {

@@ -47,9 +47,10 @@ struct PhArgs {
 };
 
 __device__ __forceinline__ float4 ph_ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-// sigmoid through the SFU: ex2.approx + rcp (relative error ~2e-7 for |v| < 30, far inside the 1e-4 parity bar); the
-// IEEE expf + division pair costs ~25 instructions per pixel, which made these kernels issue-bound
-__device__ __forceinline__ float ph_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
+// sigmoid: cae_fast_sigmoid (common.cuh) - __expf + __frcp_rn still expand to ~16 instructions (the IEEE-rounded
+// reciprocal is a Newton iteration, ex2 without .ftz carries denormal scaling): ncu showed 127 instructions per 4-pixel
+// strip against 32 FFMA2 of useful work.
+__device__ __forceinline__ float ph_sigmoid(float v) { return cae_fast_sigmoid(v); }
 
 // packed fp32 pairs: sm_100 issues two FMAs per FFMA2 instruction (fma.rn.f32x2), which halves the issue slots of the
 // three 16 x 4 FMA blocks these kernels are made of
@@ -63,6 +64,11 @@ __device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b6
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     f32x2 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
@@ -103,12 +109,19 @@ __device__ __forceinline__ void ph_preact(const W4 (&w)[PH_CIN], const float* sa
         av[2 * q] = t.x;
         av[2 * q + 1] = t.y;
     }
+    // two independent accumulation chains per pair (even / odd channels): the 16-deep FFMA2 chain was the longest
+    // fixed-latency dependency of a strip ("wait" is the top stall reason in ncu)
     acc01 = acc23 = pk(b, b);
+    f32x2 b01 = 0ull, b23 = 0ull;
 #pragma unroll
-    for (int ci = 0; ci < PH_CIN; ++ci) {
+    for (int ci = 0; ci < PH_CIN; ci += 2) {
         acc01 = fma2(av[ci], w[ci].lo, acc01);
         acc23 = fma2(av[ci], w[ci].hi, acc23);
+        b01 = fma2(av[ci + 1], w[ci + 1].lo, b01);
+        b23 = fma2(av[ci + 1], w[ci + 1].hi, b23);
     }
+    acc01 = add2(acc01, b01);
+    acc23 = add2(acc23, b23);
 }
 
 // one CTA (the last of k_ph_fwd to finish): per-plane moments (sum of the patch-row partials, in row order) -> losses +
@@ -612,10 +625,11 @@ extern "C" int cae_patch_head_fwd(const CaePatchHead* h, const CaeView* yhat, vo
     const bool loss = a.target.t0.p != nullptr, mask = loss && a.mask.t0.p != nullptr, write = a.yhat.p != nullptr;
     CAE_REQUIRE(!(loss && write), "patch_head_fwd: writing yhat and computing the loss in one call is not supported "
                                   "(score writes, train / test reduce)");
-    const bool pf2 = a.Win % 2 == 0;
+    const bool pf2 = a.Win % 2 == 0, pf4 = write && a.Win % 4 == 0;     // the write-only variant has registers to spare
 #define PH_FWD(K_, L_, M_, W_)                                                                      \
     do {                                                                                            \
-        if (pf2) k_ph_fwd<K_, L_, M_, W_, 2><<<grid, CAE_NT, smem, st>>>(a);                        \
+        if (W_ && pf4) k_ph_fwd<K_, L_, M_, W_, (W_ ? 4 : 2)><<<grid, CAE_NT, smem, st>>>(a);       \
+        else if (pf2) k_ph_fwd<K_, L_, M_, W_, 2><<<grid, CAE_NT, smem, st>>>(a);                   \
         else k_ph_fwd<K_, L_, M_, W_, 1><<<grid, CAE_NT, smem, st>>>(a);                            \
     } while (0)
     if (K == 32) {

@@ -314,7 +314,9 @@ extern "C" int cae_conv_up(const CaeSrc* in, const float* weight, const CaeConvG
         rc = (a.kh == 3) ? launch_up3<3>(a, st, handled) : launch_up3<4>(a, st, handled);
         if (handled) return rc;
     }
-    if (!v1_only_up && g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+    // (epi_row handles addend / MASK too; measured: with an addend the tiled kernel wins from 32 input channels on -
+    //  unet conv2.dgrad 23 -> 18 us - and loses below - conv1.dgrad 12.5 -> 17.8 us)
+    if (g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4) && (!v1_only_up || a.Cin >= 32)) {
         bool handled = false;
         rc = (a.kh == 3) ? launch_up2<3, 3>(a, st, handled) : launch_up2<4, 4>(a, st, handled);
         if (handled) return rc;
@@ -354,7 +356,7 @@ extern "C" int cae_conv_down(const CaeSrc* in, const float* weight, const CaeCon
         rc = (a.kh == 3) ? launch_down3<3>(a, st, handled) : launch_down3<4>(a, st, handled);
         if (handled) return rc;
     }
-    if (!v1_only_dn && g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
+    if (g_use_v2 && a.s == 2 && a.kh == a.kw && (a.kh == 3 || a.kh == 4)) {
         bool handled = false;
         rc = (a.kh == 3) ? launch_down2<3, 3>(a, st, handled) : launch_down2<4, 4>(a, st, handled);
         if (handled) return rc;

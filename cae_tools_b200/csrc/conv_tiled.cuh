@@ -61,11 +61,33 @@ __device__ __forceinline__ void reduce_over_tk(float* acc, float* scratch, int t
 // ---------------------------------------------------------------------------------------
 template <int NE>
 __device__ __forceinline__ void epi_row(const CaeEpilogue& e, const CaeView& out, const EpiCh& ch, int n, int co, int oy,
-                                        int ox0, const float (&acc)[NE], long long tgt_base, float inv_count, float& s1,
+                                        int ox0, const float (&acc_in)[NE], long long tgt_base, float inv_count, float& s1,
                                         float& s2) {
     const int Wout = out.W;
     float* orow = out.p + ((long long)n * out.sN + (long long)co * out.sC + (long long)oy * out.ld);
+    float accl[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) accl[i] = acc_in[i];
+    if (e.addend.t0.p) {                  // second gradient of the same geometry (skip-connection fan-in)
+        const CaeView& av = e.addend.t0;
+        const long long aoff = (long long)n * av.sN + (long long)co * av.sC + (long long)oy * av.ld;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+            int ox = ox0 + i;
+            if (ox >= 0 && ox < Wout) accl[i] += src_value(e.addend, aoff + ox, ch.ak);
+        }
+    }
+    const float (&acc)[NE] = accl;
     switch (e.mode) {
+        case CAE_EPI_MASK: {
+            const CaeView& a = e.act;
+            const float* arow = a.p + ((long long)n * a.sN + (long long)co * a.sC + (long long)oy * a.ld);
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                int ox = ox0 + i;
+                if (ox >= 0 && ox < Wout) orow[ox] = __ldg(arow + ox) > 0.f ? acc[i] : 0.f;
+            }
+        } break;
         case CAE_EPI_PLAIN:
 #pragma unroll
             for (int i = 0; i < NE; ++i) {

@@ -21,6 +21,8 @@ Kernel schedule for one optimiser step (L_e encoder convs, L_d transposed convs)
 
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -634,9 +636,12 @@ class _Program:
     # concurrently with the input-gradient chain (most launches of this network fill a fraction of the GPU)
     SIDE_SUFFIXES = (".wgrad", ".dW")
     JOIN_BEFORE = ("adam", "grad_allreduce")
-    N_SIDE = 3
+    N_SIDE = int(os.environ.get("CAE_SIDE_STREAMS", "3"))     # 0: everything on one stream
 
     def run_forked(self):
+        if self.N_SIDE <= 0:
+            self.run_eager()
+            return
         main = torch.cuda.current_stream()
         if not hasattr(self, "_side"):
             self._side = [torch.cuda.Stream() for _ in range(self.N_SIDE)]

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=200)
     ap.add_argument("--stride", type=int, default=1, help="time every stride-th prefix")
     ap.add_argument("--kind", default="train", choices=["train", "score", "test"])
+    ap.add_argument("--main-only", action="store_true", help="drop the side-stream ops (weight gradients): the critical chain alone")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -43,6 +44,8 @@ def main():
         eng._eval_prepare_op()()
     full = eng._program(args.kind, data, B)
     sched = full.sched
+    if args.main_only:
+        sched = [(n, op) for n, op in sched if not n.endswith(_Program.SIDE_SUFFIXES)]
     prev = 0.0
     print(f"{'op':34s} {'cumulative us':>14s} {'adds us':>10s}")
     for k in range(1, len(sched) + 1):

@@ -279,12 +279,14 @@ def run_b200(args):
     method = args.method
     spec, enc, dec = build_modules(method)          # identical initial weights on every rank (seed 0)
     hook = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    hook_async = (lambda g: dist.all_reduce(g, async_op=True)) if world > 1 else None
     if method == "unet":
         from cae_tools_b200.engine.unet import UNetEngine
         eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5, device=dev,
-                         grad_hook=hook, grad_scale=1.0 / world)
+                         grad_hook=hook, grad_hook_async=hook_async, grad_scale=1.0 / world)
     else:
-        eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=dev, grad_hook=hook, grad_scale=1.0 / world)
+        eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=dev, grad_hook=hook, grad_hook_async=hook_async,
+                           grad_scale=1.0 / world)
 
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     NB = args.n_batches

@@ -2,8 +2,9 @@
 
 The reference has no multi-GPU path (single `device`, conv_ae_model.py:294-297); this is the
 data-parallel wrapper BASELINE.json's north_star asks for.  Every optimiser step has exactly one
-exchange: a SUM all-reduce of the flat fp32 gradient arena (NCCL over NVLink on GPUs; gloo in the
-CPU tests), captured inside the step's CUDA graph.  Each rank computes on its contiguous share of
+exchange of the flat fp32 gradient arena (NCCL over NVLink on GPUs; gloo in the CPU tests), in two buckets: the
+decoder + fc gradients are SUM-all-reduced asynchronously while the encoder backward still runs, the encoder bucket
+right after it; the optimiser waits for both (engine/convae.py:_BucketedProgram).  Each rank computes on its contiguous share of
 every global batch; the loss epilogue divides by the GLOBAL element count (count_scale =
 n_local/n_global), so the summed gradients - and the summed per-batch losses - are exactly those of
 the global batch.  BatchNorm uses the statistics of the local share ("local BN").  `apply` shards the
@@ -60,6 +61,11 @@ class DPContext:
         """the per-step exchange: in-place SUM over ranks of the flat gradient arena"""
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         return flat
+
+    def allreduce_grads_async(self, bucket):
+        """one gradient bucket (a contiguous slice of the flat arena): SUM over ranks, asynchronous; the caller keeps
+        computing (the encoder backward) and calls .wait() on the handle before the optimiser"""
+        return dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def reduce_losses(self, losses):
         """per-batch losses were divided by the global count on every rank: SUM gives the global batch MSE"""

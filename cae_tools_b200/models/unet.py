@@ -70,7 +70,8 @@ class UNET(ConvAEModel):
         from ..engine.unet import UNetEngine
         kw = dict(lr=self.lr, weight_decay=self.weight_decay, device=device)
         if dp is not None:
-            kw.update(grad_hook=dp.allreduce_grads, count_scale=1.0 / dp.world)
+            kw.update(grad_hook=dp.allreduce_grads, grad_hook_async=dp.allreduce_grads_async,
+                      count_scale=1.0 / dp.world)
         return UNetEngine(self.encoder, self.decoder, lambda_pearson=self.lambda_pearson,
                           dropout_rate=self.dropout_rate, **kw)
 

@@ -33,7 +33,7 @@ def _data():
     return torch.rand(8, 1, 16, 16, generator=g), torch.rand(8, 1, 64, 64, generator=g)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, overlap):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -44,7 +44,8 @@ def _worker(rank, world, port, out_dir):
     enc, dec = _models()
     x, y = _data()
     eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=torch.device("cuda", rank),
-                       grad_hook=dp.allreduce_grads, count_scale=1.0 / world)
+                       grad_hook=dp.allreduce_grads, grad_hook_async=dp.allreduce_grads_async, count_scale=1.0 / world)
+    eng.overlap_allreduce = overlap          # two buckets, the first one reduced while the encoder backward runs
     data = eng.bind(x, y, 8)
     losses = []
     for _ in range(4):
@@ -56,11 +57,12 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_nccl_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_two_rank_nccl_equals_single_gpu(tmp_path, overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), overlap), nprocs=2, join=True)
     got = dict(np.load(os.path.join(str(tmp_path), "dp.npz")))
     from cae_tools_b200.engine.convae import ConvAEEngine
     enc, dec = _models()

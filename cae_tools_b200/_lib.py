@@ -99,6 +99,7 @@ EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_MASK = 0,
 EXPORTS = {
     "cae_last_error": (C.c_char_p, []),
     "cae_version": (C.c_int, []),
+    "cae_struct_size": (C.c_longlong, [C.c_int]),
     "cae_set_kernel_generation": (None, [C.c_int]),
     "cae_partials_len": (C.c_longlong, [C.c_int]),
     "cae_conv_down": (C.c_int, [C.POINTER(CaeSrc), C.c_void_p, C.POINTER(CaeConvGeom), C.POINTER(CaeView),

@@ -3,6 +3,21 @@
 #include "dense_misc.cuh"
 #include "unet_ops.cuh"
 
+extern "C" long long cae_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(CaeView);
+        case 1: return sizeof(CaeSrc);
+        case 2: return sizeof(CaeConvGeom);
+        case 3: return sizeof(CaeBN);
+        case 4: return sizeof(CaeEpilogue);
+        case 5: return sizeof(CaeGemm);
+        case 6: return sizeof(CaePatchHead);
+        case 7: return sizeof(CaeFcStack);
+        case 8: return sizeof(CaeUnetStem);
+        default: return -1;
+    }
+}
+
 // ---- dense / misc ------------------------------------------------------------------------
 extern "C" int cae_gemm(const CaeGemm* g, void* stream) {
     CAE_REQUIRE(g && g->A && g->B && g->C, "gemm: null argument");

@@ -116,6 +116,9 @@ const char* cae_last_error(void);
 /* 1: generic direct kernels only (v1); 2 (default): tiled shared-memory kernels where they apply */
 void cae_set_kernel_generation(int gen);
 int  cae_version(void);
+/* sizeof() of the PODs of this header as the library was compiled (binding self-check): which = 0 CaeView, 1 CaeSrc,
+ * 2 CaeConvGeom, 3 CaeBN, 4 CaeEpilogue, 5 CaeGemm, 6 CaePatchHead, 7 CaeFcStack, 8 CaeUnetStem; -1 otherwise */
+long long cae_struct_size(int which);
 /* number of doubles the `partials` workspace must hold for a kernel whose output has C channels */
 long long cae_partials_len(int C);
 

@@ -40,6 +40,12 @@ def test_struct_sizes_match_c_layout():
     assert ctypes.sizeof(_lib.CaeConvGeom) == 16
     assert ctypes.sizeof(_lib.CaeSrc) == ctypes.sizeof(_lib.CaeView) + 4 * 8 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.CaeBN) == 16 + 15 * 8
+    # ... and every mirror has exactly the size the compiled library sees
+    lib = _lib.lib()
+    for which, cls in enumerate([_lib.CaeView, _lib.CaeSrc, _lib.CaeConvGeom, _lib.CaeBN, _lib.CaeEpilogue, _lib.CaeGemm,
+                                 _lib.CaePatchHead, _lib.CaeFcStack, _lib.CaeUnetStem]):
+        assert lib.cae_struct_size(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib.cae_struct_size(99) == -1
 
 
 def test_product_path_refuses_to_run_without_cuda():

@@ -24,7 +24,12 @@ extern "C" int cae_gemm(const CaeGemm* g, void* stream) {
     CAE_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm: empty problem %dx%dx%d", g->M, g->N, g->K);
     CAE_REQUIRE((!g->a_k0 || (g->a_k2 && g->a_hw > 0)) && (!g->b_k0 || (g->b_k2 && g->b_hw > 0)),
                 "gemm: on-load affine needs k0, k2 and hw");
-    if (!g->a_k0 && !g->b_k0 && !g->a_relu && !g->b_relu && !g->rowsum_A && (long long)g->M * g->N <= 8192) {
+    const bool plain = !g->a_k0 && !g->b_k0 && !g->a_relu && !g->b_relu && !g->rowsum_A;
+    if (plain && g->K >= 256 && (long long)g->M * g->N <= 16384) {
+        k_gemm_warpk<<<ceil_div((long long)g->M * g->N, CAE_NWARP), CAE_NT, 0, (cudaStream_t)stream>>>(*g);
+        return cae_check_launch("cae_gemm(warp-k)");
+    }
+    if (plain && (long long)g->M * g->N <= 8192) {
         k_gemm_skinny<<<ceil_div((long long)g->M * g->N, CAE_NT), CAE_NT, 0, (cudaStream_t)stream>>>(*g);
         return cae_check_launch("cae_gemm(skinny)");
     }

@@ -115,6 +115,35 @@ static __global__ void __launch_bounds__(CAE_NT) k_gemm_skinny(const CaeGemm g) 
     g.C[off] = v;
 }
 
+// Few outputs, long reduction (the ConvAE bottleneck's input gradient: M x N = 64 x 16 outputs, K = 576): one WARP per
+// output element, lanes over k, butterfly sum.  The thread-per-output kernel above walks K serially (37 us for this
+// shape, two dependent loads per step); here every lane does K / 32 steps.
+static __global__ void __launch_bounds__(CAE_NT) k_gemm_warpk(const CaeGemm g) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * CAE_NWARP + (threadIdx.x >> 5);
+    if (idx >= g.M * g.N) return;
+    const int m = idx / g.N, n = idx - m * g.N;
+    const float* ap = g.A + (long long)m * g.sAm;
+    const float* bp = g.B + (long long)n * g.sBn;
+    float acc0 = 0.f, acc1 = 0.f;
+    int k = lane;
+    for (; k + 32 < g.K; k += 64) {
+        const float a0 = __ldg(ap + (long long)k * g.sAk), a1 = __ldg(ap + (long long)(k + 32) * g.sAk);
+        const float b0 = __ldg(bp + (long long)k * g.sBk), b1 = __ldg(bp + (long long)(k + 32) * g.sBk);
+        acc0 = fmaf(a0, b0, acc0);
+        acc1 = fmaf(a1, b1, acc1);
+    }
+    for (; k < g.K; k += 32) acc0 = fmaf(__ldg(ap + (long long)k * g.sAk), __ldg(bp + (long long)k * g.sBk), acc0);
+    float v = warp_sum(acc0 + acc1);
+    if (lane == 0) {
+        if (g.bias) v += __ldg(g.bias + n);
+        if (g.relu_out) v = fmaxf(v, 0.f);
+        const long long off = (long long)m * g.sCm + (long long)n * g.sCn;
+        if (g.mask) v = __ldg(g.mask + off) > 0.f ? v : 0.f;
+        g.C[off] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // eval-mode BatchNorm: scale/shift from the running statistics; one CTA per layer
 // ---------------------------------------------------------------------------------------

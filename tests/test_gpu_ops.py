@@ -359,6 +359,26 @@ def test_gemm_variants():
     close(dx, (dy.double() @ W.double()) * (mask.double() > 0), what="gemm dx")
 
 
+@pytest.mark.parametrize("K", [256, 576, 1000])
+def test_gemm_long_k_few_outputs(K):
+    """the warp-per-output path (cae_gemm with K >= 256 and M*N <= 16384): bias, relu, mask, strided operands"""
+    from cae_tools_b200.engine import ops
+    dev = _dev()
+    N, O = 64, 16
+    dy = rnd(N, K, seed=171).float()
+    W = rnd(K, O, seed=172, scale=0.2).float()              # nn.Linear weight [out = K][in = O]: dx = dy W
+    mask = rnd(N, O, seed=173).float()
+    b = rnd(O, seed=174).float()
+    dx = torch.empty(N, O, device=dev)
+    ops.gemm(N, O, K, dy.to(dev), K, 1, W.to(dev), O, 1, dx, O, 1, mask=mask.to(dev))
+    torch.cuda.synchronize()
+    close(dx, (dy.double() @ W.double()) * (mask.double() > 0), what="dx long K")
+    out = torch.empty(N, O, device=dev)
+    ops.gemm(N, O, K, dy.to(dev), K, 1, W.to(dev), O, 1, out, O, 1, bias=b.to(dev), relu_out=True)
+    torch.cuda.synchronize()
+    close(out, F.relu(dy.double() @ W.double() + b.double()), what="fwd long K")
+
+
 @pytest.mark.parametrize("decoupled", [False, True])
 def test_adam_matches_torch(decoupled):
     from cae_tools_b200.engine import ops

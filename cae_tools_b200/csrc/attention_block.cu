@@ -285,7 +285,9 @@ extern "C" int cae_attention_block_fwd(const CaeView* y, const CaeSrc* skip, con
     }
     const int C = y->C, HW = y->H * y->W;
     const size_t smem = (size_t)((C * HW + 3 * C + 2 * Cr + 1) & ~1) * 4 + (size_t)4 * C * 8;
-    const int rows = min(ab_rows(y->N), CAE_MAX_GRID_X);
+    // training: one partial row per CTA (<= AB_MAX_ROWS, CTAs loop over samples); eval: no cross-sample state at all, so
+    // one CTA per sample up to 16 waves of the machine (apply() batches of 4096 ran 14 samples per CTA in sequence)
+    const int rows = a.train ? min(ab_rows(y->N), CAE_MAX_GRID_X) : min(y->N, CAE_NUM_SMS * 8 * 16);
     k_att_block_fwd<<<rows, CAE_NT, smem, (cudaStream_t)stream>>>(a);
     return cae_check_launch("cae_attention_block_fwd");
 }

@@ -254,8 +254,7 @@ class UNetEngine(ConvAEEngine):
                                   a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True, bn1=blk1, bn3=blk3,
                                   train=train, relu_mid=True)
             S.append(("fwd.fcstack", lambda p=p: ops.fc_stack_fwd(p)))
-        S_chain = S if not fused_fc else []
-        S, S_keep = S_chain, S
+        S_main, S = S, []          # the cae_gemm chain is collected on its own and dropped when the fused kernel runs
         S.append(("fwd.fc1", lambda: ops.gemm(N, fc_e, flat, ylast, flat, 1, lin[0].weight, 1, flat, b["t1"], fc_e, 1,
                                               a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True,
                                               bias=lin[0].bias)))
@@ -273,7 +272,7 @@ class UNetEngine(ConvAEEngine):
         S.append(("fwd.fc4", lambda: ops.gemm(N, flat0, fc_d, b["t3"], fc_d, 1, dlin[4].weight, 1, fc_d, b["u"], flat0,
                                               1, a_k0=s3[0], a_k2=s3[1], a_hw=1, a_relu=True, bias=dlin[4].bias,
                                               relu_out=True)))
-        S = S_keep
+        S = S_main + ([] if fused_fc else S)
         # ---- decoder
         src = ops.make_src(b["u"], n=N)
         nd, ne = len(self.dec3), len(self.enc_layers)
@@ -401,7 +400,7 @@ class UNetEngine(ConvAEEngine):
                                   a_k0=s_last[0], a_k2=s_last[1], a_hw=he * we, a_relu=True, bn1=blk1, bn3=blk3,
                                   train=True, relu_mid=True, du=b["du"], grads=G, dA=b["da"])
             S.append(("bwd.fcstack", lambda p=p: ops.fc_stack_bwd(p)))
-        S_keep, S = S, (S if not fused_fc else [])
+        S_main, S = S, []          # (same pattern as in the forward schedule)
         # decoder_lin.4: u = relu(a3 W^T + b), a3 = relu(bn1d(t3))
         S.append(("bwd.fc4.dW", lambda: ops.gemm(flat0, fc_d, N, b["du"], 1, flat0, b["t3"], fc_d, 1, G(dlin[4].weight),
                                                  fc_d, 1, b_k0=s3[0], b_k2=s3[1], b_hw=1, b_relu=True,
@@ -440,7 +439,7 @@ class UNetEngine(ConvAEEngine):
                                                  1, b_k0=s_last[0], b_k2=s_last[1], b_hw=he * we, b_relu=True)))
         S.append(("bwd.fc1.dx", lambda: ops.gemm(N, flat, fc_e, b["dt1"], fc_e, 1, lin[0].weight, flat, 1, b["da"], flat,
                                                  1)))
-        S = S_keep
+        S = S_main + ([] if fused_fc else S)
         # ---- encoder
         conv, bn = self.enc_layers[ne - 1]
         blk, _ = self._bn(("e", ne - 1), bn, G(conv.bias))

@@ -79,7 +79,15 @@ def _worker(rank, world, port, out_dir):
         m.optim.zero_grad()
         loss.backward()
         flat = torch.cat([p.grad.reshape(-1) for p in m.params])
-        dp.allreduce_grads(flat)                                 # the per-step exchange
+        if step == 1:
+            # the bucketed variant (engine/convae.py:_BucketedProgram): two contiguous slices of the arena, each reduced
+            # asynchronously, both waited for before the optimiser
+            cut = flat.numel() // 3
+            handles = [dp.allreduce_grads_async(flat[cut:]), dp.allreduce_grads_async(flat[:cut])]
+            for h in handles:
+                h.wait()
+        else:
+            dp.allreduce_grads(flat)                             # the per-step exchange
         off = 0
         for p in m.params:
             p.grad.copy_(flat[off:off + p.numel()].view_as(p))

@@ -102,3 +102,19 @@ def test_xr_lite_netcdf_roundtrip(tmp_path):
     assert back["hires"].dims == ("n", "chan", "y2", "x2")
     both = xr_lite.open_mfdataset([path, path], concat_dim="box", combine="nested")
     assert both["lowres"].shape == (4, 1, 3, 4)
+
+
+def test_bench_algorithmic_bytes_convention():
+    """B_train = 2 in + 5 inter + 5 out, B_apply = in + 2 inter + out (fp32) - the roofline numerators"""
+    import bench
+    spec, enc, dec = bench.build_modules("conv")
+    bt, ba = bench.bytes_per_sample(spec, bench.FC, bench.LATENT)
+    assert (bt, ba) == (2547488, 757056)                       # the figures SURVEY 8(d) states for config 1
+    uspec, _, _ = bench.build_modules("unet")
+    bt, ba = bench.bytes_per_sample(uspec, bench.FC, bench.LATENT)
+    inter = 4 * (8 * 8 * 8 + 16 * 4 * 4 + 32 * 2 * 2 + 16 * 4 * 4 + 8 * 8 * 8 + 16 + 4 + 16 + 32 * 2 * 2)
+    assert bt == 2 * 1024 + 5 * inter + 5 * 262144 and ba == 1024 + 2 * inter + 262144
+    # per-launch bytes of the fused head: input + one pass over the target (forward), + act / gradient of the input (backward)
+    assert bench.op_bytes("fwd.head2+sigmoid+loss", uspec, 64) == 4 * 64 * (16 * 8 * 8 + 256 * 256)
+    assert bench.op_bytes("bwd.head2", uspec, 64) == 4 * 64 * (3 * 16 * 8 * 8 + 256 * 256)
+    assert bench.op_bytes("bwd.convT0.db", uspec, 64) is None

@@ -282,3 +282,34 @@ class OracleUNet:
     def score(self, x):
         with torch.no_grad():
             return unet_forward(self.enc, self.dec, self.spec, x, False)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LinearModel (reference: src/cae_tools/models/linear.py:33-49, linear_model.py:142-184,236-242)
+# ---------------------------------------------------------------------------------------------------------------
+class OracleLinear:
+    """Flatten - nn.Linear - Unflatten with MSELoss and Adam(lr, weight_decay): the reference's `--method linear`"""
+
+    def __init__(self, sd, out_shape, lr=1e-3, weight_decay=1e-5):
+        self.w = sd["linear.1.weight"].detach().clone().float().requires_grad_(True)
+        self.b = sd["linear.1.bias"].detach().clone().float().requires_grad_(True)
+        self.out_shape = tuple(out_shape)
+        self.optim = torch.optim.Adam([self.w, self.b], lr=lr, weight_decay=weight_decay)
+
+    def forward(self, x):
+        return F.linear(x.flatten(1), self.w, self.b).view(-1, *self.out_shape)
+
+    def train_step(self, x, y):
+        loss = F.mse_loss(self.forward(x), y)
+        self.optim.zero_grad()
+        loss.backward()
+        self.optim.step()
+        return float(loss.detach())
+
+    def test_loss(self, x, y):
+        with torch.no_grad():
+            return float(F.mse_loss(self.forward(x), y))
+
+    def score(self, x):
+        with torch.no_grad():
+            return self.forward(x)

@@ -4,9 +4,11 @@
 //   decoder  [ConvTranspose2d, ChannelAttention gate, concat with the encoder skip, BatchNorm2d(eval), ReLU] x n_up
 //            (unet.py:23-39,131-163)
 // In eval mode BatchNorm is a per-channel affine, so nothing couples the samples of a batch: a CTA takes STEM_S samples
-// through the whole stem with every activation in shared memory (<= 3 K floats per sample for the shipped spec) and
-// only the weights (L1 / L2 resident, each load shared by the STEM_S samples) and the final activated concat tensor
-// touch global memory.  Replaces 11 launches that together took 47 % of an apply() batch.
+// through the whole stem with every activation in shared memory (<= 3 K floats per sample for the shipped spec); each
+// layer's weights are staged through shared memory as well (every weight load is shared by the STEM_S samples) and only
+// the final activated concat tensor is written to global memory.  Replaces the 11 launches before the head.
+// Measured (B200): 150 us against 218 us for the chain at batch 1024, 577 against 537 us at 4096 - the inner loops are
+// plain per-thread loops with run-time geometry (~1 TFLOP/s); the engine uses this kernel for batches <= 2048.
 #include "capi_host.h"
 
 #define STEM_S 4

@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--method", default="unet", choices=["unet", "conv"])
+    ap.add_argument("--method", default="unet", choices=["unet", "conv", "var"])
     ap.add_argument("--n-batches", type=int, default=N_BATCHES,
                     help="device-resident batches the steps cycle through (small values only for runs under ncu, whose "
                          "kernel replay saves / restores all device memory)")
@@ -193,12 +193,15 @@ def build_modules(method):
     from cae_tools_b200.models.encoder import Encoder
     spec = create_model_spec(input_size=IN_SHAPE[1:], input_channels=IN_SHAPE[0], output_size=OUT_SHAPE[1:],
                              output_channels=OUT_SHAPE[0])
+    if method == "var":
+        from cae_tools_b200.models.var_encoder import VarEncoder
+        return spec, VarEncoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
     return spec, Encoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
 
 
 def cpu_train_rate(method, batch, steps, warmup):
     import torch
-    from oracle.torch_port import OracleModel, OracleUNet
+    from oracle.torch_port import OracleModel, OracleUNet, OracleVarModel
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     spec, enc, dec = build_modules(method)
@@ -207,6 +210,9 @@ def cpu_train_rate(method, batch, steps, warmup):
         m = OracleUNet(enc.state_dict(), dec.state_dict(), spec.save(), lambda_pearson=1.0)
         ones = torch.ones_like(y)
         step = lambda: m.train_step(x, y, ones)
+    elif method == "var":
+        m = OracleVarModel(enc.state_dict(), dec.state_dict(), spec.save(), lambda_mse=1.0, lambda_kl=1.0)
+        step = lambda: m.train_step(x, y, torch.randn(batch, LATENT))
     else:
         m = OracleModel(enc.state_dict(), dec.state_dict(), spec.save())
         step = lambda: m.train_step(x, y)
@@ -249,6 +255,9 @@ def workload_config(method, batch, world):
         w = ("UNET method=unet 1x16x16->1x256x256 with skip connections + channel attention (BASELINE configs[1]): shipped "
              "spec enc 8x8x8/16x4x4/32x2x2 (k3 s2 p1), dec k4 s2 p1 x2 + k32 s32 head, latent 4, fc 16, dropout 0, "
              "loss masked-MSE + 1.0*(1 - Pearson), AdamW, fp32")
+    elif method == "var":
+        w = ("VarAEModel method=var 1x16x16->1x256x256 (BASELINE configs[2] geometry; the reference ships no implementation - "
+             "parity unpinned), latent 4, fc 16, k3 s2, loss MSE + KL, reparameterisation noise drawn on the device, Adam, fp32")
     else:
         w = "ConvAEModel method=conv 1x16x16->1x256x256, latent 4, fc 16, k3 s2 (BASELINE configs[0] geometry), MSE, Adam, fp32"
     return {"workload": w, "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
@@ -284,6 +293,10 @@ def run_b200(args):
         from cae_tools_b200.engine.unet import UNetEngine
         eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5, device=dev,
                          grad_hook=hook, grad_hook_async=hook_async, grad_scale=1.0 / world)
+    elif method == "var":
+        from cae_tools_b200.engine.varae import VarAEEngine
+        eng = VarAEEngine(enc, dec, lambda_mse=1.0, lambda_kl=1.0, lr=1e-3, weight_decay=1e-5, device=dev,
+                          grad_hook=hook, grad_scale=1.0 / world)
     else:
         eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=dev, grad_hook=hook, grad_hook_async=hook_async,
                            grad_scale=1.0 / world)

@@ -3,6 +3,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from helpers import load_npz, split_sd
@@ -118,3 +119,27 @@ def test_bench_algorithmic_bytes_convention():
     assert bench.op_bytes("fwd.head2+sigmoid+loss", uspec, 64) == 4 * 64 * (16 * 8 * 8 + 256 * 256)
     assert bench.op_bytes("bwd.head2", uspec, 64) == 4 * 64 * (3 * 16 * 8 * 8 + 256 * 256)
     assert bench.op_bytes("bwd.convT0.db", uspec, 64) is None
+
+
+def test_linear_container_matches_reference_module_tree():
+    """`--method linear`: same state_dict keys and the same initial values for the same seed as the reference's module
+    (skipped where the reference tree is not mounted)"""
+    import importlib.util
+    import torch
+    path = "/root/reference/src/cae_tools/models/linear.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not available")
+    spec = importlib.util.spec_from_file_location("_ref_linear", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from cae_tools_b200.models.linear import Linear
+    torch.manual_seed(1)
+    a = Linear((1, 4, 4), (2, 3, 3)).state_dict()
+    torch.manual_seed(1)
+    b = ref.Linear((1, 4, 4), (2, 3, 3)).state_dict()
+    assert list(a.keys()) == list(b.keys()) == ["linear.1.weight", "linear.1.bias"]
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    from cae_tools_b200.models.linear_model import LinearModel
+    m = LinearModel(batch_size=7, lr=0.01)
+    assert (m.batch_size, m.lr, m.weight_decay, m.test_interval) == (7, 0.01, 1e-5, 10)
+    assert m.summary() == "Model has not been trained"

@@ -428,7 +428,7 @@ def run_b200(args):
                                "frac": b_apply * AB / (ms_apply / Ka / 1e3) / 1e9 / hbm_peak}}
 
     # ncu --set full (profiles/r01_head_ncu.md): DRAM bytes of one launch of the fused head kernels at batch 64
-    NCU_TRAFFIC = {"bwd.head2": 17172480, "fwd.head2+sigmoid+loss": 17160704}
+    NCU_TRAFFIC = {"bwd.head2": 17163008, "fwd.head2+sigmoid+loss": 17154048}
     if B == 64 and method == "unet" and top[0] in NCU_TRAFFIC:
         roofline["traffic"] = NCU_TRAFFIC[top[0]]
         roofline["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_head_ncu.md"

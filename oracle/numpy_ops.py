@@ -83,3 +83,50 @@ def adam_step(p, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, wd=0.0, decoup
     v = b2 * v + (1 - b2) * g * g
     p = p - (lr / (1 - b1 ** t)) * m / (np.sqrt(v) / np.sqrt(1 - b2 ** t) + eps)
     return p, m, v
+
+
+# ---- UNET pieces (reference: src/cae_tools/models/unet.py) --------------------------------------------------------------
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-np.asarray(x, np.float64)))
+
+
+def channel_attention(y, w1, w2):
+    """att[n,c] = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max)), avg / max over (H, W); W1 [Cr,C], W2 [C,Cr] are the 1x1
+    convolutions without bias of ChannelAttention (unet.py:23-39).  Returns att with shape [N, C, 1, 1]."""
+    y = np.asarray(y, np.float64)
+    w1 = np.asarray(w1, np.float64).reshape(w1.shape[0], -1)
+    w2 = np.asarray(w2, np.float64).reshape(w2.shape[0], -1)
+    avg, mx = y.mean(axis=(2, 3)), y.max(axis=(2, 3))
+    branch = lambda v: np.maximum(v @ w1.T, 0.0) @ w2.T
+    return sigmoid(branch(avg) + branch(mx))[:, :, None, None]
+
+
+def masked_mse(pred, target, mask):
+    """sum(((pred - target) * mask)^2) / sum(mask)   (unet.py:635-639)"""
+    pred, target, mask = (np.asarray(a, np.float64) for a in (pred, target, mask))
+    d = (pred - target) * mask
+    return float(np.sum(d * d) / np.sum(mask))
+
+
+def pearson_corr(pred, target, mask):
+    """masked Pearson correlation per (sample, channel) plane, the +1e-8 terms exactly where the reference puts them
+    (unet.py:641-678); loops over planes, no broadcasting tricks.  Returns [N, C]."""
+    pred, target, mask = (np.asarray(a, np.float64) for a in (pred, target, mask))
+    N, C = pred.shape[:2]
+    mask = np.broadcast_to(mask, pred.shape)
+    out = np.zeros((N, C))
+    for n in range(N):
+        for c in range(C):
+            d, t, m = pred[n, c].ravel(), target[n, c].ravel(), mask[n, c].ravel()
+            M = m.sum()
+            mu_d, mu_t = (d * m).sum() / (M + 1e-8), (t * m).sum() / (M + 1e-8)
+            sd = np.sqrt((m * (d - mu_d) ** 2).sum() / (M + 1e-8) + 1e-8)
+            st = np.sqrt((m * (t - mu_t) ** 2).sum() / (M + 1e-8) + 1e-8)
+            out[n, c] = (m * ((d - mu_d) / sd) * ((t - mu_t) / st)).sum() / M
+    return out
+
+
+def linear(x, w, b=None):
+    """y = x W^T + b  (nn.Linear)"""
+    y = np.asarray(x, np.float64) @ np.asarray(w, np.float64).T
+    return y if b is None else y + np.asarray(b, np.float64)

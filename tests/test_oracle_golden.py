@@ -153,3 +153,48 @@ def test_unet_port_matches_reference(name):
             if ref.dtype.kind == "f":
                 assert np.abs(v.detach().numpy() - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-3), k
     assert rel_err(m.score(x).numpy(), g["eval_yhat"]) < 2e-4
+
+
+@pytest.mark.parametrize("name", ["nomask", "mask", "head16_mask"])
+def test_numpy_unet_definitions_match_reference_values(name):
+    """oracle/numpy_ops restatements of the UNET pieces against numbers the REFERENCE itself produced (golden fixtures
+    written by oracle/gen_golden.py from cae_tools.models.unet): the loss terms of step 0 from its yhat, the first
+    decoder block (transposed conv -> ChannelAttention gate -> concat -> BatchNorm -> ReLU -> next transposed conv),
+    the last layer + sigmoid."""
+    from oracle import numpy_ops as npo
+    g = load_npz(f"unet_{name}.npz")
+    spec = spec_of(g)
+    mask = g["mask"]
+    assert abs(npo.masked_mse(g["yhat"], g["y"], mask) - g["mse"][0]) <= 1e-6 * g["mse"][0]
+    pl = 1.0 - npo.pearson_corr(g["yhat"], g["y"], mask).mean()
+    assert abs(pl - g["pearson_loss"][0]) <= 2e-6 * abs(g["pearson_loss"][0])
+    # encoder skip activations: relu(bn_train(conv)) of the golden raw conv outputs
+    enc = split_sd(g, "init.enc.")
+    dec = split_sd(g, "init.dec.")
+    skips = []
+    for i in range(len(spec["input_layers"])):
+        raw = g[f"act.enc.{4 * i}"]
+        a, _, _ = npo.batch_norm_train(raw, enc[f"encoder_cnn.{4 * i + 1}.weight"].numpy(), enc[f"encoder_cnn.{4 * i + 1}.bias"].numpy(),
+                                       np.zeros(raw.shape[1]), np.ones(raw.shape[1]))
+        skips.append(np.maximum(a, 0.0))
+    # decoder block 0: gate the golden raw output, concat the deepest-but-one skip, BN, ReLU, then the next transposed conv
+    y0 = g["act.dec.0"]
+    att = npo.channel_attention(y0, dec["attention_layers.0.fc1.weight"].numpy(), dec["attention_layers.0.fc2.weight"].numpy())
+    cat = np.concatenate([y0 * att, skips[-2]], axis=1)
+    a0, _, _ = npo.batch_norm_train(cat, dec["decoder_conv.1.weight"].numpy(), dec["decoder_conv.1.bias"].numpy(),
+                                    np.zeros(cat.shape[1]), np.ones(cat.shape[1]))
+    sp1 = spec["output_layers"][1]
+    y1 = npo.conv_transpose2d(np.maximum(a0, 0.0), dec["decoder_conv.4.weight"].numpy(), dec["decoder_conv.4.bias"].numpy(),
+                              sp1["stride"], pad=sp1["output_padding"])
+    assert rel_err(y1, g["act.dec.4"]) < 1e-5
+    # last layer: the golden raw output of the last transposed conv through the sigmoid is the golden prediction
+    last = 4 * (len(spec["output_layers"]) - 1)
+    assert rel_err(npo.sigmoid(g[f"act.dec.{last}"]), g["yhat"]) < 1e-6
+
+
+def test_numpy_linear_and_adamw_match_torch():
+    from oracle import numpy_ops as npo
+    rng = np.random.RandomState(3)
+    x, w, b = rng.randn(5, 7), rng.randn(4, 7), rng.randn(4)
+    ref = torch.nn.functional.linear(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b)).numpy()
+    np.testing.assert_allclose(npo.linear(x, w, b), ref, atol=1e-12)

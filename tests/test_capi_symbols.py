@@ -63,3 +63,16 @@ def test_product_path_refuses_to_run_without_cuda():
     m2 = ConvAEModel(use_gpu=False)
     with pytest.raises(CaeError):
         m2.train(["lowres"], "hires", tr, te)
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under cae_tools_b200/ may import or execute it"""
+    pkg = os.path.join(ROOT, "cae_tools_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "import_module(\"oracle" in text:
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders

@@ -16,6 +16,7 @@ for method in ("unet", "conv"):
     spec, enc, dec = bench.build_modules(method)
     eng = (UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, device=dev, use_graphs=False) if method == "unet"
            else ConvAEEngine(enc, dec, device=dev, use_graphs=False))
+    eng.use_fused_fc = True        # the one-launch fc bottleneck is off by default
     X, Y = torch.rand(64, *bench.IN_SHAPE, device=dev), torch.rand(64, *bench.OUT_SHAPE, device=dev)
     data = eng.bind(X, Y, 64)
     for _ in range(2):

@@ -93,6 +93,13 @@ class CaeUnetStem(C.Structure):
                 ("fc", CaeStemFc * STEM_MAX), ("up", CaeStemUp * STEM_MAX)]
 
 
+class CaeTcGemm(C.Structure):
+    _fields_ = [("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("a_hi", C.c_void_p), ("a_lo", C.c_void_p),
+                ("lda", C.c_longlong), ("a_mn_major", C.c_int), ("b_hi", C.c_void_p), ("b_lo", C.c_void_p),
+                ("ldb", C.c_longlong), ("b_mn_major", C.c_int), ("C", C.c_void_p), ("ldc", C.c_longlong),
+                ("splits", C.c_int), ("split_stride", C.c_longlong), ("tile_n", C.c_int)]
+
+
 EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_MASK = 0, 1, 2, 3, 4, 5
 
 # every symbol include/cae_b200.h declares
@@ -151,6 +158,8 @@ EXPORTS = {
                                      C.c_void_p]),
     "cae_patch_head_wgrad_reduce": (C.c_int, [C.POINTER(CaePatchHead), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cae_patch_head_partials_len": (C.c_longlong, [C.POINTER(CaePatchHead)]),
+    "cae_tc_gemm": (C.c_int, [C.POINTER(CaeTcGemm), C.c_void_p]),
+    "cae_tc_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cae_randn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
 }
 

@@ -14,6 +14,7 @@ extern "C" long long cae_struct_size(int which) {
         case 6: return sizeof(CaePatchHead);
         case 7: return sizeof(CaeFcStack);
         case 8: return sizeof(CaeUnetStem);
+        case 9: return sizeof(CaeTcGemm);
         default: return -1;
     }
 }

@@ -10,7 +10,7 @@ import ctypes as C
 
 import torch
 
-from .._lib import (CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
+from .._lib import (CaeTcGemm, CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
                     CaeUnetStem, CaeView, STEM_MAX, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
                     EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
 
@@ -362,3 +362,16 @@ def fc_stack_fwd(p: CaeFcStack):
 
 def fc_stack_bwd(p: CaeFcStack):
     check(lib().cae_fc_stack_bwd(C.byref(p), _stream()), "cae_fc_stack_bwd")
+
+
+# ---- tensor-core GEMM (tcgen05 / TMEM / TMA) ---------------------------------------------------------------------------
+def tc_split(x, hi, lo):
+    """hi = x with the low 13 mantissa bits cleared, lo = x - hi (operands of the 3xTF32 GEMM)"""
+    check(lib().cae_tc_split(_ptr(x), _ptr(hi), _ptr(lo), int(x.numel()), _stream()), "cae_tc_split")
+
+
+def tc_gemm(M, N, K, a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, Cout, ldc, splits=1, split_stride=0, tile_n=128):
+    """C[m,n] = sum_k A[m,k] B[n,k]; operands K-major (x[row*ld + k]) or MN-major (x[k*ld + row]); lo=None: 1xTF32"""
+    g = CaeTcGemm(int(M), int(N), int(K), _ptr(a_hi), _ptr(a_lo), int(lda), int(bool(a_mn)), _ptr(b_hi), _ptr(b_lo),
+                  int(ldb), int(bool(b_mn)), _ptr(Cout), int(ldc), int(splits), int(split_stride), int(tile_n))
+    check(lib().cae_tc_gemm(C.byref(g), _stream()), "cae_tc_gemm")

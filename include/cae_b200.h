@@ -347,6 +347,32 @@ int cae_randn(float* out, long long n, unsigned long long seed, const int* step_
 /* out = a + b (gradient fan-in) */
 int cae_add2(const float* a, const float* b, float* out, long long n, void* stream);
 
+/* ---- tensor-core GEMM (tc_gemm.cu): tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA ----------
+ * C[m,n] = sum_k A[m,k] * B[n,k] for the genuinely dense contractions of the path: the fat ConvTranspose2d layers
+ * (decoder.py:44-48 -> aten::convolution / convolution_backward: Cin >= 64) as GEMM + col2im / im2col, and nn.Linear
+ * (linear.py:43, unet.py:92-100,121-129).  Operands arrive split for 3xTF32 (x = hi + lo, cae_tc_split or the
+ * producers below): hi*hi + hi*lo + lo*hi keeps ~2^-21 relative error per product (the path's 1e-4 bar); a_lo = b_lo =
+ * NULL selects 1xTF32.  An operand is K-major (A[m*lda + k]) or MN-major (A[k*lda + m]); pitches are multiples of 4
+ * floats, pointers 16-byte aligned.  splits > 1: split-K, slice z writes its partial tile to C + z*split_stride (the
+ * caller reduces the slices in a fixed order: cae_tc_reduce).  tile_n: 128 (default) or 256. */
+typedef struct CaeTcGemm {
+    int M, N, K;
+    const float *a_hi, *a_lo;
+    long long lda;
+    int a_mn_major;
+    const float *b_hi, *b_lo;
+    long long ldb;
+    int b_mn_major;
+    float* C;
+    long long ldc;
+    int splits;
+    long long split_stride;
+    int tile_n;
+} CaeTcGemm;
+int cae_tc_gemm(const CaeTcGemm* g, void* stream);
+/* hi = x with the low 13 mantissa bits cleared, lo = x - hi */
+int cae_tc_split(const float* x, float* hi, float* lo, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

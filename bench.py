@@ -45,15 +45,30 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--method", default="unet", choices=["unet", "conv", "var"])
-    ap.add_argument("--n-batches", type=int, default=N_BATCHES,
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 64; conv4: 128)")
+    ap.add_argument("--method", default="unet", choices=["unet", "conv", "var", "conv4"],
+                    help="conv4 = BASELINE configs[3]: synthetic 4x64x64 -> 4x1024x1024 ConvAE, batch 128")
+    ap.add_argument("--n-batches", type=int, default=None,
                     help="device-resident batches the steps cycle through (small values only for runs under ncu, whose "
                          "kernel replay saves / restores all device memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
     ap.add_argument("--train-only", action="store_true", help="skip the e2e / apply legs (short runs under ncu)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    set_workload(a.method)
+    if a.batch is None:
+        a.batch = 128 if a.method == "conv4" else BATCH
+    if a.n_batches is None:
+        a.n_batches = 2 if a.method == "conv4" else N_BATCHES      # conv4: one batch of targets alone is 2.1 GB
+    return a
+
+
+def set_workload(method):
+    """shapes of the synthetic data per method (module globals read by every leg)"""
+    global IN_SHAPE, OUT_SHAPE, APPLY_BATCH, APPLY_BATCHES
+    if method == "conv4":
+        IN_SHAPE, OUT_SHAPE = (4, 64, 64), (4, 1024, 1024)
+        APPLY_BATCH, APPLY_BATCHES = 128, 2
 
 
 def free_port():
@@ -99,6 +114,8 @@ def op_bytes(name, spec, B):
         return f * (3 * numel(dec[-1][0]) + numel(dec[-1][1]))
     if name.startswith("bwd.") and not name.endswith((".wgrad", ".dgrad")):
         return None
+    if ".tc" in name:
+        return None                          # tensor-core layers are compute-bound: see the "tensor" roofline entry
     if name.startswith("fwd.convT"):
         j = int(name[len("fwd.convT"):].split("+")[0])
         b = f * (numel(dec[j][0]) + numel(dec[j][1]))
@@ -121,6 +138,19 @@ def op_bytes(name, spec, B):
             return f * (numel(enc[i][0]) + dy)
         return f * (dy + 2 * numel(enc[i][0]))
     return None
+
+
+def tc_flops(name, spec, B):
+    """fp32-equivalent FLOPs (2 * MACs) of one tensor-core launch group of decoder layer j"""
+    if ".tc" not in name or "im2col" in name:
+        return None
+    enc, dec = layer_table(spec)
+    j = int(name.split("convT")[1].split(".")[0])
+    lay = spec.get_output_layers()[j]
+    k = lay.get_kernel_size()
+    kh, kw = (k if isinstance(k, (tuple, list)) else (k, k))
+    (ci, hi, wi), (co, _, _) = dec[j]
+    return 2.0 * B * hi * wi * ci * co * kh * kw
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -191,8 +221,10 @@ def build_modules(method):
         return spec, UNetEncoder(spec.get_input_layers(), LATENT, FC, 0.0), UNetDecoder(spec.get_output_layers(), LATENT, FC, 0.0)
     from cae_tools_b200.models.decoder import Decoder
     from cae_tools_b200.models.encoder import Encoder
-    spec = create_model_spec(input_size=IN_SHAPE[1:], input_channels=IN_SHAPE[0], output_size=OUT_SHAPE[1:],
-                             output_channels=OUT_SHAPE[0])
+    if method == "conv4":
+        spec = create_model_spec(input_size=(64, 64), input_channels=4, output_size=(1024, 1024), output_channels=4)
+        return spec, Encoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
+    spec = create_model_spec(input_size=(16, 16), input_channels=1, output_size=(256, 256), output_channels=1)
     if method == "var":
         from cae_tools_b200.models.var_encoder import VarEncoder
         return spec, VarEncoder(spec.get_input_layers(), LATENT, FC), Decoder(spec.get_output_layers(), LATENT, FC)
@@ -205,7 +237,8 @@ def cpu_train_rate(method, batch, steps, warmup):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     spec, enc, dec = build_modules(method)
-    x, y = torch.rand(batch, *IN_SHAPE), torch.rand(batch, *OUT_SHAPE)
+    ishape, oshape = ((4, 64, 64), (4, 1024, 1024)) if method == "conv4" else ((1, 16, 16), (1, 256, 256))
+    x, y = torch.rand(batch, *ishape), torch.rand(batch, *oshape)
     if method == "unet":
         m = OracleUNet(enc.state_dict(), dec.state_dict(), spec.save(), lambda_pearson=1.0)
         ones = torch.ones_like(y)
@@ -236,14 +269,17 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 60))      # bounded sample: ~0.15 s per step on 8 cores
-    rate, ms, cores, apply_rate = cpu_train_rate(args.method, args.batch, steps, max(1, min(args.warmup, 3)))
+    cpu_batch = args.batch
+    if args.method == "conv4":               # 3.6 GFLOP per sample and step: a few batch-8 steps are the bounded sample
+        steps, cpu_batch = min(steps, 3), min(args.batch, 8)
+    rate, ms, cores, apply_rate = cpu_train_rate(args.method, cpu_batch, steps, max(1, min(args.warmup, 3 if args.method != "conv4" else 1)))
     line = {
         "impl": "reference", "metric": "train_samples_per_sec", "value": rate, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.method, args.batch, 1),
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} optimiser steps at batch {args.batch} (oracle/torch_port.py, torch CPU)"},
+                         "sample": f"{steps} optimiser steps at batch {cpu_batch} (oracle/torch_port.py, torch CPU)"},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "apply": {"value": apply_rate, "unit": "images/s"},
     }
@@ -258,11 +294,16 @@ def workload_config(method, batch, world):
     elif method == "var":
         w = ("VarAEModel method=var 1x16x16->1x256x256 (BASELINE configs[2] geometry; the reference ships no implementation - "
              "parity unpinned), latent 4, fc 16, k3 s2, loss MSE + KL, reparameterisation noise drawn on the device, Adam, fp32")
+    elif method == "conv4":
+        w = ("ConvAEModel method=conv synthetic 4x64x64->4x1024x1024 (BASELINE configs[3]): spec from create_model_spec "
+             "(4 encoder convs, 8 transposed convs 1024->512->...->8->4), latent 4, fc 16, k3 s2, MSE, Adam, fp32; decoder "
+             "layers with >= 64 input channels run as tcgen05 3xTF32 GEMMs (tc_conv.cu), the rest on the SIMT kernels")
     else:
         w = "ConvAEModel method=conv 1x16x16->1x256x256, latent 4, fc 16, k3 s2 (BASELINE configs[0] geometry), MSE, Adam, fp32"
+    nb = 2 if method == "conv4" else N_BATCHES
     return {"workload": w, "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
-            "l2": f"steps cycle through {N_BATCHES} device-resident batches "
-                  f"({N_BATCHES * batch * (numel(IN_SHAPE) + numel(OUT_SHAPE)) * 4 / 1e6:.0f} MB > 126 MB L2); "
+            "l2": f"steps cycle through {nb} device-resident batches "
+                  f"({nb * batch * (numel(IN_SHAPE) + numel(OUT_SHAPE)) * 4 / 1e6:.0f} MB > 126 MB L2); "
                   "no explicit flush"}
 
 
@@ -346,7 +387,7 @@ def run_b200(args):
 
     # ---- train end to end through the engine's host-fed entry point: every step's inputs come from pinned host
     # memory (double-buffered: the copy of batch i+1 overlaps step i) and every step's loss goes back to the host
-    nh = 8
+    nh = 2 if method == "conv4" else 8
     xh = torch.rand(nh, B, *IN_SHAPE).pin_memory()
     yh = torch.rand(nh, B, *OUT_SHAPE).pin_memory()
     state = {"i": 0}
@@ -427,6 +468,19 @@ def run_b200(args):
                 "apply_step": {"bytes_per_image": b_apply, "achieved": b_apply * AB / (ms_apply / Ka / 1e3) / 1e9,
                                "frac": b_apply * AB / (ms_apply / Ka / 1e3) / 1e9 / hbm_peak}}
 
+    # tensor-core layers (conv4): fp32-equivalent FLOPs of the three GEMMs of every tcgen05 layer against the TF32 peak
+    # (= half the measured bf16 GEMM throughput); 3xTF32 issues three MMAs per product, so the pipe runs at 3x this
+    tc_rows = [(n, t, tc_flops(n, spec, B)) for n, t in table if tc_flops(n, spec, B)]
+    if tc_rows:
+        tf32_peak = 0.5 * float(peaks.get("bf16_tflops_sustained", 1404.4))
+        fl, tt = sum(r[2] for r in tc_rows), sum(r[1] for r in tc_rows)
+        roofline["tensor"] = {"bound": "tensor", "unit": "TFLOP/s", "peak": tf32_peak,
+                              "peak_source": "0.5 x bf16_tflops_sustained (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks else "fallback",
+                              "achieved": fl / (tt / 1e3) / 1e12, "tf32_issue_rate": 3 * fl / (tt / 1e3) / 1e12,
+                              "frac": fl / (tt / 1e3) / 1e12 / tf32_peak, "frac_of_issue_rate": 3 * fl / (tt / 1e3) / 1e12 / tf32_peak,
+                              "launch_groups_us": {n: t * 1e3 for n, t, _ in tc_rows},
+                              "note": "time includes the pack / im2col / col2im passes of each layer, not the GEMM alone"}
+
     # ncu --set full (profiles/r01_head_ncu.md): DRAM bytes of one launch of the fused head kernels at batch 64
     NCU_TRAFFIC = {"bwd.head2": 17163008, "fwd.head2+sigmoid+loss": 17154048}
     if B == 64 and method == "unet" and top[0] in NCU_TRAFFIC:
@@ -459,9 +513,10 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cms, cores, arate = cpu_train_rate(method, B, 40, 3)
+        csteps, cb = (3, min(B, 8)) if method == "conv4" else (40, B)
+        rate, cms, cores, arate = cpu_train_rate(method, cb, csteps, 1 if method == "conv4" else 3)
         cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "apply_images_per_sec": arate,
-               "sample": f"40 optimiser steps at batch {B} (+10 eval batches) of the same workload, oracle port on torch CPU"}
+               "sample": f"{csteps} optimiser steps at batch {cb} (+ eval batches) of the same workload, oracle port on torch CPU"}
 
     if rank == 0:
         line = {

@@ -100,6 +100,13 @@ class CaeTcGemm(C.Structure):
                 ("splits", C.c_int), ("split_stride", C.c_longlong), ("tile_n", C.c_int)]
 
 
+class CaeTcConv(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("Cin", "Cout", "kh", "kw", "stride", "N", "Hin", "Win", "Hout", "Wout")] + \
+               [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_longlong), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
+                ("cols", C.c_void_p), ("cols_len", C.c_longlong), ("dcols_hi", C.c_void_p), ("dcols_lo", C.c_void_p),
+                ("ldn", C.c_longlong)]
+
+
 EPI_PLAIN, EPI_STATS, EPI_MASKSTATS, EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_MASK = 0, 1, 2, 3, 4, 5
 
 # every symbol include/cae_b200.h declares
@@ -160,6 +167,14 @@ EXPORTS = {
     "cae_patch_head_partials_len": (C.c_longlong, [C.POINTER(CaePatchHead)]),
     "cae_tc_gemm": (C.c_int, [C.POINTER(CaeTcGemm), C.c_void_p]),
     "cae_tc_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cae_tc_convt_supported": (C.c_int, [C.c_int] * 6),
+    "cae_tc_convt_wgrad_splits": (C.c_longlong, [C.POINTER(CaeTcConv)]),
+    "cae_tc_convt_fwd": (C.c_int, [C.POINTER(CaeTcConv), C.POINTER(CaeSrc), C.c_void_p, C.POINTER(CaeView),
+                                   C.POINTER(CaeEpilogue), C.c_void_p]),
+    "cae_tc_convt_im2col": (C.c_int, [C.POINTER(CaeTcConv), C.POINTER(CaeSrc), C.c_void_p]),
+    "cae_tc_convt_dgrad": (C.c_int, [C.POINTER(CaeTcConv), C.c_void_p, C.POINTER(CaeView), C.POINTER(CaeEpilogue),
+                                     C.c_void_p]),
+    "cae_tc_convt_wgrad": (C.c_int, [C.POINTER(CaeTcConv), C.c_void_p, C.c_void_p]),
     "cae_randn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
 }
 

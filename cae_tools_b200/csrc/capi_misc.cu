@@ -15,6 +15,7 @@ extern "C" long long cae_struct_size(int which) {
         case 7: return sizeof(CaeFcStack);
         case 8: return sizeof(CaeUnetStem);
         case 9: return sizeof(CaeTcGemm);
+        case 10: return sizeof(CaeTcConv);
         default: return -1;
     }
 }

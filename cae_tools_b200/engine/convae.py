@@ -102,6 +102,7 @@ class ConvAEEngine:
         self._tickets = torch.zeros(4096, dtype=torch.int32, device=self.device)
         self._next_ticket = 0
         self._bn_table = None
+        self._tc, self._tc_shared = {}, {}
 
     # ------------------------------------------------------------------ parameters
     def _build_arena(self):
@@ -199,6 +200,31 @@ class ConvAEEngine:
         b["dzl"] = self._f32(B, lin[2].out_features)
         b["dh1"] = self._f32(B, lin[0].out_features)
 
+    # ------------------------------------------------------------------ tensor-core layers
+    # A transposed conv goes to the tcgen05 path (tc_conv.cu: pack -> 3xTF32 GEMM -> col2im) when it is a genuinely dense
+    # contraction: >= TC_MIN_CIN input channels and >= TC_MIN_FLOPS per launch.  BASELINE configs[3] (4x64x64 ->
+    # 4x1024x1024, batch 128): the layers 1024->512 ... 64->32; nothing in the 16x16 -> 256x256 configs qualifies.
+    TC_MIN_CIN = int(os.environ.get("CAE_TC_MIN_CIN", "64"))
+    TC_MIN_FLOPS = float(os.environ.get("CAE_TC_MIN_FLOPS", "2e9"))
+
+    def _tc_desc(self, j, N):
+        """CaeTcConv descriptor of decoder layer j at batch N, or None when the layer stays on the SIMT kernels"""
+        key = (j, N)
+        if key in self._tc:
+            return self._tc[key]
+        sp = self.dec_specs[j]
+        cin, hin, win = sp.get_input_dimensions()
+        cout, hout, wout = sp.get_output_dimensions()
+        k = sp.get_kernel_size()
+        kh, kw = (k if isinstance(k, (tuple, list)) else (k, k))
+        flops = 2.0 * N * hin * win * cin * cout * kh * kw
+        desc = None
+        if j < len(self.dec_specs) - 1 and cin >= self.TC_MIN_CIN and flops >= self.TC_MIN_FLOPS and \
+                ops.tc_convT_supported(cin, cout, k, sp.get_stride(), 0):
+            desc = ops.make_tc_conv(cin, cout, k, sp.get_stride(), N, hin, win, hout, wout, self.device, self._tc_shared)
+        self._tc[key] = desc
+        return desc
+
     # ------------------------------------------------------------------ schedules
     def _forward_ops(self, b, N, data, train, final):
         """final: 'loss_grad' (train), 'loss' (test epoch), 'yhat' (score: writes sigmoid output into y_d[-1])"""
@@ -231,8 +257,13 @@ class ConvAEEngine:
                                             partials=self._partials(conv.out_channels), ticket=self._ticket(), bn=blk)
                 else:
                     epi = ops.make_epilogue(ops.EPI_PLAIN, bias=conv.bias)
-                sched.append((f"fwd.convT{j}", lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi:
-                              ops.conv_up(src, w, g, o, e)))
+                tc = self._tc_desc(j, N)
+                if tc is not None:
+                    sched.append((f"fwd.convT{j}.tc", lambda tc=tc, src=src, w=conv.weight, o=ops.view4(y, N), e=epi:
+                                  ops.tc_convT_fwd(tc, src, w, o, e)))
+                else:
+                    sched.append((f"fwd.convT{j}", lambda src=src, w=conv.weight, g=g, o=ops.view4(y, N), e=epi:
+                                  ops.conv_up(src, w, g, o, e)))
                 src = ops.make_src(y, k0=s[0], k2=s[1], relu=True, n=N)
             else:
                 if final == "yhat":
@@ -343,7 +374,9 @@ class ConvAEEngine:
                 x_in = ops.make_src(b["y_d"][j - 1], k0=sp_prev[0], k2=sp_prev[1], relu=True, n=N)
             else:
                 x_in = ops.make_src(b["u"], n=N)
-            sched.append((f"bwd.convT{j}.wgrad", self._wgrad_op(x_in, dy, g, self.g(conv.weight))))
+            tc = self._tc_desc(j, N)
+            if tc is None:
+                sched.append((f"bwd.convT{j}.wgrad", self._wgrad_op(x_in, dy, g, self.g(conv.weight))))
             if j > 0:
                 pconv, pbn = self.dec_layers[j - 1]
                 blk, _ = self._bn(("d", j - 1), pbn, self.g(pconv.bias))
@@ -353,6 +386,14 @@ class ConvAEEngine:
             else:
                 epi = ops.make_epilogue(ops.EPI_PLAIN)
                 out = ops.view4(b["du"], N)
+            if tc is not None:
+                # tensor-core layer: one im2col of dL/dy feeds both GEMMs; they fill the machine, so everything stays on
+                # the main stream (the scratch operands are shared between layers)
+                sched.append((f"bwd.convT{j}.tc.im2col", lambda tc=tc, dy=dy: ops.tc_convT_im2col(tc, dy)))
+                sched.append((f"bwd.convT{j}.tc.dgrad", lambda tc=tc, w=conv.weight, o=out, e=epi:
+                              ops.tc_convT_dgrad(tc, w, o, e)))
+                sched.append((f"bwd.convT{j}.tc.wgrad_gemm", lambda tc=tc, gw=self.g(conv.weight): ops.tc_convT_wgrad(tc, gw)))
+                continue
             sched.append((f"bwd.convT{j}.dgrad", lambda dy=dy, w=conv.weight, g=g, o=out, e=epi:
                           ops.conv_down(dy, w, g, o, e)))
         sched += self._fc_backward_ops(b, N, data)

@@ -10,7 +10,7 @@ import ctypes as C
 
 import torch
 
-from .._lib import (CaeTcGemm, CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
+from .._lib import (CaeTcConv, CaeTcGemm, CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
                     CaeUnetStem, CaeView, STEM_MAX, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
                     EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
 
@@ -375,3 +375,62 @@ def tc_gemm(M, N, K, a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, Cout, ldc, sp
     g = CaeTcGemm(int(M), int(N), int(K), _ptr(a_hi), _ptr(a_lo), int(lda), int(bool(a_mn)), _ptr(b_hi), _ptr(b_lo),
                   int(ldb), int(bool(b_mn)), _ptr(Cout), int(ldc), int(splits), int(split_stride), int(tile_n))
     check(lib().cae_tc_gemm(C.byref(g), _stream()), "cae_tc_gemm")
+
+
+# ---- ConvTranspose2d on the tensor cores ---------------------------------------------------------------------------------
+def tc_convT_supported(Cin, Cout, kernel, stride, pad) -> bool:
+    kh, kw = (kernel if isinstance(kernel, (tuple, list)) else (kernel, kernel))
+    return bool(lib().cae_tc_convt_supported(int(Cin), int(Cout), int(kh), int(kw), int(stride), int(pad)))
+
+
+def make_tc_conv(Cin, Cout, kernel, stride, N, Hin, Win, Hout, Wout, device, shared=None) -> CaeTcConv:
+    """descriptor + workspaces of one layer; `shared` (dict) carries the scratch buffers layers can share
+    (weight operand, GEMM output, im2col operand): they are grown to the largest request"""
+    kh, kw = (kernel if isinstance(kernel, (tuple, list)) else (kernel, kernel))
+    T = kh * kw
+    lda = (Cin + 3) // 4 * 4
+    ldn = (T * Cout + 3) // 4 * 4
+    P = N * Hin * Win
+    c = CaeTcConv()
+    c.Cin, c.Cout, c.kh, c.kw, c.stride = int(Cin), int(Cout), int(kh), int(kw), int(stride)
+    c.N, c.Hin, c.Win, c.Hout, c.Wout = int(N), int(Hin), int(Win), int(Hout), int(Wout)
+    c.lda, c.ldn = lda, ldn
+    a = torch.zeros(2, P, lda, dtype=torch.float32, device=device)
+    c.a_hi, c.a_lo = a[0].data_ptr(), a[1].data_ptr()
+    shared = shared if shared is not None else {}
+    splits = int(lib().cae_tc_convt_wgrad_splits(C.byref(c)))
+    need = {"w": 2 * max(T * Cout * lda, Cin * ldn), "cols": max(P * max(ldn, lda), splits * Cin * ldn), "dcols": 2 * P * ldn}
+    for k, n in need.items():
+        if k not in shared or shared[k].numel() < n:
+            shared[k] = torch.zeros(n, dtype=torch.float32, device=device)
+    c._keep = (a, shared)
+    c._shared = shared
+    return c
+
+
+def _tc_bind(c: CaeTcConv):
+    """(re)point the descriptor at the current shared scratch (it may have grown after this layer was described)"""
+    sh = c._shared
+    w, cols, dcols = sh["w"], sh["cols"], sh["dcols"]
+    c.w_hi, c.w_lo = w.data_ptr(), w.data_ptr() + (w.numel() // 2) * 4
+    c.cols, c.cols_len = cols.data_ptr(), cols.numel()
+    c.dcols_hi, c.dcols_lo = dcols.data_ptr(), dcols.data_ptr() + (dcols.numel() // 2) * 4
+    return c
+
+
+def tc_convT_fwd(c: CaeTcConv, src: CaeSrc, weight, out: CaeView, epi: CaeEpilogue):
+    check(lib().cae_tc_convt_fwd(C.byref(_tc_bind(c)), C.byref(src), _ptr(weight), C.byref(out), C.byref(epi), _stream()),
+          "cae_tc_convt_fwd")
+
+
+def tc_convT_im2col(c: CaeTcConv, dy: CaeSrc):
+    check(lib().cae_tc_convt_im2col(C.byref(_tc_bind(c)), C.byref(dy), _stream()), "cae_tc_convt_im2col")
+
+
+def tc_convT_dgrad(c: CaeTcConv, weight, dx: CaeView, epi: CaeEpilogue):
+    check(lib().cae_tc_convt_dgrad(C.byref(_tc_bind(c)), _ptr(weight), C.byref(dx), C.byref(epi), _stream()),
+          "cae_tc_convt_dgrad")
+
+
+def tc_convT_wgrad(c: CaeTcConv, grad):
+    check(lib().cae_tc_convt_wgrad(C.byref(_tc_bind(c)), _ptr(grad), _stream()), "cae_tc_convt_wgrad")

@@ -373,6 +373,37 @@ int cae_tc_gemm(const CaeTcGemm* g, void* stream);
 /* hi = x with the low 13 mantissa bits cleared, lo = x - hi */
 int cae_tc_split(const float* x, float* hi, float* lo, long long n, void* stream);
 
+/* ---- ConvTranspose2d on the tensor cores (tc_conv.cu) --------------------------------------------------------------
+ * Drop-in replacements of cae_conv_up (forward), cae_conv_down-as-input-gradient and cae_conv_wgrad for a transposed
+ * convolution (padding 0) whose channel counts make it a dense contraction (decoder.py:44-48 at config-4 widths):
+ * pack -> tcgen05 GEMM (3xTF32) -> col2im / unpack with the conv family's epilogues.  Tensors outside stay fp32 NCHW.
+ * Workspaces are caller-owned: a_hi/a_lo [N*Hin*Win, lda] (written by the forward call, read again by the weight
+ * gradient), w_hi/w_lo (>= max(kh*kw*Cout*lda, Cin*ldn) floats each), cols (GEMM outputs; cols_len floats:
+ * >= N*Hin*Win*max(ldn, lda) and >= splits*Cin*ldn, splits from cae_tc_convt_wgrad_splits), dcols_hi/dcols_lo
+ * [N*Hin*Win, ldn] (written by cae_tc_convt_im2col, read by _dgrad and _wgrad). */
+typedef struct CaeTcConv {
+    int Cin, Cout, kh, kw, stride;
+    int N, Hin, Win, Hout, Wout;
+    float *a_hi, *a_lo;
+    long long lda;          /* >= Cin, multiple of 4 */
+    float *w_hi, *w_lo;
+    float* cols;
+    long long cols_len;
+    float *dcols_hi, *dcols_lo;
+    long long ldn;          /* >= kh*kw*Cout, multiple of 4 */
+} CaeTcConv;
+int       cae_tc_convt_supported(int Cin, int Cout, int kh, int kw, int stride, int pad);
+long long cae_tc_convt_wgrad_splits(const CaeTcConv* c);
+/* y = ConvTranspose2d(transform(in)) + bias; epilogue PLAIN or STATS (BatchNorm statistics, as cae_conv_up) */
+int cae_tc_convt_fwd(const CaeTcConv* c, const CaeSrc* in, const float* weight, const CaeView* out, const CaeEpilogue* epi,
+                     void* stream);
+/* dcols = im2col(transform(dy)) for the two backward GEMMs of the layer */
+int cae_tc_convt_im2col(const CaeTcConv* c, const CaeSrc* dy, void* stream);
+/* dx = input gradient; epilogue PLAIN, MASK or MASKSTATS (as cae_conv_down used as the input gradient) */
+int cae_tc_convt_dgrad(const CaeTcConv* c, const float* weight, const CaeView* dx, const CaeEpilogue* epi, void* stream);
+/* grad[Cin][Cout][kh][kw] = weight gradient (split-K, slices summed in index order) */
+int cae_tc_convt_wgrad(const CaeTcConv* c, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,14 +68,16 @@ def trainable_keys(sd):
 class OracleModel:
     """weights + Adam state + the train/test/score loops of ConvAEModel (conv_ae_model.py:185-239,303-334)"""
 
-    def __init__(self, enc_sd, dec_sd, spec, lr=1e-3, weight_decay=1e-5, decoupled=False, zero_dead_bias_grads=False):
+    def __init__(self, enc_sd, dec_sd, spec, lr=1e-3, weight_decay=1e-5, decoupled=False, zero_dead_bias_grads=False,
+                 dtype=torch.float32):
         """zero_dead_bias_grads: the bias of a conv that feeds a training-mode BatchNorm has an identically zero
         gradient; autograd returns rounding noise (~1e-9) there which Adam then amplifies into a random walk of
         that (output-irrelevant) bias.  The CUDA path writes the exact zero; set this flag to compare tightly."""
         self.zero_dead_bias_grads = zero_dead_bias_grads
-        self.enc = {k: v.detach().clone().float() if v.is_floating_point() else v.detach().clone()
+        # dtype=torch.float64 gives the adjudicator for "which fp32 result is closer to the exact one" (tests only)
+        self.enc = {k: v.detach().clone().to(dtype) if v.is_floating_point() else v.detach().clone()
                     for k, v in enc_sd.items()}
-        self.dec = {k: v.detach().clone().float() if v.is_floating_point() else v.detach().clone()
+        self.dec = {k: v.detach().clone().to(dtype) if v.is_floating_point() else v.detach().clone()
                     for k, v in dec_sd.items()}
         self.spec = spec  # dict as written to spec.json
         self.params = []

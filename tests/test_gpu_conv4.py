@@ -1,0 +1,105 @@
+"""BASELINE configs[3] (4x64x64 -> 4x1024x1024 ConvAE) and the tensor-core layer path inside the engine.
+
+* the reference-produced fixture layers_multich.npz (48 -> 24 first decoder layer) with the tcgen05 path forced on:
+  gradients / losses held to the same 1e-4 bar as the SIMT path;
+* the config-4 geometry itself (spec = golden config4_64x64_1024x1024, from the live reference's create_model_spec) at a
+  small batch against the oracle port: loss and every gradient after one step, parameters after two."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, load_npz, pre_bn_bias_keys, spec_of, split_sd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def force_tc(monkeypatch):
+    from cae_tools_b200.engine.convae import ConvAEEngine
+    monkeypatch.setattr(ConvAEEngine, "TC_MIN_CIN", 32)
+    monkeypatch.setattr(ConvAEEngine, "TC_MIN_FLOPS", 0.0)
+
+
+def test_tc_layer_vs_reference_fixture(force_tc):
+    from test_gpu_model import _build
+    from cae_tools_b200.engine.convae import ConvAEEngine
+    g = load_npz("layers_multich.npz")
+    spec, enc, dec = _build(g)
+    eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    data = eng.bind(x, y, x.shape[0])
+    losses = []
+    for step in range(3):
+        losses.append(float(eng.train_epoch(data).cpu()[0]))
+        if step == 0:
+            names = [n for n, _ in eng._program("train", data, x.shape[0]).sched]
+            assert "fwd.convT0.tc" in names and "bwd.convT0.tc.wgrad_gemm" in names, names
+            for prefix, mod in (("enc.", enc), ("dec.", dec)):
+                zero_bias = set(pre_bn_bias_keys(list(mod.state_dict().keys()), prefix))
+                for k, p in mod.named_parameters():
+                    ref = g["grad." + prefix + k]
+                    got = p.grad.detach().cpu().numpy()
+                    if k in zero_bias:
+                        assert np.abs(got).max() <= 1e-6, k
+                        continue
+                    scale = max(np.abs(ref).max(), 1e-7)
+                    assert np.abs(got - ref).max() <= 1e-4 * scale + 1e-9, (k, np.abs(got - ref).max(), scale)
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_config4_geometry_vs_oracle(tc, monkeypatch):
+    from cae_tools_b200.engine.convae import ConvAEEngine
+    from cae_tools_b200.models.decoder import Decoder
+    from cae_tools_b200.models.encoder import Encoder
+    from cae_tools_b200.models.model_sizer import ModelSpec, create_model_spec
+    from oracle.torch_port import OracleModel
+    if tc:
+        monkeypatch.setattr(ConvAEEngine, "TC_MIN_FLOPS", 0.0)      # batch 2: below the production FLOP threshold
+    else:
+        monkeypatch.setattr(ConvAEEngine, "TC_MIN_CIN", 1 << 30)
+    spec = create_model_spec(input_size=(64, 64), input_channels=4, output_size=(1024, 1024), output_channels=4)
+    golden = json.load(open(os.path.join(GOLDEN, "specs.json")))["config4_64x64_1024x1024"]
+    assert spec.save() == golden["spec"]
+    torch.manual_seed(3)
+    enc, dec = Encoder(spec.get_input_layers(), 4, 16), Decoder(spec.get_output_layers(), 4, 16)
+    oracle = OracleModel(enc.state_dict(), dec.state_dict(), spec.save(), zero_dead_bias_grads=True)
+    exact = OracleModel(enc.state_dict(), dec.state_dict(), spec.save(), zero_dead_bias_grads=True, dtype=torch.float64)
+    B = 2
+    x, y = torch.rand(B, 4, 64, 64), torch.rand(B, 4, 1024, 1024)
+    eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5)
+    data = eng.bind(x, y, B)
+    names = [n for n, _ in eng._program("train", data, B).sched]
+    assert ("fwd.convT0.tc" in names) == tc and ("fwd.convT4.tc" in names) == tc
+    for step in range(2):
+        got = float(eng.train_epoch(data).cpu()[0])
+        want = float(oracle.train_step(x, y))
+        assert abs(got - want) <= 2e-5 * want, (step, got, want)
+        if step == 0:
+            # Bar: 1e-4 of the max-norm against the fp32 oracle.  The gradients at the far end of this 17-layer chain
+            # (encoder convs; batch-2 BatchNorm amplifies rounding) differ between two fp32 evaluations by more than
+            # that: there the CUDA result must instead be as close to the float64 evaluation of the same step as the
+            # fp32 oracle itself is (within 2x).
+            exact.train_step(x.double(), y.double())
+            worst = {}
+            for sd, sd64, mod in ((oracle.enc, exact.enc, enc), (oracle.dec, exact.dec, dec)):
+                for k, p in mod.named_parameters():
+                    ref = sd[k].grad.numpy()
+                    ref64 = sd64[k].grad.numpy()
+                    gotg = p.grad.detach().cpu().numpy()
+                    scale = max(np.abs(ref).max(), 1e-7)
+                    err = np.abs(gotg - ref).max()
+                    if err > 1e-4 * scale + 1e-9:
+                        e_gpu, e_cpu = np.abs(gotg - ref64).max(), np.abs(ref - ref64).max()
+                        assert k.startswith("encoder_") and e_gpu <= 2.0 * e_cpu + 1e-9, (k, err, scale, e_gpu, e_cpu)
+                        worst[k] = (float(err / scale), float(e_gpu / scale), float(e_cpu / scale))
+            print("beyond 1e-4 vs fp32 oracle, adjudicated by float64 (vs oracle, gpu vs f64, oracle vs f64):", worst)
+    for sd, mod in ((oracle.enc, enc), (oracle.dec, dec)):
+        for k, v in mod.state_dict().items():
+            ref = sd[k].detach().numpy()
+            gv = v.detach().cpu().numpy()
+            if ref.dtype.kind == "f":
+                assert np.abs(gv - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-3), k

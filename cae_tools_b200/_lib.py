@@ -100,6 +100,28 @@ class CaeTcGemm(C.Structure):
                 ("splits", C.c_int), ("split_stride", C.c_longlong), ("tile_n", C.c_int)]
 
 
+class CaeStemTrainConv(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("Cin", "Hin", "Win", "Cout", "Hout", "Wout", "k", "stride", "pad")] + \
+               [(k, C.c_void_p) for k in ("w", "b", "dw", "db")] + [("bn", CaeBN)]
+
+
+class CaeStemTrainFc(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("inp", "out", "has_bn")] + [(k, C.c_void_p) for k in ("w", "b", "dw", "db")] + \
+               [("bn", CaeBN)]
+
+
+class CaeStemTrainUp(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("Cin", "Hin", "Win", "Cout", "Hout", "Wout", "k", "stride", "pad", "Cr", "skip")] + \
+               [(k, C.c_void_p) for k in ("w", "b", "W1", "W2", "dw", "db", "dW1", "dW2")] + [("bn", CaeBN)]
+
+
+class CaeStemTrain(C.Structure):
+    _fields_ = [("n_conv", C.c_int), ("n_fc", C.c_int), ("n_up", C.c_int), ("N", C.c_int),
+                ("conv", CaeStemTrainConv * STEM_MAX), ("fc", CaeStemTrainFc * STEM_MAX), ("up", CaeStemTrainUp * STEM_MAX),
+                ("params", C.c_void_p), ("params_len", C.c_longlong), ("tape", C.c_void_p), ("hin", C.c_void_p), ("dhin", C.c_void_p), ("dropout_p", C.c_float),
+                ("seed", C.c_ulonglong), ("step_count", C.c_void_p), ("bnpart", C.c_void_p), ("wpart", C.c_void_p)]
+
+
 class CaeTcConv(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("Cin", "Cout", "kh", "kw", "stride", "N", "Hin", "Win", "Hout", "Wout")] + \
                [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_longlong), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
@@ -175,6 +197,12 @@ EXPORTS = {
     "cae_tc_convt_dgrad": (C.c_int, [C.POINTER(CaeTcConv), C.c_void_p, C.POINTER(CaeView), C.POINTER(CaeEpilogue),
                                      C.c_void_p]),
     "cae_tc_convt_wgrad": (C.c_int, [C.POINTER(CaeTcConv), C.c_void_p, C.c_void_p]),
+    "cae_unet_stem_train_supported": (C.c_int, [C.POINTER(CaeStemTrain)]),
+    "cae_unet_stem_train_tape_elems": (C.c_longlong, [C.POINTER(CaeStemTrain)]),
+    "cae_unet_stem_train_workspace": (C.c_longlong, [C.POINTER(CaeStemTrain), C.c_int]),
+    "cae_unet_stem_train_fwd": (C.c_int, [C.POINTER(CaeStemTrain), C.POINTER(CaeSrc), C.c_void_p]),
+    "cae_unet_stem_train_profile": (C.c_int, [C.c_void_p]),
+    "cae_unet_stem_train_bwd": (C.c_int, [C.POINTER(CaeStemTrain), C.POINTER(CaeSrc), C.c_void_p]),
     "cae_randn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
 }
 

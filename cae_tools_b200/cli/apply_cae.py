@@ -23,7 +23,16 @@ def main(argv=None):
     parser.add_argument("--prediction-variable", help="name of the prediction variable to create in output data",
                         default="model_output")
     parser.add_argument("--mask-variable", type=str, help="name of the mask variable", default=None)
+    # not in the reference: the cases are sharded over N GPUs of this node (one process per GPU, no collective on the
+    # compute path); rank 0 writes the output file
+    parser.add_argument("--gpus", type=int, default=1, help="shard the cases over N GPUs (ignored under torchrun)")
     args = parser.parse_args(argv)
+    import sys
+    from ..engine import dp as _dp
+    if args.gpus > 1 and "RANK" not in os.environ:
+        _dp.respawn_under_torchrun(args.gpus, sys.argv[1:] if argv is None else argv, "cae_tools_b200.cli.apply_cae")
+    ctx = _dp.init_from_env()
+    lead = ctx is None or ctx.rank == 0
 
     with open(os.path.join(args.model_folder, "parameters.json")) as f:
         parameters = json.loads(f.read())
@@ -43,9 +52,15 @@ def main(argv=None):
     score_ds = xr.open_mfdataset(args.data_paths, concat_dim="box", combine="nested")
     case_dimension = score_ds[names[0]].dims[0]
     expand_scalar_inputs(score_ds, names, case_dimension)
-    print("Applying model for %d cases" % score_ds[names[0]].shape[0])
+    if lead:
+        print("Applying model for %d cases" % score_ds[names[0]].shape[0])
     mt.apply(score_ds, names, args.prediction_variable, mask_variable_name=args.mask_variable)
-    score_ds.to_netcdf(args.output_path)
+    if lead:
+        score_ds.to_netcdf(args.output_path)
+    if ctx is not None:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -62,6 +62,11 @@ def build_parser():
     p.add_argument("--chunk-size", type=int, help="chunk size for xarray", default=1000)
     p.add_argument("--include-coasts", help="include coastal areas", default=False)
     p.add_argument("--mask-variable", type=str, help="name of the mask variable", default=None)
+    # not in the reference (it has no multi-GPU path): batch-sharded data parallelism, one process per GPU
+    p.add_argument("--gpus", type=int, default=1, help="data-parallel training on N GPUs of this node (one process per "
+                   "GPU, NCCL gradient all-reduce); under torchrun the environment decides and this flag is ignored")
+    p.add_argument("--sync-bn", action="store_true", help="with --gpus > 1: BatchNorm statistics over the GLOBAL batch "
+                   "(all-reduced), so the loss curve matches a single-GPU run of the same global batch")
     return p
 
 
@@ -99,12 +104,21 @@ def expand_scalar_inputs(ds, names, case_dimension):
 
 
 def main(argv=None):
+    import sys
     args = build_parser().parse_args(argv)
+    from ..engine import dp as _dp
+    if args.gpus > 1 and "RANK" not in os.environ:
+        _dp.respawn_under_torchrun(args.gpus, sys.argv[1:] if argv is None else argv, "cae_tools_b200.cli.train_cae")
+    ctx = _dp.init_from_env()
+    lead = ctx is None or ctx.rank == 0
     train_ds = xr.open_mfdataset(args.train_inputs, concat_dim="box", combine="nested")
     test_ds = xr.open_mfdataset(args.test_inputs, concat_dim="box", combine="nested")
     case_dimension = train_ds[args.output_variable].dims[0]
-    print("Training cases: %d, Test cases: %d" % (train_ds[args.output_variable].shape[0],
-                                                  test_ds[args.output_variable].shape[0]))
+    if lead:
+        print("Training cases: %d, Test cases: %d" % (train_ds[args.output_variable].shape[0],
+                                                      test_ds[args.output_variable].shape[0]))
+        if ctx is not None:
+            print(f"Data parallel over {ctx.world} GPUs (batch {args.batch_size} split {args.batch_size // ctx.world} per GPU)")
     expand_scalar_inputs(train_ds, args.input_variables, case_dimension)
     expand_scalar_inputs(test_ds, args.input_variables, case_dimension)
 
@@ -142,12 +156,22 @@ def main(argv=None):
                 spec.load(json.loads(f.read()))
                 mt.spec = spec
 
+    if ctx is not None and not lead:
+        mt.verbose = False
+    if args.sync_bn:
+        mt.sync_bn = True
     start_time = time.time()
-    print("Ready for training process")
+    if lead:
+        print("Ready for training process")
     mt.train(args.input_variables, args.output_variable, training_ds=train_ds, testing_ds=test_ds,
              model_path=args.model_folder, training_paths=";".join(args.train_inputs),
              testing_paths=";".join(args.test_inputs), mask_variable_name=args.mask_variable)
-    print(f"Time taken to train: {time.time() - start_time:.2f} seconds")
+    if lead:
+        print(f"Time taken to train: {time.time() - start_time:.2f} seconds")
+    if ctx is not None:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

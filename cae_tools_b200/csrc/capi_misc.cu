@@ -16,6 +16,7 @@ extern "C" long long cae_struct_size(int which) {
         case 8: return sizeof(CaeUnetStem);
         case 9: return sizeof(CaeTcGemm);
         case 10: return sizeof(CaeTcConv);
+        case 11: return sizeof(CaeStemTrain);
         default: return -1;
     }
 }

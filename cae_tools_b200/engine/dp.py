@@ -7,7 +7,10 @@ decoder + fc gradients are SUM-all-reduced asynchronously while the encoder back
 right after it; the optimiser waits for both (engine/convae.py:_BucketedProgram).  Each rank computes on its contiguous share of
 every global batch; the loss epilogue divides by the GLOBAL element count (count_scale =
 n_local/n_global), so the summed gradients - and the summed per-batch losses - are exactly those of
-the global batch.  BatchNorm uses the statistics of the local share ("local BN").  `apply` shards the
+the global batch for the plain MSE.  The UNET's masked MSE divides by the mask count: with count_scale = 1/world the
+sum over ranks equals the global masked MSE only when every rank's share of a batch has the same number of valid
+pixels; with land/sea masks it is the mean of the per-share masked MSEs instead (a different weighting of the same
+pixels, exact again for mask-free data).  BatchNorm uses the statistics of the local share ("local BN").  `apply` shards the
 samples over ranks with no collective at all.
 """
 
@@ -76,3 +79,41 @@ class DPContext:
     def broadcast_(self, tensors, src=0):
         for t in tensors:
             dist.broadcast(t, src=src, group=self.group)
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from the torchrun environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR /
+    MASTER_PORT): one process per GPU, NCCL when CUDA is present (gloo otherwise: CPU tests).  No-op outside torchrun or
+    when a group already exists.  Returns the DPContext (None for a single process)."""
+    import os
+    if not dist.is_available():
+        return None
+    if not dist.is_initialized():
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world <= 1 or "RANK" not in os.environ:
+            return None
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return DPContext.from_env()
+
+
+def respawn_under_torchrun(gpus, argv, module):
+    """`--gpus N` given to a CLI outside torchrun: re-execute `python -m torch.distributed.run --nproc-per-node N -m
+    <module> <argv>` on this node (the way bench.py launches itself); never returns."""
+    import os
+    import socket
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={gpus}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), "-m", module] + list(argv)
+    os.execv(sys.executable, cmd)

@@ -10,7 +10,7 @@ import ctypes as C
 
 import torch
 
-from .._lib import (CaeTcConv, CaeTcGemm, CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
+from .._lib import (CaeStemTrain, CaeStemTrainConv, CaeStemTrainFc, CaeStemTrainUp, CaeTcConv, CaeTcGemm, CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
                     CaeUnetStem, CaeView, STEM_MAX, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
                     EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
 
@@ -434,3 +434,90 @@ def tc_convT_dgrad(c: CaeTcConv, weight, dx: CaeView, epi: CaeEpilogue):
 
 def tc_convT_wgrad(c: CaeTcConv, grad):
     check(lib().cae_tc_convt_wgrad(C.byref(_tc_bind(c)), _ptr(grad), _stream()), "cae_tc_convt_wgrad")
+
+
+# ---- training-mode UNET stem (two cooperative launches) ---------------------------------------------------------------------
+def make_stem_train(N, convs, fcs, ups, dropout_p, seed, step_count, device, params) -> CaeStemTrain:
+    """convs: [(Cin,Hin,Win,Cout,Hout,Wout,k,stride,pad, w,b,dw,db, CaeBN)], fcs: [(in,out,has_bn, w,b,dw,db, CaeBN|None)],
+    ups: [(Cin,Hin,Win,Cout,Hout,Wout,k,stride,pad,Cr,skip, w,b,W1,W2,dw,db,dW1,dW2, CaeBN)].  Returns None when the geometry
+    or the batch does not fit the fused kernels; otherwise the descriptor with its tape / hin / dhin / workspaces allocated
+    (attributes .t_tape, .t_hin, .t_dhin)."""
+    if max(len(convs), len(fcs), len(ups)) > STEM_MAX:
+        return None
+    st = CaeStemTrain()
+    st.n_conv, st.n_fc, st.n_up, st.N = len(convs), len(fcs), len(ups), int(N)
+    keep = []
+    for i, c in enumerate(convs):
+        e = CaeStemTrainConv(*[int(v) for v in c[:9]], *[_ptr(t) for t in c[9:13]])
+        e.bn = c[13]
+        st.conv[i] = e
+        keep += list(c[9:])
+    for i, c in enumerate(fcs):
+        e = CaeStemTrainFc(*[int(v) for v in c[:3]], *[_ptr(t) for t in c[3:7]])
+        if c[7] is not None:
+            e.bn = c[7]
+        st.fc[i] = e
+        keep += list(c[3:])
+    for i, c in enumerate(ups):
+        e = CaeStemTrainUp(*[int(v) for v in c[:11]], *[_ptr(t) for t in c[11:19]])
+        e.bn = c[19]
+        st.up[i] = e
+        keep += list(c[11:])
+    st.params, st.params_len = params.data_ptr(), int(params.numel())     # contiguous block holding every stem parameter
+    st.dropout_p = float(dropout_p)
+    st.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    st.step_count = _ptr(step_count)
+    # the support check wants non-null workspaces: size them first with placeholders
+    c_last, h_last, w_last = ups[-1][3], ups[-1][4], ups[-1][5]
+    hin = torch.zeros(N, 2 * c_last, h_last, w_last, dtype=torch.float32, device=device)
+    dhin = torch.zeros_like(hin)
+    st.hin, st.dhin = hin.data_ptr(), dhin.data_ptr()
+    if not lib().cae_unet_stem_train_supported(C.byref(st)):
+        return None
+    tape = torch.zeros(N, int(lib().cae_unet_stem_train_tape_elems(C.byref(st))), dtype=torch.float32, device=device)
+    bnpart = torch.zeros(int(lib().cae_unet_stem_train_workspace(C.byref(st), 0)), dtype=torch.float64, device=device)
+    wpart = torch.zeros(int(lib().cae_unet_stem_train_workspace(C.byref(st), 1)), dtype=torch.float32, device=device)
+    st.tape, st.bnpart, st.wpart = tape.data_ptr(), bnpart.data_ptr(), wpart.data_ptr()
+    st.t_tape, st.t_hin, st.t_dhin = tape, hin, dhin
+    # per-sample tape layout (mirror of st_plan in unet_stem_train.cu; every slot rounded up to 4 floats): for inspection
+    off, lay = 0, {}
+
+    def take(name, shape):
+        nonlocal off
+        n = 1
+        for d in shape:
+            n *= int(d)
+        lay[name] = (off, tuple(int(d) for d in shape))
+        off += (n + 3) // 4 * 4
+    take("x", convs[0][0:3])
+    for i, c in enumerate(convs):
+        take(f"y_e{i}", c[3:6])
+    for i, c in enumerate(fcs):
+        take(f"t{i}", (c[1],))
+    for j, c in enumerate(ups):
+        take(f"y_d{j}", c[3:6])
+        take(f"cat{j}", (2 * c[3], c[4], c[5]))
+        take(f"att{j}", (c[3],))
+        take(f"hid{j}", (2 * c[9],))
+        take(f"pool{j}", (3, c[3]))
+    assert off == tape.shape[1], (off, tape.shape)
+    st.layout = lay
+    st._keep = (keep, step_count, tape, hin, dhin, bnpart, wpart, params)
+    return st
+
+
+def stem_train_fwd(st: CaeStemTrain, x: CaeSrc):
+    check(lib().cae_unet_stem_train_fwd(C.byref(st), C.byref(x), _stream()), "cae_unet_stem_train_fwd")
+
+
+def stem_train_bwd(st: CaeStemTrain, x: CaeSrc):
+    check(lib().cae_unet_stem_train_bwd(C.byref(st), C.byref(x), _stream()), "cae_unet_stem_train_bwd")
+
+
+def stem_tape_view(st: CaeStemTrain, name):
+    """tensor view [N, ...] of one tape slot (raw layer output) after a fused forward launch"""
+    off, shape = st.layout[name]
+    n = 1
+    for d in shape:
+        n *= d
+    return st.t_tape[:, off:off + n].reshape(st.t_tape.shape[0], *shape)

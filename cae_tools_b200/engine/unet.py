@@ -29,11 +29,15 @@ from .convae import ConvAEEngine, DataBinding
 
 class UNetEngine(ConvAEEngine):
 
-    def __init__(self, encoder, decoder, lambda_pearson=1.0, dropout_rate=0.0, **kw):
+    def __init__(self, encoder, decoder, lambda_pearson=1.0, dropout_rate=0.0, seed=None, **kw):
         kw.setdefault("decoupled", True)         # torch.optim.AdamW (unet.py:457)
         super().__init__(encoder, decoder, **kw)
         self.lambda_pearson = float(lambda_pearson)
         self.dropout_rate = float(dropout_rate)
+        # dropout masks are a counter-based hash of (seed, optimiser step, site, sample, element): nothing is stored and a
+        # replayed CUDA graph draws fresh masks every step.  Data-parallel ranks pass different seeds.
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self._stem_train = {}
         self.dec3 = self.decoder.conv_layers()   # [(convT, bn2c|None, attention|None)]
         if len(self.dec3) != len(self.enc_layers):
             raise ValueError("UNET needs as many decoder as encoder layers (skip connections pair them up)")
@@ -213,13 +217,64 @@ class UNetEngine(ConvAEEngine):
             self._stem = stem
         return self._stem
 
+    # training: the whole stem in one forward and one backward cooperative launch (unet_stem_train.cu) whenever the
+    # geometry fits (the last layer must be the fused patch head; <= 4 samples per CTA on 148 CTAs: batch <= 592)
+    use_fused_train_stem = True
+
+    def _train_stem(self, N):
+        """CaeStemTrain descriptor for batch N (cached), or None when the stem stays on the per-layer kernels"""
+        if N in self._stem_train:
+            return self._stem_train[N]
+        st = None
+        ks = lambda sp: sp.get_kernel_size()
+        tuple_k = any(isinstance(ks(sp), (tuple, list)) for sp in list(self.enc_specs) + list(self.dec_specs))
+        sp_last = self.dec_specs[-1]
+        cin_l, hin_l, win_l = sp_last.get_input_dimensions()
+        if self.use_fused_train_stem and self.use_patch_head and not tuple_k and len(self.dec3) >= 2 and \
+                ops.patch_head_supported(ks(sp_last), sp_last.get_stride(), sp_last.get_output_padding(), cin_l, win_l):
+            G = self.g
+            convs, fcs, ups = [], [], []
+            for i, ((conv, bn), sp) in enumerate(zip(self.enc_layers, self.enc_specs)):
+                blk, _ = self._bn(("e", i), bn, G(conv.bias))
+                convs.append((*sp.get_input_dimensions(), *sp.get_output_dimensions(), ks(sp), sp.get_stride(),
+                              sp.get_output_padding(), conv.weight, conv.bias, G(conv.weight), G(conv.bias), blk))
+            lin, dlin = self.encoder.encoder_lin, self.decoder.decoder_lin
+            blk1, _ = self._bn(("l", 0), lin[1])
+            blk3, _ = self._bn(("l", 1), dlin[1])
+            for L, blk in ((lin[0], blk1), (lin[4], None), (dlin[0], blk3), (dlin[4], None)):
+                fcs.append((L.in_features, L.out_features, int(blk is not None), L.weight, L.bias, G(L.weight), G(L.bias), blk))
+            ne = len(self.enc_layers)
+            for j, ((conv, bn, att), sp) in enumerate(zip(self.dec3[:-1], self.dec_specs[:-1])):
+                blk, _ = self._bn(("d", j), bn)
+                ups.append((*sp.get_input_dimensions(), *sp.get_output_dimensions(), ks(sp), sp.get_stride(),
+                            sp.get_output_padding(), att.fc1.out_channels, ne - 2 - j, conv.weight, conv.bias, att.fc1.weight,
+                            att.fc2.weight, G(conv.weight), G(conv.bias), G(att.fc1.weight), G(att.fc2.weight), blk))
+            # every stem parameter lives in the flat arena in front of the head's weight (parameter order: encoder,
+            # decoder_lin, attention layers, decoder_conv with the head last)
+            head_w = self.dec3[-1][0].weight
+            end = (head_w.data_ptr() - self.arena.data_ptr()) // 4
+            st = ops.make_stem_train(N, convs, fcs, ups, self.dropout_rate, self.seed, self.step_count, self.device,
+                                     self.arena[:end])
+        self._stem_train[N] = st
+        return st
+
     # ------------------------------------------------------------------ forward
     def _forward_ops(self, b, N, data, train, final):
-        if train and self.dropout_rate > 0:
-            raise NotImplementedError("UNET training with dropout_rate > 0 is not implemented on the CUDA path "
-                                      "(use dropout_rate=0; inference is unaffected)")
         S = []
         src = self._x_src(data, N)
+        self._stem_active = None
+        if train:
+            st = self._train_stem(N)
+            if st is not None:
+                nd = len(self.dec3)
+                S.append(("fwd.stem_train", lambda st=st, x=src: ops.stem_train_fwd(st, x)))
+                self._last_layer_ops(S, b, N, data, ops.make_src(st.t_hin, n=N), self.dec3[-1][0], self.dec_specs[-1], nd - 1, final)
+                assert self._head is not None
+                self._stem_active = (st, src)
+                return S
+            if self.dropout_rate > 0:
+                raise NotImplementedError("UNET training with dropout_rate > 0 needs the fused training stem (unet_stem_train.cu), "
+                                          "which does not cover this geometry / batch size; use dropout_rate=0")
         if not train and self.use_fused_stem and N <= self.fused_stem_max_batch:
             stem = self._eval_stem()
             if stem is not None:
@@ -317,6 +372,18 @@ class UNetEngine(ConvAEEngine):
         co = self.dec_specs[-1].get_output_dimensions()[0]
         last_conv = self.dec3[-1][0]
         head = getattr(self, "_head", None)
+        if getattr(self, "_stem_active", None) is not None:
+            # fused stem: the head hands over the raw gradient of its (activated) input; masks, BatchNorm backward and
+            # every other gradient happen inside the one backward launch
+            st, xsrc = self._stem_active
+            part = torch.zeros(ops.patch_head_partials_len(head), dtype=torch.float32, device=self.device)
+            self._keep.append(part)
+            S.append((f"bwd.head{nd - 1}", lambda h=head, o=ops.view4(st.t_dhin, N), e=ops.make_epilogue(ops.EPI_PLAIN), part=part:
+                      ops.patch_head_bwd(h, o, e, part)))
+            S.append((f"bwd.head{nd - 1}.wgrad", lambda h=head, cv=last_conv, part=part:
+                      ops.patch_head_wgrad_reduce(h, G(cv.weight), G(cv.bias), part)))
+            S.append(("bwd.stem_train", lambda st=st, x=xsrc: ops.stem_train_bwd(st, x)))
+            return S
         if head is None:
             S.append(("bwd.convT_last.db", lambda: ops.sum_over_n(b["psL"], N, co, G(last_conv.bias))))
         for j in range(nd - 1, -1, -1):

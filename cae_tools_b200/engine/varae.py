@@ -65,7 +65,8 @@ class VarAEEngine(ConvAEEngine):
         kl_scale = self.lambda_kl * self.count_scale
         if train and fixed is None:
             sched.append(("fwd.randn", lambda: ops.randn(b["eps"], N * lat, self.seed, self.step_count)))
-            sched.append(("fwd.reparam+kl", lambda: ops.vae_reparam_fwd(b["mu"], b["lv"], b["eps"], 0, None, b["z"], N,
+            # (the cursor selects the KL slot of this batch; the noise buffer is per step: stride 0)
+            sched.append(("fwd.reparam+kl", lambda: ops.vae_reparam_fwd(b["mu"], b["lv"], b["eps"], 0, data.cursor, b["z"], N,
                                                                         lat, True, kl_scale, data.kl)))
         elif train:
             sched.append(("fwd.reparam+kl", lambda: ops.vae_reparam_fwd(b["mu"], b["lv"], fixed,

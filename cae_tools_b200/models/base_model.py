@@ -72,10 +72,46 @@ class BaseModel:
         ds = DSDataset(score_ds, input_variables, input_variables[0], normalise_in=self.normalise_input,
                        mask_variable_name=mask_variable_name)
         ds.set_normalisation_parameters(self.normalisation_parameters)
-        scores = self.predict_array(ds.input_array())
+        inputs = ds.input_array()
+        n = inputs.shape[0]
+        # one process per GPU (torch.distributed initialised): every rank predicts its contiguous share of the cases -
+        # the compute has no collective; the shares are then exchanged so that every rank's data set carries the whole
+        # variable, as in the single-process call.  apply_shard() below skips the exchange (sweeps too large to gather).
+        from ..engine.dp import DPContext, shard_bounds
+        dp = DPContext.from_env()
+        if dp is None:
+            scores = self.predict_array(inputs)
+        else:
+            lo, hi, mine = self.predict_shard(inputs, dp)
+            scores = np.empty((n,) + mine.shape[1:], dtype=np.float32)
+            scores[lo:hi] = mine
+            import torch.distributed as dist
+            for r in range(dp.world):
+                rlo, rhi = shard_bounds(n, r, dp.world)
+                if rhi > rlo:
+                    t = torch.from_numpy(scores[rlo:rhi])
+                    if dist.get_backend(dp.group) == "nccl":
+                        t = t.cuda()
+                    dist.broadcast(t, src=r, group=dp.group)
+                    if r != dp.rank:
+                        scores[rlo:rhi] = t.cpu().numpy()
         out = ds.denormalise_output(scores.astype(np.float64))
         score_ds[prediction_variable] = _xr.DataArray(out, dims=(n_dimension, channel_dimension, y_dimension,
                                                                   x_dimension))
+
+    def apply_shard(self, score_ds, input_variables, mask_variable_name=None):
+        """Sharded apply() for sweeps that must not be gathered (BASELINE configs[4]: N = 1 M cases over 8 GPUs): returns
+        (lo, hi, de-normalised float64 estimates of cases [lo, hi)) of THIS rank; no collective, no full-N allocation
+        (the reference allocates all N outputs as float64 on the host, base_model.py:123)."""
+        from ..engine.dp import DPContext, shard_bounds
+        dp = DPContext.from_env()
+        n = score_ds[input_variables[0]].shape[0]
+        lo, hi = (0, n) if dp is None else shard_bounds(n, dp.rank, dp.world)
+        ds = DSDataset(score_ds, input_variables, input_variables[0], normalise_in=self.normalise_input,
+                       mask_variable_name=mask_variable_name)
+        ds.set_normalisation_parameters(self.normalisation_parameters)
+        scores = self.predict_array(ds.input_array(list(range(lo, hi))))
+        return lo, hi, ds.denormalise_output(scores.astype(np.float64))
 
     def evaluate(self, dataset, device=None):
         """mse / rmse / mae / mean Pearson of de-normalised predictions against the data set's output"""

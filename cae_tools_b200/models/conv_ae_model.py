@@ -78,7 +78,7 @@ class ConvAEModel(BaseModel):
             from ..utils.model_database import ModelDatabase
             self.db = ModelDatabase(database_path)
         self.engine = None
-        self.apply_batch_size = 1024   # eval-mode outputs do not depend on the batch split
+        self.apply_batch_size = 4096   # eval-mode outputs do not depend on the batch split (kernels tuned at 4096)
         self.verbose = True
 
     # ------------------------------------------------------------------ parameters / persistence
@@ -179,18 +179,58 @@ class ConvAEModel(BaseModel):
         return self.engine
 
     # ------------------------------------------------------------------ inference
-    def predict_array(self, inputs):
+    def predict_array(self, inputs, out=None):
+        """eval-mode forward of `inputs` [n, C, y, x] (normalised fp32) -> [n, C', y', x'].  Predictions stream back
+        through two pinned staging buffers on a copy stream: the device -> host copy of batch i overlaps the kernels of
+        batch i + 1 and the host-side scatter of batch i - 1 (reference: one blocking .cpu() per batch,
+        conv_ae_model.py:238).  `out` may be a preallocated array (any float dtype) that receives the result."""
         eng = self._ensure_engine()
         n = inputs.shape[0]
         bs = max(1, min(self.apply_batch_size, n))
         data = eng.bind(torch.from_numpy(np.ascontiguousarray(inputs, dtype=np.float32)), None, bs)
-        out = np.empty((n,) + tuple(self.output_shape), dtype=np.float32)
+        if out is None:
+            out = np.empty((n,) + tuple(self.output_shape), dtype=np.float32)
+        dev = eng.device
+        copy = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        stage = [torch.empty((bs,) + tuple(self.output_shape), dtype=torch.float32).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        taken = [torch.cuda.Event(), torch.cuda.Event()]      # the copy of slot k has read the engine's output buffer
+        pending = [None, None]                                # (first row, rows) waiting in the staging slot
+
+        def flush(k):
+            if pending[k] is not None:
+                done[k].synchronize()
+                lo, cnt = pending[k]
+                out[lo:lo + cnt] = stage[k][:cnt].numpy()
+                pending[k] = None
 
         def sink(i, yhat):
-            out[i * bs:i * bs + yhat.shape[0]] = yhat.cpu().numpy()
+            k = i & 1
+            flush(k)                                          # host scatter of batch i - 2 (its copy finished long ago)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(copy):
+                copy.wait_event(ready)
+                stage[k][:yhat.shape[0]].copy_(yhat, non_blocking=True)
+                done[k].record(copy)
+                taken[k].record(copy)
+            main.wait_event(taken[k])                         # the next batch overwrites the engine's output buffer
+            pending[k] = (i * bs, yhat.shape[0])
 
         eng.score_batches(data, sink)
+        flush(0)
+        flush(1)
         return out
+
+    def predict_shard(self, inputs, dp=None):
+        """apply() sharding (N split into contiguous ranges over the ranks, no collective): this rank's
+        (lo, hi, predictions[lo:hi]).  `dp` defaults to the initialised torch.distributed group (None / world 1: all)."""
+        from ..engine.dp import DPContext, shard_bounds
+        dp = dp if dp is not None else DPContext.from_env()
+        n = inputs.shape[0]
+        lo, hi = (0, n) if dp is None else shard_bounds(n, dp.rank, dp.world)
+        return lo, hi, self.predict_array(inputs[lo:hi])
 
     def score(self, batches, save_arr):
         """reference signature (conv_ae_model.py:223-239): `batches` is a list of input tensors, predictions are
@@ -271,12 +311,17 @@ class ConvAEModel(BaseModel):
         self.encoder.eval()
         self.decoder.eval()
 
-        if self.db:
+        # data parallel: weights are identical on every rank; rank 0 alone writes the model folder / tracking DB and runs
+        # the post-training evaluation (no duplicate sqlite rows, no concurrent writers)
+        lead = dp is None or dp.rank == 0
+        if self.db and lead:
             self.db.add_training_result(self.get_model_id(), self.DB_TYPE, output_variable, input_variables,
                                         self.summary(), model_path, training_paths, train_loss, testing_paths,
                                         test_loss, self.get_parameters(), self.spec.save())
-        if model_path and (dp is None or dp.rank == 0):
+        if model_path and lead:
             self.save(model_path)
+        if not lead:
+            return
 
         metrics = {"test": self.evaluate(test_ds, device), "train": self.evaluate(train_ds, device)}
         if self.verbose:

@@ -69,11 +69,13 @@ class UNET(ConvAEModel):
     def _make_engine(self, device, dp=None):
         from ..engine.unet import UNetEngine
         kw = dict(lr=self.lr, weight_decay=self.weight_decay, device=device)
+        seed = torch.initial_seed()
         if dp is not None:
             kw.update(grad_hook=dp.allreduce_grads, grad_hook_async=dp.allreduce_grads_async,
                       count_scale=1.0 / dp.world)
+            seed ^= (dp.rank + 1) * 0x9E3779B97F4A7C15           # independent dropout masks on every rank's shard
         return UNetEngine(self.encoder, self.decoder, lambda_pearson=self.lambda_pearson,
-                          dropout_rate=self.dropout_rate, **kw)
+                          dropout_rate=self.dropout_rate, seed=seed & 0xFFFFFFFFFFFFFFFF, **kw)
 
     def train(self, input_variables, output_variable, training_ds, testing_ds, model_path="", training_paths="",
               testing_paths="", mask_variable_name=None):
@@ -145,12 +147,15 @@ class UNET(ConvAEModel):
             print("elapsed:" + str(elapsed))
         self.encoder.eval()
         self.decoder.eval()
-        if self.db:
+        lead = dp is None or dp.rank == 0      # rank 0 alone writes the folder / tracking DB and evaluates
+        if self.db and lead:
             self.db.add_training_result(self.get_model_id(), self.DB_TYPE, output_variable, input_variables,
                                         self.summary(), model_path, training_paths, train_loss, testing_paths,
                                         test_loss, self.get_parameters(), self.spec.save())
-        if model_path and (dp is None or dp.rank == 0):
+        if model_path and lead:
             self.save(model_path)
+        if not lead:
+            return
         metrics = {"test": self.evaluate(test_ds, device), "train": self.evaluate(train_ds, device)}
         if self.verbose:
             self.dump_metrics("Test Metrics", metrics["test"])

@@ -45,7 +45,11 @@ class VarAEModel(ConvAEModel):
     def _make_engine(self, device, dp=None):
         from ..engine.varae import VarAEEngine
         kw = dict(lr=self.lr, weight_decay=self.weight_decay, device=device)
+        seed = self.seed
         if dp is not None:
-            kw.update(grad_hook=dp.allreduce_grads, count_scale=1.0 / dp.world)
+            kw.update(grad_hook=dp.allreduce_grads, count_scale=1.0 / dp.world,
+                      grad_hook_async=dp.allreduce_grads_async)
+            # every rank holds a different shard: its reparameterisation noise must be independent too
+            seed = (seed ^ ((dp.rank + 1) * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
         return VarAEEngine(self.encoder, self.decoder, lambda_mse=self.lambda_mse, lambda_kl=self.lambda_kl,
-                           seed=self.seed, **kw)
+                           seed=seed, **kw)

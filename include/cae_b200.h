@@ -288,6 +288,66 @@ typedef struct CaeUnetStem {
 int cae_unet_stem_supported(const CaeUnetStem* s);
 int cae_unet_stem_eval(const CaeUnetStem* s, const CaeSrc* x, const CaeView* out, void* stream);
 
+/* ---- training-mode UNET stem in TWO launches (unet_stem_train.cu) ------------------------------------------------------
+ * Everything before the last transposed convolution of UNET.__train_epoch (unet.py:295-337 over Encoder.forward :102-112
+ * and Decoder.forward :149-163) - Conv2d/BatchNorm2d/ReLU/Dropout blocks, the two Linear-BatchNorm1d-ReLU-Dropout-Linear-
+ * ReLU-Dropout stacks, ConvTranspose2d + ChannelAttention gate + skip concat + BatchNorm2d(2C)/ReLU/Dropout blocks - as one
+ * forward and one backward COOPERATIVE kernel: a CTA owns 1..4 samples and keeps their activations (forward) and gradients
+ * (backward) in shared memory; training-mode BatchNorm couples the samples, so every BatchNorm layer is one fixed-order
+ * cross-CTA reduction (per-CTA partial rows in global memory + a grid barrier) - 7 barriers forward, 8 backward for the
+ * shipped spec, instead of ~55 dependent launches.  The weight gradients are per-CTA partial rows summed in row order.
+ * Dropout (p > 0): mask = hash(seed, step_count[0], site, sample, element) >= p, recomputed (never stored) in backward;
+ * skip connections read the activation BEFORE dropout, as the reference does (in-place ReLU, unet.py:84-85,108-109).
+ *   forward : writes `tape` ([N][tape_elems] raw layer outputs), the BatchNorm scale/shift/mean/invstd + running
+ *             statistics of every CaeBN, and `hin` = the ACTIVATED input of the head [N, 2C, H, W]
+ *   backward: reads `tape` and `dhin` (= dL/d hin, PLAIN epilogue of cae_patch_head_bwd), writes every gradient
+ *             (dw / db / dW1 / dW2, dgamma / dbeta of every CaeBN; zero for the dead biases in front of a BatchNorm) */
+typedef struct CaeStemTrainConv {
+    int Cin, Hin, Win, Cout, Hout, Wout, k, stride, pad;
+    const float *w, *b;
+    float *dw, *db;
+    CaeBN bn;
+} CaeStemTrainConv;
+typedef struct CaeStemTrainFc {
+    int in, out, has_bn;       /* has_bn: Linear - BatchNorm1d - ReLU - Dropout; else Linear - ReLU - Dropout */
+    const float *w, *b;
+    float *dw, *db;
+    CaeBN bn;
+} CaeStemTrainFc;
+typedef struct CaeStemTrainUp {
+    int Cin, Hin, Win, Cout, Hout, Wout, k, stride, pad, Cr, skip;
+    const float *w, *b, *W1, *W2;
+    float *dw, *db, *dW1, *dW2;
+    CaeBN bn;                  /* BatchNorm2d(2*Cout) */
+} CaeStemTrainUp;
+typedef struct CaeStemTrain {
+    int n_conv, n_fc, n_up, N;
+    CaeStemTrainConv conv[CAE_STEM_MAX];
+    CaeStemTrainFc   fc[CAE_STEM_MAX];
+    CaeStemTrainUp   up[CAE_STEM_MAX];
+    const float* params;       /* contiguous block (16-byte aligned, multiple of 4 floats) that holds EVERY w / b / W1 / W2 /
+                                  gamma / beta above: the engine's flat parameter arena up to the head's weights; copied to
+                                  shared memory by one bulk async copy per launch */
+    long long params_len;
+    float* tape;               /* [N][cae_unet_stem_train_tape_elems] */
+    float* hin;                /* [N, 2*C_last, H_last, W_last] contiguous */
+    const float* dhin;
+    float dropout_p;
+    unsigned long long seed;
+    const int* step_count;
+    double* bnpart;            /* cae_unet_stem_train_workspace(.., 0) doubles */
+    float* wpart;              /* cae_unet_stem_train_workspace(.., 1) floats */
+} CaeStemTrain;
+/* 1 when the geometry / batch fit the fused kernels (<= 4 samples per CTA on 148 CTAs, activations in shared memory) */
+int       cae_unet_stem_train_supported(const CaeStemTrain* s);
+long long cae_unet_stem_train_tape_elems(const CaeStemTrain* s);
+long long cae_unet_stem_train_workspace(const CaeStemTrain* s, int which);
+int       cae_unet_stem_train_fwd(const CaeStemTrain* s, const CaeSrc* x, void* stream);
+int       cae_unet_stem_train_bwd(const CaeStemTrain* s, const CaeSrc* x, void* stream);
+/* profiling aid: 64 clock64() phase timestamps of CTA 0 from the last forward ([0..31]) and backward ([32..63]) launch
+ * (slot 31 / 63 = one past the last slot used) */
+int       cae_unet_stem_train_profile(unsigned long long* out64);
+
 /* ---- patch head: transposed convolution with kernel == stride, pad 0 (the last layer of the UNET spec, e.g. k32 s32
  * 16x8x8 -> 1x256x256: nn.ConvTranspose2d unet.py:138-140), fused with torch.sigmoid (unet.py:162) and with
  * masked_mse_loss + lambda * pearson (unet.py:314-320,635-678).  Non-overlapping output patches: one tap per input

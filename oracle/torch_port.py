@@ -248,8 +248,10 @@ def unet_forward(enc, dec, spec, x, training, trace=None):
 class OracleUNet:
     """UNET.__train_epoch / __test_epoch / score (unet.py:295-380) with AdamW (unet.py:457), dropout 0"""
 
-    def __init__(self, enc_sd, dec_sd, spec, lr=1e-3, weight_decay=1e-5, lambda_pearson=1.0, zero_dead_bias_grads=False):
-        clone = lambda sd: {k: (v.detach().clone().float() if v.is_floating_point() else v.detach().clone())
+    def __init__(self, enc_sd, dec_sd, spec, lr=1e-3, weight_decay=1e-5, lambda_pearson=1.0, zero_dead_bias_grads=False,
+                 dtype=torch.float32):
+        # dtype=torch.float64: the adjudicator for "which fp32 result is closer to the exact one" (tests only)
+        clone = lambda sd: {k: (v.detach().clone().to(dtype) if v.is_floating_point() else v.detach().clone())
                             for k, v in sd.items()}
         self.enc, self.dec, self.spec = clone(enc_sd), clone(dec_sd), spec
         self.lambda_pearson = lambda_pearson

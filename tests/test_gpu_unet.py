@@ -33,9 +33,16 @@ def _dead(k):
 
 
 @pytest.mark.parametrize("use_graphs", [False, True])
-@pytest.mark.parametrize("name", ["nomask", "mask", "head16_mask"])
-def test_unet_train_steps_vs_reference(name, use_graphs):
+@pytest.mark.parametrize("name", ["nomask", "mask", "head16_mask", "head16_mask-chain"])
+def test_unet_train_steps_vs_reference(name, use_graphs, monkeypatch):
+    """`head16_mask` runs the stem as the two cooperative launches of unet_stem_train.cu (the default whenever the last
+    layer is the fused patch head), `head16_mask-chain` the same fixture through the per-layer kernels"""
+    from cae_tools_b200.engine import ops
     from cae_tools_b200.engine.unet import UNetEngine
+    chain = name.endswith("-chain")
+    name = name.replace("-chain", "")
+    if chain:
+        monkeypatch.setattr(UNetEngine, "use_fused_train_stem", False)
     g = load_npz(f"unet_{name}.npz")
     spec, enc, dec = _build(g)
     eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5, use_graphs=use_graphs)
@@ -49,9 +56,18 @@ def test_unet_train_steps_vs_reference(name, use_graphs):
         pls.append(float(data.pearson.cpu()[0]))
         if step == 0:
             b = eng._act_buffers(x.shape[0])
-            for i, t in enumerate(b["y_e"]):
+            st = eng._train_stem(x.shape[0])
+            assert (st is not None) == (fused_head and not chain)
+            if st is not None:
+                names = [n for n, _ in eng._program("train", data, x.shape[0]).sched]
+                assert "fwd.stem_train" in names and "bwd.stem_train" in names and len(names) <= 8, names
+                y_e = [ops.stem_tape_view(st, f"y_e{i}") for i in range(len(b["y_e"]))]
+                y_d = [ops.stem_tape_view(st, f"y_d{j}") for j in range(len(b["y_d"]))]
+            else:
+                y_e, y_d = b["y_e"], b["y_d"]
+            for i, t in enumerate(y_e):
                 assert rel_err(t.cpu().numpy(), g[f"act.enc.{4 * i}"]) < 1e-4, f"enc conv {i}"
-            for j, t in enumerate(b["y_d"]):
+            for j, t in enumerate(y_d):
                 assert rel_err(t.cpu().numpy(), g[f"act.dec.{4 * j}"]) < 1e-4, f"dec convT {j}"
             if fused_head:
                 assert eng._head is not None and float(b["yhat"].abs().max()) == 0.0
@@ -167,6 +183,8 @@ def test_patch_head_k32_vs_oracle_and_generic(batch, with_mask):
         if fused:
             oracle = OracleUNet(enc.state_dict(), dec.state_dict(), spec_json, lambda_pearson=0.7,
                                 zero_dead_bias_grads=True)
+            exact = OracleUNet(enc.state_dict(), dec.state_dict(), spec_json, lambda_pearson=0.7,
+                               zero_dead_bias_grads=True, dtype=torch.float64)
         eng = UNetEngine(enc, dec, lambda_pearson=0.7, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5)
         eng.use_patch_head = fused
         eng.use_fused_attention = fused        # second engine: unfused attention chain + generic conv / loss kernels
@@ -182,16 +200,26 @@ def test_patch_head_k32_vs_oracle_and_generic(batch, with_mask):
             assert abs(mse - want[0]) <= 2e-5 * want[0] and abs(pl - want[1]) <= 2e-5 * abs(want[1]), (step, mse, pl, want)
         if step == 0:
             assert engines[0][0]._head is not None and engines[1][0]._head is None
-            for prefix, sd in (("enc", oracle.enc), ("dec", oracle.dec)):
+            # Bar: 1e-4 of the tensor's max-norm against the fp32 oracle.  Where two fp32 evaluations of the same step
+            # differ by more than that (sums with heavy cancellation: the head bias, BatchNorm-coupled deep layers), the
+            # float64 evaluation adjudicates: the CUDA result must be at least as close to it as the fp32 oracle is (x2).
+            exact.train_step(x.double(), y.double(), (mask if with_mask else ones).double())
+            beyond = {}
+            for prefix, sd, sd64 in (("enc", oracle.enc, exact.enc), ("dec", oracle.dec, exact.dec)):
                 mods = [dict(e[1 if prefix == "enc" else 2].named_parameters()) for e in engines]
                 for k, ref in sd.items():
                     if not ref.requires_grad:
                         continue
-                    r = ref.grad.numpy()
+                    r, r64 = ref.grad.numpy(), sd64[k].grad.numpy()
                     scale = max(np.abs(r).max(), 1e-7)
-                    for m in mods:
+                    for mi, m in enumerate(mods):
                         got = m[k].grad.detach().cpu().numpy()
-                        assert np.abs(got - r).max() <= 2e-4 * scale + 1e-9, (prefix, k, np.abs(got - r).max(), scale)
+                        err = np.abs(got - r).max()
+                        if err > 1e-4 * scale + 1e-9:
+                            e_gpu, e_cpu = np.abs(got - r64).max(), np.abs(r - r64).max()
+                            assert e_gpu <= 2.0 * e_cpu + 1e-9 and err <= 1e-3 * scale, (prefix, k, mi, err, scale, e_gpu, e_cpu)
+                            beyond[(k, mi)] = (float(err / scale), float(e_gpu / scale), float(e_cpu / scale))
+            print("gradients beyond 1e-4 of the fp32 oracle, adjudicated by float64 (rel: vs oracle, gpu vs f64, oracle vs f64):", beyond)
     ref = oracle.score(x).numpy()
     for eng, enc, dec, data in engines:
         out = []

@@ -85,3 +85,22 @@ def test_var_model_api_trains_and_applies(tmp_path):
     m2.apply(te, ["lowres"], "est")
     m.apply(te, ["lowres"], "est0")
     np.testing.assert_allclose(np.asarray(te["est"].data), np.asarray(te["est0"].data), rtol=1e-6)
+
+
+def test_var_kl_recorded_for_every_batch_with_device_noise():
+    """the KL term of every batch lands in its own slot when the noise is drawn on the device (the path VarAEModel.train
+    uses): the reported epoch loss is mean(mse + kl), not mean(mse) + kl_last / n_batches"""
+    from cae_tools_b200.engine.varae import VarAEEngine
+    from cae_tools_b200.models.decoder import Decoder
+    from cae_tools_b200.models.model_sizer import create_model_spec
+    from cae_tools_b200.models.var_encoder import VarEncoder
+    torch.manual_seed(5)
+    spec = create_model_spec(input_size=(16, 16), input_channels=1, output_size=(64, 64), output_channels=1)
+    enc, dec = VarEncoder(spec.get_input_layers(), 4, 16), Decoder(spec.get_output_layers(), 4, 16)
+    eng = VarAEEngine(enc, dec, lambda_mse=1.0, lambda_kl=0.5, seed=7)
+    x, y = torch.rand(24, 1, 16, 16), torch.rand(24, 1, 64, 64)
+    data = eng.bind(x, y, 8)                       # 3 batches, noise drawn by cae_randn
+    losses = eng.train_epoch(data).cpu()
+    kl = data.kl.cpu()
+    assert kl.shape == (3,) and bool((kl > 0).all()), kl
+    assert torch.allclose(losses, data.losses.cpu() + kl)

@@ -153,6 +153,9 @@ EXPORTS = {
     "cae_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float,
                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "cae_step_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cae_adam_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float,
+                                   C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p]),
     "cae_vae_reparam_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "cae_vae_reparam_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,

@@ -65,6 +65,16 @@ extern "C" int cae_adam(float* p, const float* g, float* m, float* v, long long 
     return cae_check_launch("cae_adam");
 }
 
+extern "C" int cae_adam_advance(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                                float eps, float weight_decay, int decoupled, float grad_scale, int* step_count, int* cursor,
+                                int n_batches, unsigned int* ticket, void* stream) {
+    CAE_REQUIRE(p && g && m && v && step_count && ticket && n > 0, "adam_advance: bad argument");
+    int grid = min(ceil_div(n, CAE_NT), CAE_NUM_SMS * 8);
+    k_adam_advance<<<grid, CAE_NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled,
+                                                               grad_scale, step_count, cursor, n_batches, ticket);
+    return cae_check_launch("cae_adam_advance");
+}
+
 extern "C" int cae_step_advance(int* step_count, int* cursor, int n_batches, void* stream) {
     CAE_REQUIRE(step_count || cursor, "step_advance: nothing to do");
     k_step_advance<<<1, 32, 0, (cudaStream_t)stream>>>(step_count, cursor, n_batches);

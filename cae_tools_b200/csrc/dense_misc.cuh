@@ -229,6 +229,44 @@ static __global__ void __launch_bounds__(CAE_NT) k_adam(float* __restrict__ p, c
     }
 }
 
+// Adam + the step bookkeeping in ONE launch: the CTA that finishes last (ticket) advances the step counter and the batch
+// cursor - no CTA can still be reading step_count then (the separate one-thread k_step_advance launch cost ~6 us of a
+// ~220 us training step).
+static __global__ void __launch_bounds__(CAE_NT) k_adam_advance(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, long long n, float lr, float beta1, float beta2,
+                                                         float eps, float wd, int decoupled, float gscale, int* step_count,
+                                                         int* cursor, int n_batches, unsigned int* ticket) {
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        double t = (double)(*reinterpret_cast<volatile int*>(step_count) + 1);
+        double bc1 = 1.0 - pow((double)beta1, t);
+        double bc2 = 1.0 - pow((double)beta2, t);
+        s_step_size = (float)((double)lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+    for (long long i = (long long)blockIdx.x * CAE_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CAE_NT) {
+        float pi = p[i], gi = g[i] * gscale, mi = m[i], vi = v[i];
+        if (decoupled) pi *= (1.f - lr * wd);
+        else gi = fmaf(wd, pi, gi);
+        mi = fmaf(gi - mi, 1.f - beta1, mi);
+        vi = fmaf((1.f - beta2) * gi, gi, vi * beta2);
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi -= step_size * (mi / denom);
+        p[i] = pi;
+        m[i] = mi;
+        v[i] = vi;
+    }
+    if (cae_last_block(ticket) && threadIdx.x == 0) {
+        step_count[0] += 1;
+        if (cursor) {
+            int c = cursor[0] + 1;
+            cursor[0] = (c >= n_batches) ? 0 : c;
+        }
+    }
+}
+
 static __global__ void k_step_advance(int* step_count, int* cursor, int n_batches) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (step_count) step_count[0] += 1;

@@ -94,7 +94,12 @@ struct StDrop {
 // x * d < 2^32 (every index here is < 2^20, every divisor < 2^12).  One 32-bit divide per construction.
 struct StDiv {
     uint32_t m, d;
-    __device__ __forceinline__ explicit StDiv(int dd) : m(dd > 1 ? 0xFFFFFFFFu / (uint32_t)dd + 1u : 0u), d((uint32_t)dd) {}
+    // m: an over-estimate of 2^32 / d by at most 2^-21 relative (float reciprocal + guard), which keeps floor(x*m / 2^32)
+    // exact for x < 2^20 - a handful of instructions instead of an integer divide per construction
+    __device__ __forceinline__ explicit StDiv(int dd) : d((uint32_t)dd) {
+        const uint32_t a = __float2uint_rz(4294967296.f * __frcp_rn((float)dd) * 0.99999994f);
+        m = dd > 1 ? a + (a >> 21) + 2u : 0u;
+    }
     __device__ __forceinline__ int div(int x) const { return d > 1 ? (int)__umulhi((uint32_t)x, m) : x; }
     __device__ __forceinline__ int mod(int x, int q) const { return x - q * (int)d; }
 };
@@ -163,11 +168,15 @@ __device__ __forceinline__ int st_ksplit(int items, int Ci) {
 }
 
 // strided gather:  out[co][oy][ox] = bias[co] + sum_{ci,ky,kx} in[ci][oy*s - p + ky][ox*s - p + kx] * w[ci][t][co]
-__device__ __forceinline__ void st_sconv(const float* in, int Ci, int Hi, int Wi, float* out, int Co, int Ho, int Wo, int k, int s,
-                                         int p, const float* wsm, const float* bias) {
+// K > 0: kernel size known at compile time (3 / 4: every spec of the reference) - the tap loops unroll into predicated
+// LDS + LDS.128 + 4 FMA groups; K == 0: run-time loops.
+template <int K>
+__device__ __forceinline__ void st_sconv_k(const float* in, int Ci, int Hi, int Wi, float* out, int Co, int Ho, int Wo, int k, int s,
+                                           int p, const float* wsm, const float* bias) {
     const int CoP = (Co + 3) & ~3, HWo = Ho * Wo, items = HWo * (CoP >> 2), KK = k * k;
     const int KS = st_ksplit(items, Ci), slice = threadIdx.x & (KS - 1), per = ST_NT / KS;
     const StDiv dHWo(HWo), dWo(Wo);
+    const int HWi = Hi * Wi, wstep = KK * CoP;
     for (int it0 = 0; it0 < items; it0 += per) {
         const int it = it0 + threadIdx.x / KS;
         const bool valid = it < items;
@@ -176,16 +185,31 @@ __device__ __forceinline__ void st_sconv(const float* in, int Ci, int Hi, int Wi
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         const int iy0 = oy * s - p, ix0 = ox * s - p;
         const int ky0 = max(0, -iy0), ky1 = valid ? min(k, Hi - iy0) : 0, kx0 = max(0, -ix0), kx1 = min(k, Wi - ix0);
-        for (int ci = slice; ci < Ci; ci += KS) {
-            const float* ip = in + ci * Hi * Wi + iy0 * Wi + ix0;
-            const float* wp = wsm + (size_t)ci * KK * CoP + cg4;
-            for (int ky = ky0; ky < ky1; ++ky)
-                for (int kx = kx0; kx < kx1; ++kx) {
-                    const float v = ip[ky * Wi + kx];
-                    const float4 w4 = *reinterpret_cast<const float4*>(wp + (ky * k + kx) * CoP);
-                    acc[0] = fmaf(v, w4.x, acc[0]); acc[1] = fmaf(v, w4.y, acc[1]);
-                    acc[2] = fmaf(v, w4.z, acc[2]); acc[3] = fmaf(v, w4.w, acc[3]);
+        const float* ip = in + slice * HWi + iy0 * Wi + ix0;
+        const float* wp = wsm + (size_t)slice * wstep + cg4;
+        for (int ci = slice; ci < Ci; ci += KS, ip += KS * HWi, wp += KS * wstep) {
+            if (K > 0) {
+#pragma unroll
+                for (int ky = 0; ky < K; ++ky) {
+                    if (ky < ky0 || ky >= ky1) continue;
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx) {
+                        if (kx < kx0 || kx >= kx1) continue;
+                        const float v = ip[ky * Wi + kx];
+                        const float4 w4 = *reinterpret_cast<const float4*>(wp + (ky * K + kx) * CoP);
+                        acc[0] = fmaf(v, w4.x, acc[0]); acc[1] = fmaf(v, w4.y, acc[1]);
+                        acc[2] = fmaf(v, w4.z, acc[2]); acc[3] = fmaf(v, w4.w, acc[3]);
+                    }
                 }
+            } else {
+                for (int ky = ky0; ky < ky1; ++ky)
+                    for (int kx = kx0; kx < kx1; ++kx) {
+                        const float v = ip[ky * Wi + kx];
+                        const float4 w4 = *reinterpret_cast<const float4*>(wp + (ky * k + kx) * CoP);
+                        acc[0] = fmaf(v, w4.x, acc[0]); acc[1] = fmaf(v, w4.y, acc[1]);
+                        acc[2] = fmaf(v, w4.z, acc[2]); acc[3] = fmaf(v, w4.w, acc[3]);
+                    }
+            }
         }
         for (int o = KS >> 1; o > 0; o >>= 1) {
 #pragma unroll
@@ -198,13 +222,23 @@ __device__ __forceinline__ void st_sconv(const float* in, int Ci, int Hi, int Wi
         }
     }
 }
+__device__ __forceinline__ void st_sconv(const float* in, int Ci, int Hi, int Wi, float* out, int Co, int Ho, int Wo, int k, int s,
+                                         int p, const float* wsm, const float* bias) {
+    if (k == 3) st_sconv_k<3>(in, Ci, Hi, Wi, out, Co, Ho, Wo, k, s, p, wsm, bias);
+    else if (k == 4) st_sconv_k<4>(in, Ci, Hi, Wi, out, Co, Ho, Wo, k, s, p, wsm, bias);
+    else st_sconv_k<0>(in, Ci, Hi, Wi, out, Co, Ho, Wo, k, s, p, wsm, bias);
+}
 
 // transposed gather:  out[co][oy][ox] = bias[co] + sum_{ci} sum_{ky = (oy+p) % s + m*s} in[ci][(oy+p-ky)/s][..] * w[ci][t][co]
+// k <= 2*s (every transposed conv of the reference's specs: k4 s2, k3 s2): an output pixel has at most 2 x 2 taps; their
+// input / weight offsets are computed once per item and the channel loop is four predicated LDS + LDS.128 + 4 FMA groups.
 __device__ __forceinline__ void st_tconv(const float* in, int Ci, int Hi, int Wi, float* out, int Co, int Ho, int Wo, int k, int s,
                                          int p, const float* wsm, const float* bias) {
     const int CoP = (Co + 3) & ~3, HWo = Ho * Wo, items = HWo * (CoP >> 2), KK = k * k;
     const int KS = st_ksplit(items, Ci), slice = threadIdx.x & (KS - 1), per = ST_NT / KS;
-    const StDiv dHWo(HWo), dWo(Wo);
+    const StDiv dHWo(HWo), dWo(Wo), dS(s);
+    const int HWi = Hi * Wi, wstep = KK * CoP;
+    const bool two = k <= 2 * s;
     for (int it0 = 0; it0 < items; it0 += per) {
         const int it = it0 + threadIdx.x / KS;
         const bool valid = it < items;
@@ -212,21 +246,44 @@ __device__ __forceinline__ void st_tconv(const float* in, int Ci, int Hi, int Wi
         const int cgi = dHWo.div(itc), pos = dHWo.mod(itc, cgi), cg4 = cgi * 4, oy = dWo.div(pos), ox = dWo.mod(pos, oy);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         // taps ky = kyf + m*s read input row iyf - m; valid m: ky < k, 0 <= iyf - m < Hi
-        const StDiv dS(s);
         const int ty = oy + p, tx = ox + p;
         const int iyf = dS.div(ty), kyf = dS.mod(ty, iyf), ixf = dS.div(tx), kxf = dS.mod(tx, ixf);
-        const int my0 = max(0, iyf - Hi + 1), my1 = valid ? min(dS.div(k - kyf + s - 1), iyf + 1) : 0;
-        const int mx0 = max(0, ixf - Wi + 1), mx1 = min(dS.div(k - kxf + s - 1), ixf + 1);
-        for (int ci = slice; ci < Ci; ci += KS) {
-            const float* ip = in + ci * Hi * Wi + iyf * Wi + ixf;
-            const float* wp = wsm + ((size_t)ci * KK + kyf * k + kxf) * CoP + cg4;
-            for (int my = my0; my < my1; ++my)
-                for (int mx = mx0; mx < mx1; ++mx) {
-                    const float v = ip[-my * Wi - mx];
-                    const float4 w4 = *reinterpret_cast<const float4*>(wp + (my * s * k + mx * s) * CoP);
-                    acc[0] = fmaf(v, w4.x, acc[0]); acc[1] = fmaf(v, w4.y, acc[1]);
-                    acc[2] = fmaf(v, w4.z, acc[2]); acc[3] = fmaf(v, w4.w, acc[3]);
+        const float* ip = in + slice * HWi + iyf * Wi + ixf;
+        const float* wp = wsm + ((size_t)slice * KK + kyf * k + kxf) * CoP + cg4;
+        if (two) {
+            bool ok[4];
+            int io[4], wo[4];
+#pragma unroll
+            for (int my = 0; my < 2; ++my)
+#pragma unroll
+                for (int mx = 0; mx < 2; ++mx) {
+                    const int u = my * 2 + mx;
+                    ok[u] = valid && kyf + my * s < k && iyf - my >= 0 && iyf - my < Hi && kxf + mx * s < k && ixf - mx >= 0 &&
+                            ixf - mx < Wi;
+                    io[u] = -my * Wi - mx;
+                    wo[u] = (my * s * k + mx * s) * CoP;
                 }
+            for (int ci = slice; ci < Ci; ci += KS, ip += KS * HWi, wp += KS * wstep) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u]) {
+                        const float v = ip[io[u]];
+                        const float4 w4 = *reinterpret_cast<const float4*>(wp + wo[u]);
+                        acc[0] = fmaf(v, w4.x, acc[0]); acc[1] = fmaf(v, w4.y, acc[1]);
+                        acc[2] = fmaf(v, w4.z, acc[2]); acc[3] = fmaf(v, w4.w, acc[3]);
+                    }
+            }
+        } else {
+            const int my0 = max(0, iyf - Hi + 1), my1 = valid ? min(dS.div(k - kyf + s - 1), iyf + 1) : 0;
+            const int mx0 = max(0, ixf - Wi + 1), mx1 = min(dS.div(k - kxf + s - 1), ixf + 1);
+            for (int ci = slice; ci < Ci; ci += KS, ip += KS * HWi, wp += KS * wstep)
+                for (int my = my0; my < my1; ++my)
+                    for (int mx = mx0; mx < mx1; ++mx) {
+                        const float v = ip[-my * Wi - mx];
+                        const float4 w4 = *reinterpret_cast<const float4*>(wp + (my * s * k + mx * s) * CoP);
+                        acc[0] = fmaf(v, w4.x, acc[0]); acc[1] = fmaf(v, w4.y, acc[1]);
+                        acc[2] = fmaf(v, w4.z, acc[2]); acc[3] = fmaf(v, w4.w, acc[3]);
+                    }
         }
         for (int o = KS >> 1; o > 0; o >>= 1) {
 #pragma unroll
@@ -396,16 +453,23 @@ __device__ __forceinline__ void st_grid_sums(cg::grid_group& grid, double* bnpar
     const int col = threadIdx.x / tpc, sub = threadIdx.x & (tpc - 1);
     double s = 0.0;
     if (col < 2 * C) {
-        // loads issued eight at a time (one exposed L2 latency per batch), added in row order
+        // loads issued sixteen (then four) at a time - one exposed L2 latency per batch - and added in row order
         const double* cp = base + col;
         const size_t rs = 2 * ST_CMAX;
         int r = sub;
-        for (; r + 7 * tpc < rows; r += 8 * tpc) {
-            double v[8];
+        for (; r + 15 * tpc < rows; r += 16 * tpc) {
+            double v[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(cp + (size_t)(r + u * tpc) * rs);
+            for (int u = 0; u < 16; ++u) v[u] = __ldcg(cp + (size_t)(r + u * tpc) * rs);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) s += v[u];
+            for (int u = 0; u < 16; ++u) s += v[u];
+        }
+        for (; r + 3 * tpc < rows; r += 4 * tpc) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcg(cp + (size_t)(r + u * tpc) * rs);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s += v[u];
         }
         for (; r < rows; r += tpc) s += __ldcg(cp + (size_t)r * rs);
     }

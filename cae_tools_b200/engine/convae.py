@@ -434,10 +434,10 @@ class ConvAEEngine:
         out = []
         if self.grad_hook is not None:
             out.append(("grad_allreduce", lambda: self.grad_hook(self.grads)))
-        out.append(("adam", lambda: ops.adam(self.arena, self.grads, self.adam_m, self.adam_v, self.n_params, self.lr,
-                                             self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                             self.decoupled, self.grad_scale, self.step_count)))
-        out.append(("advance", lambda: ops.step_advance(self.step_count, data.cursor, data.n_batches)))
+        # optimiser + bookkeeping (step counter, batch cursor) in one launch
+        out.append(("adam", lambda t=self._ticket(): ops.adam_advance(
+            self.arena, self.grads, self.adam_m, self.adam_v, self.n_params, self.lr, self.betas[0], self.betas[1], self.eps,
+            self.weight_decay, self.decoupled, self.grad_scale, self.step_count, data.cursor, data.n_batches, t)))
         return out
 
     def _eval_prepare_op(self):

@@ -158,6 +158,13 @@ def adam(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, grad_sca
                          _stream()), "cae_adam")
 
 
+def adam_advance(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, grad_scale, step_count, cursor, n_batches,
+                 ticket):
+    check(lib().cae_adam_advance(_ptr(p), _ptr(g), _ptr(m), _ptr(v), int(n), float(lr), float(beta1), float(beta2),
+                                 float(eps), float(weight_decay), int(bool(decoupled)), float(grad_scale), _ptr(step_count),
+                                 _ptr(cursor), int(n_batches), _ptr(ticket), _stream()), "cae_adam_advance")
+
+
 def step_advance(step_count, cursor, n_batches):
     check(lib().cae_step_advance(_ptr(step_count), _ptr(cursor), int(n_batches), _stream()), "cae_step_advance")
 

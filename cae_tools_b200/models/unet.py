@@ -10,7 +10,9 @@ Differences that are deliberate:
 * the cosine schedule with eta_min == lr is the identity (unet.py:458-459): constant learning rate;
 * with no mask variable the reference builds a mask shaped like the INPUT, which cannot broadcast against the
   output unless both sizes agree; here the default mask is all ones of the OUTPUT shape;
-* dropout_rate > 0 is not implemented for training on the CUDA path (raises); apply() is unaffected.
+* dropout (the reference default is 0.1): masks come from a counter-based hash inside the fused training stem
+  (csrc/unet_stem_train.cu), not from torch's generator, so a run is reproducible from (seed, step) but not
+  bit-comparable with the reference's random stream; at dropout_rate = 0 the two paths are comparable to 1e-4.
 The layer spec has to be symmetric (decoder layer j's output = encoder skip j) and is normally supplied through
 `--layer-definitions-path`, exactly as for the reference.
 """

@@ -188,6 +188,10 @@ int cae_adam(float* p, const float* g, float* m, float* v, long long n, float lr
              float eps, float weight_decay, int decoupled, float grad_scale, const int* step_count, void* stream);
 /* end-of-step bookkeeping: step_count[0] += 1 ; if cursor: cursor[0] = (cursor[0]+1) % n_batches */
 int cae_step_advance(int* step_count, int* cursor, int n_batches, void* stream);
+/* cae_adam + cae_step_advance in one launch (the last CTA to finish - `ticket`, zero-initialised - does the bookkeeping) */
+int cae_adam_advance(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int decoupled, float grad_scale, int* step_count, int* cursor,
+                     int n_batches, unsigned int* ticket, void* stream);
 
 /* ---- UNET pieces (reference: src/cae_tools/models/unet.py) -------------------------------------------
  * plane = one (n, c) image.  cae_plane_stats: stats[(n*C+c)*4 + {0..3}] = sum, sum of squares, max, argmax

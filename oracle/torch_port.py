@@ -208,8 +208,11 @@ def pearson_corr(pred, target, mask):
     return num / torch.sum(m, dim=2)
 
 
-def unet_forward(enc, dec, spec, x, training, trace=None):
-    """Encoder.forward unet.py:102-112 + Decoder.forward unet.py:149-163 with dropout p = 0"""
+def unet_forward(enc, dec, spec, x, training, trace=None, drop=None):
+    """Encoder.forward unet.py:102-112 + Decoder.forward unet.py:149-163.  drop(site, x) applies the dropout of the
+    reference's nn.Dropout layers (unet.py:85,96,99,125,128,145) with an explicit mask; None = p 0.  The skip list holds
+    the in-place ReLU outputs, i.e. the activations BEFORE dropout (unet.py:84-85,108-109)."""
+    dr = (lambda site, t: t) if (drop is None or not training) else drop
     skips = []
     for i, sp in enumerate(spec["input_layers"]):
         x = F.conv2d(x, enc[f"encoder_cnn.{4 * i}.weight"], enc[f"encoder_cnn.{4 * i}.bias"], stride=sp["stride"],
@@ -218,16 +221,18 @@ def unet_forward(enc, dec, spec, x, training, trace=None):
             trace["enc"].append(x)
         x = F.relu(_bn(x, enc, f"encoder_cnn.{4 * i + 1}", training))
         skips.append(x)
+        x = dr(i, x)
     skips.pop()
     x = x.flatten(1)
     x = F.linear(x, enc["encoder_lin.0.weight"], enc["encoder_lin.0.bias"])
-    x = F.relu(_bn(x, enc, "encoder_lin.1", training))
+    x = dr(4, F.relu(_bn(x, enc, "encoder_lin.1", training)))
     x = F.relu(F.linear(x, enc["encoder_lin.4.weight"], enc["encoder_lin.4.bias"]))
     if trace is not None:
         trace["z"] = x
+    x = dr(5, x)
     x = F.linear(x, dec["decoder_lin.0.weight"], dec["decoder_lin.0.bias"])
-    x = F.relu(_bn(x, dec, "decoder_lin.1", training))
-    x = F.relu(F.linear(x, dec["decoder_lin.4.weight"], dec["decoder_lin.4.bias"]))
+    x = dr(6, F.relu(_bn(x, dec, "decoder_lin.1", training)))
+    x = dr(7, F.relu(F.linear(x, dec["decoder_lin.4.weight"], dec["decoder_lin.4.bias"])))
     c, h, w = spec["output_layers"][0]["input_dimensions"]
     x = x.view(-1, c, h, w)
     skips = skips[::-1]
@@ -241,7 +246,7 @@ def unet_forward(enc, dec, spec, x, training, trace=None):
             avg, mx = x.mean(dim=(2, 3), keepdim=True), x.amax(dim=(2, 3), keepdim=True)
             att = torch.sigmoid(F.conv2d(F.relu(F.conv2d(avg, w1)), w2) + F.conv2d(F.relu(F.conv2d(mx, w1)), w2))
             x = torch.cat((x * att, skips[j]), 1)
-            x = F.relu(_bn(x, dec, f"decoder_conv.{4 * j + 1}", training))
+            x = dr(8 + j, F.relu(_bn(x, dec, f"decoder_conv.{4 * j + 1}", training)))
     return torch.sigmoid(x)
 
 
@@ -263,8 +268,25 @@ class OracleUNet:
                 self.params.append(sd[k])
         self.optim = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)
 
+    def set_dropout(self, p, seed):
+        """dropout with the CUDA path's counter-based masks (oracle/dropout_hash.py); the step counter advances with
+        every train_step like the device-side one"""
+        self.dropout_p, self.dropout_seed, self.steps_done = float(p), int(seed), 0
+
+    def _drop(self):
+        p = getattr(self, "dropout_p", 0.0)
+        if p <= 0:
+            return None
+        from .dropout_hash import drop_mask
+
+        def apply(site, t):
+            n = t.shape[0]
+            m = drop_mask(p, self.dropout_seed, self.steps_done, site, n, t[0].numel())
+            return t * torch.from_numpy(m).to(t.dtype).view(t.shape)
+        return apply
+
     def losses(self, x, y, mask, training):
-        yhat = unet_forward(self.enc, self.dec, self.spec, x, training)
+        yhat = unet_forward(self.enc, self.dec, self.spec, x, training, drop=self._drop())
         mse = masked_mse_loss(yhat, y, mask)
         pl = 1 - torch.mean(pearson_corr(yhat, y, mask))
         return mse, pl, yhat
@@ -281,6 +303,7 @@ class OracleUNet:
                 self.enc[k].grad.zero_()
             self.dec["decoder_lin.0.bias"].grad.zero_()
         self.optim.step()
+        self.steps_done = getattr(self, "steps_done", 0) + 1
         return float(mse.detach()), float(pl.detach())
 
     def score(self, x):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import load_npz, rel_err, spec_of, split_sd
+from helpers import ROOT, load_npz, rel_err, spec_of, split_sd
 
 pytestmark = pytest.mark.gpu
 
@@ -258,3 +258,94 @@ def test_patch_head_ragged_tail_and_multichannel():
     out = []
     eng.score_batches(eng.bind(x, None, 4), lambda i, yh: out.append(yh.cpu().numpy().copy()))
     assert rel_err(np.concatenate(out), oracle.score(x).numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("batch,p", [(5, 0.1), (64, 0.3)])
+def test_unet_dropout_matches_oracle_with_identical_masks(batch, p):
+    """dropout_rate > 0 (the reference's default is 0.1: unet.py:74,115,203, cli/train_cae.py:39): the fused stem draws its
+    masks from a counter-based hash; the oracle applies the SAME masks (oracle/dropout_hash.py) through torch autograd -
+    losses of 3 steps (fresh masks every step), every gradient of step 0, keep rate and 1/(1-p) scaling"""
+    from cae_tools_b200.engine.unet import UNetEngine
+    from cae_tools_b200.models.unet_modules import UNetDecoder, UNetEncoder
+    from oracle.dropout_hash import drop_mask
+    from oracle.torch_port import OracleUNet
+    spec, spec_json = _shipped_spec()
+    torch.manual_seed(9)
+    gen = torch.Generator().manual_seed(23)
+    x, y = torch.rand(batch, 1, 16, 16, generator=gen), torch.rand(batch, 1, 256, 256, generator=gen)
+    ones = torch.ones_like(y)
+    enc = UNetEncoder(spec.get_input_layers(), 8, 32, p)
+    dec = UNetDecoder(spec.get_output_layers(), 8, 32, p)
+    seed = 0x1234ABCD5678
+    oracle = OracleUNet(enc.state_dict(), dec.state_dict(), spec_json, lambda_pearson=0.7, zero_dead_bias_grads=True)
+    exact = OracleUNet(enc.state_dict(), dec.state_dict(), spec_json, lambda_pearson=0.7, zero_dead_bias_grads=True,
+                       dtype=torch.float64)
+    oracle.set_dropout(p, seed)
+    exact.set_dropout(p, seed)
+    eng = UNetEngine(enc, dec, lambda_pearson=0.7, dropout_rate=p, seed=seed, lr=1e-3, weight_decay=1e-5)
+    data = eng.bind(x, y, batch)
+    m = drop_mask(p, seed, 0, 8, 4096, 1024)
+    assert abs(float((m == 0).mean()) - p) < 5e-3 and abs(float(m.max()) - 1.0 / (1.0 - p)) < 1e-6
+    for step in range(3):
+        want = oracle.train_step(x, y, ones)
+        mse = float(eng.train_epoch(data).cpu()[0])
+        pl = float(data.pearson.cpu()[0])
+        # the masks make the loss landscape rougher: a single differently-rounded ReLU / mask decision is invisible at 1e-4
+        assert abs(mse - want[0]) <= 1e-4 * want[0] and abs(pl - want[1]) <= 1e-4 * abs(want[1]), (step, mse, pl, want)
+        if step == 0:
+            st = eng._train_stem(batch)
+            assert st is not None, "dropout needs the fused training stem"
+            # the activated head input carries the mask of site 8 + (n_up - 1): zeros exactly where the oracle mask is zero
+            hin = st.t_hin.cpu().numpy().reshape(batch, -1)
+            mk = drop_mask(p, seed, 0, 8 + 1, batch, hin.shape[1])
+            assert np.all(hin[mk == 0] == 0.0)
+            exact.train_step(x.double(), y.double(), ones.double())
+            for sd, sd64, mod in ((oracle.enc, exact.enc, enc), (oracle.dec, exact.dec, dec)):
+                for k, prm in mod.named_parameters():
+                    r, r64 = sd[k].grad.numpy(), sd64[k].grad.numpy()
+                    got = prm.grad.detach().cpu().numpy()
+                    scale = max(np.abs(r).max(), 1e-7)
+                    err = np.abs(got - r).max()
+                    if err > 1e-4 * scale + 1e-9:
+                        if k == "decoder_conv.8.bias":
+                            # the head bias gradient is ONE scalar: the sum of N * 65 536 cancelling terms (sum |dz| ~ 10^3 x
+                            # |sum dz|), each formed with the SFU-approximate sigmoid of patch_head.cu (2e-7 relative, not
+                            # zero-mean): 8e-4 of its value here (2e-4 at p = 0).  Accumulation itself is fp64.
+                            assert err <= 2e-3 * scale, (k, err, scale)
+                            continue
+                        e_gpu, e_cpu = np.abs(got - r64).max(), np.abs(r - r64).max()
+                        assert e_gpu <= 2.0 * e_cpu + 1e-9 and err <= 1e-3 * scale, (k, err, scale, e_gpu, e_cpu)
+    # eval mode ignores dropout
+    out = []
+    eng.score_batches(eng.bind(x, None, batch), lambda i, yh: out.append(yh.cpu().numpy().copy()))
+    assert rel_err(out[0], oracle.score(x).numpy()) < 1e-3
+
+
+def test_train_cae_unet_runs_with_the_reference_default_flags(tmp_path):
+    """`train_cae --method unet` with default flags (--dropout-rate 0.1, reference cli/train_cae.py:39,135) trains, saves,
+    reloads (parameters.json carries dropout_rate 0.1) and continues"""
+    from cae_tools_b200.cli import apply_cae, train_cae
+    from cae_tools_b200.utils import xr_lite
+    from oracle import datagen
+    paths = {}
+    for name, seed in (("train", 0), ("test", 1)):
+        lo, hi = datagen.generate(24, (16, 16), (256, 256), "circle", seed=seed)
+        ds = xr_lite.Dataset()
+        ds["lowres"] = xr_lite.DataArray(lo, dims=("n", "chan", "y1", "x1"))
+        ds["hires"] = xr_lite.DataArray(hi, dims=("n", "chan", "y2", "x2"))
+        paths[name] = str(tmp_path / f"{name}.nc")
+        ds.to_netcdf(paths[name])
+    folder = str(tmp_path / "model")
+    spec_path = os.path.join(ROOT, "cae_tools_b200", "specs", "unet_16x16_256x256.json")
+    common = ["--train-inputs", paths["train"], "--test-inputs", paths["test"], "--model-folder", folder, "--input-variables", "lowres",
+              "--output-variable", "hires", "--method", "unet", "--layer-definitions-path", spec_path]
+    train_cae.main(common + ["--nr-epochs", "6"])
+    params = json.load(open(os.path.join(folder, "parameters.json")))
+    assert params["type"] == "UNET" and abs(params["dropout_rate"] - 0.1) < 1e-12
+    hist = json.load(open(os.path.join(folder, "history.json")))
+    assert np.isfinite(hist["train_loss"]).all() and np.isfinite(hist["test_loss"]).all()
+    train_cae.main(common + ["--nr-epochs", "3", "--continue-training"])
+    assert json.load(open(os.path.join(folder, "history.json")))["nr_epochs"] == 9
+    out = str(tmp_path / "scores.nc")
+    apply_cae.main([paths["test"], out, "--model-folder", folder, "--prediction-variable", "est"])
+    assert np.isfinite(xr_lite.open_dataset(out)["est"].values).all()

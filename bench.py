@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
     ap.add_argument("--train-only", action="store_true", help="skip the e2e / apply legs (short runs under ncu)")
+    ap.add_argument("--apply-sweep", type=int, default=0, metavar="N",
+                    help="BASELINE configs[4]: apply() inference sweep over N images (16x16 -> 256x256 unet), sharded over the "
+                         "ranks with no collective; prints one apply_images_per_sec line instead of the training line")
+    ap.add_argument("--no-api-leg", action="store_true", help="skip the UNET.train / UNET.apply model-class leg")
     a = ap.parse_args()
     set_workload(a.method)
     if a.batch is None:
@@ -347,7 +351,7 @@ def run_b200(args):
     X = torch.rand(NB * B, *IN_SHAPE, device=dev, generator=gen)
     Y = torch.rand(NB * B, *OUT_SHAPE, device=dev, generator=gen)
     data = eng.bind(X, Y, B)
-    prog = eng._program("train", data, B)
+    prog = eng.program("train", data, B)
 
     def barrier():
         if world > 1:
@@ -407,7 +411,7 @@ def run_b200(args):
     XA = torch.rand(APPLY_BATCHES * AB, *IN_SHAPE, device=dev, generator=gen)
     adata = eng.bind(XA, None, AB)
     eng._eval_prepare_op()()
-    aprog = eng._program("score", adata, AB)
+    aprog = eng.program("score", adata, AB)
     for _ in range(W):
         aprog.run()
     Ka = max(10, K // 4)
@@ -417,7 +421,7 @@ def run_b200(args):
     yah = torch.empty(AB, *OUT_SHAPE).pin_memory()
     xas = torch.empty(AB, *IN_SHAPE, device=dev)
     sadata = eng.bind(xas, None, AB)
-    saprog = eng._program("score", sadata, AB)
+    saprog = eng.program("score", sadata, AB)
     yout = eng.output_buffer(eng._act_buffers(AB))
 
     def apply_e2e():
@@ -435,14 +439,21 @@ def run_b200(args):
 
     clocks.stop()       # sampled over every timed region above (train, host-fed train, apply, host-fed apply)
 
-    # ---- per-kernel table (eager, CUDA events around every launch) -> dominant kernel roofline
-    table = prog.profile(reps=5)
+    # ---- per-kernel table: what every launch adds to the critical path INSIDE the captured step (prefix graphs, warm;
+    # engine/convae.py:_Program.timeline) - the step is bound by its longest chain, not by an eager per-op sum.
+    # Programs with an eager collective between two graphs (CAE_CAPTURE_ALLREDUCE=0) fall back to eager per-op events.
+    if hasattr(prog, "timeline") and world == 1:
+        table = [(n, us / 1e3) for n, us in prog.timeline(reps=30 if method == "conv4" else 100)]
+        table_kind = "in-graph prefix timeline"
+    else:
+        table = prog.profile(reps=5)
+        table_kind = "eager CUDA events per launch"
+    step_ms = ms / K
     if args.profile_ops and rank == 0:
-        tot = sum(t for _, t in table)
         for name, t in sorted(table, key=lambda r: -r[1]):
             ob = op_bytes(name, spec, B)
-            gbs = f"{ob / t / 1e6:8.0f} GB/s" if ob else ""
-            print(f"  {name:28s} {t * 1e3:8.1f} us {100 * t / tot:5.1f}%  {gbs}", file=sys.stderr)
+            gbs = f"{ob / t / 1e6:8.0f} GB/s" if ob and t > 0 else ""
+            print(f"  {name:28s} {t * 1e3:8.1f} us {100 * t / step_ms:5.1f}% of the step  {gbs}", file=sys.stderr)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -451,16 +462,20 @@ def run_b200(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    conv_rows = [(n, t, op_bytes(n, spec, B)) for n, t in table if op_bytes(n, spec, B)]
-    # dominant kernel = the launch that carries the most algorithmic bytes of the step (what bounds the step at the
-    # roofline); the longest launches by wall time are listed beside it in "kernels"
+    conv_rows = [(n, t, op_bytes(n, spec, B)) for n, t in table if op_bytes(n, spec, B) and t > 0]
+    # dominant kernel = the launch that carries the most algorithmic bytes of the step (what bounds the step at the HBM
+    # roofline); "longest" = the launch that adds the most time to the step, whatever it moves
     top = max(conv_rows, key=lambda r: (r[2], r[1]))
     achieved = top[2] / (top[1] / 1e3) / 1e9
     b_train, b_apply = bytes_per_sample(spec, FC, LATENT)
+    longest = max(table, key=lambda r: r[1])
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "kernel_us": top[1] * 1e3, "kernel_share_of_step": top[1] / sum(t for _, t in table),
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "timing": table_kind,
+                "kernel_us": top[1] * 1e3, "kernel_share_of_step": top[1] / step_ms,
                 "algorithmic_bytes_per_launch": top[2],
+                "longest": {"kernel": longest[0], "us": longest[1] * 1e3, "share_of_step": longest[1] / step_ms,
+                            "algorithmic_bytes": op_bytes(longest[0], spec, B)},
+                "launches": [{"kernel": n, "us": t * 1e3, "share_of_step": t / step_ms} for n, t in table] if len(table) <= 12 else None,
                 "kernels": [{"kernel": n, "us": t * 1e3, "algorithmic_bytes": ob, "achieved_gbs": ob / (t / 1e3) / 1e9}
                             for n, t, ob in sorted(conv_rows, key=lambda r: -r[1])[:5]],
                 "step": {"bytes_per_sample": b_train, "achieved": b_train * B / (ms / K / 1e3) / 1e9,
@@ -481,11 +496,23 @@ def run_b200(args):
                               "launch_groups_us": {n: t * 1e3 for n, t, _ in tc_rows},
                               "note": "time includes the pack / im2col / col2im passes of each layer, not the GEMM alone"}
 
-    # ncu --set full (profiles/r01_head_ncu.md): DRAM bytes of one launch of the fused head kernels at batch 64
-    NCU_TRAFFIC = {"bwd.head2": 17163008, "fwd.head2+sigmoid+loss": 17154048}
-    if B == 64 and method == "unet" and top[0] in NCU_TRAFFIC:
-        roofline["traffic"] = NCU_TRAFFIC[top[0]]
-        roofline["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_head_ncu.md"
+    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json: op name, batch and the
+    # hash of the kernel's source file at capture time; a stale hash is reported instead of a stale number)
+    try:
+        import hashlib
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ncu = json.load(f)
+        ent = ncu.get(f"{method}:{top[0]}:{B}")
+        if ent:
+            with open(os.path.join(ROOT, ent["source"]), "rb") as f:
+                cur = hashlib.sha256(f.read()).hexdigest()[:16]
+            if cur == ent["source_sha256_16"]:
+                roofline["traffic"] = ent["dram_bytes"]
+                roofline["traffic_source"] = ent["capture"]
+            else:
+                roofline["traffic_source"] = f"stale: {ent['source']} changed since {ent['capture']}"
+    except Exception:
+        pass
 
     # ---- the ConvAEModel geometry of BASELINE configs[0] at the same batch, short run (secondary numbers)
     also = None
@@ -493,23 +520,49 @@ def run_b200(args):
         spec_c, enc_c, dec_c = build_modules("conv")
         eng_c = ConvAEEngine(enc_c, dec_c, lr=1e-3, weight_decay=1e-5, device=dev)
         data_c = eng_c.bind(X[:16 * B], Y[:16 * B], B)
-        prog_c = eng_c._program("train", data_c, B)
+        prog_c = eng_c.program("train", data_c, B)
         for _ in range(W):
             prog_c.run()
         kc = max(20, K // 4)
         ms_c = timed(prog_c.run, kc)
         adata_c = eng_c.bind(XA, None, AB)
         eng_c._eval_prepare_op()()
-        aprog_c = eng_c._program("score", adata_c, AB)
+        aprog_c = eng_c.program("score", adata_c, AB)
         for _ in range(3):
             aprog_c.run()
         ms_ca = timed(aprog_c.run, 10)
         bt_c, ba_c = bytes_per_sample(spec_c, FC, LATENT)
+        # ... and at configs[0]'s own batch size (10)
+        data_c10 = eng_c.bind(X[:64 * 10], Y[:64 * 10], 10)
+        prog_c10 = eng_c.program("train", data_c10, 10)
+        for _ in range(W):
+            prog_c10.run()
+        ms_c10 = timed(prog_c10.run, kc)
         also = {"workload": workload_config("conv", B, 1)["workload"],
                 "train_samples_per_sec": B * kc / (ms_c / 1e3), "ms_per_step": ms_c / kc,
+                "batch10": {"train_samples_per_sec": 10 * kc / (ms_c10 / 1e3), "ms_per_step": ms_c10 / kc,
+                            "step_frac_of_hbm_roofline": bt_c * 10 / (ms_c10 / kc / 1e3) / 1e9 / hbm_peak},
                 "apply_images_per_sec": AB * 10 / (ms_ca / 1e3), "launches_per_step": prog_c.n_launches,
                 "step_frac_of_hbm_roofline": bt_c * B / (ms_c / kc / 1e3) / 1e9 / hbm_peak,
                 "apply_frac_of_hbm_roofline": ba_c * AB / (ms_ca / 10 / 1e3) / 1e9 / hbm_peak}
+
+    # ---- the model classes themselves (what train_cae / apply_cae call): UNET(...).train on an in-memory data set
+    # (normalisation + one H2D of everything + epochs, as the reference does) and UNET.apply (host arrays in, host
+    # float64 array out).  Wall clock, everything included.
+    api = None
+    if method == "unet" and world == 1 and not args.no_api_leg:
+        api = api_leg(B)
+
+    # ---- data-parallel exchange: the flat gradient arena, all-reduced alone (what one step's exchange costs)
+    comm = None
+    if world > 1:
+        g = eng.grads
+        for _ in range(5):
+            dist.all_reduce(g)
+        ms_ar = timed(lambda: dist.all_reduce(g), 50)
+        comm = {"allreduce_us": ms_ar / 50 * 1e3, "arena_bytes": g.numel() * 4,
+                "in_step_graph": bool(getattr(eng, "capture_allreduce", False)),
+                "note": "one NCCL all-reduce of the flat fp32 gradient arena per optimiser step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -534,9 +587,139 @@ def run_b200(args):
                               "d2h_bytes_per_step": AB * numel(OUT_SHAPE) * 4}},
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "api": api,
+            "comm": comm,
             "conv": also,
             "final_loss": final_loss,
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def api_leg(B):
+    """UNET model class end to end on host data: train (E epochs over n cases) and apply; wall-clock rates"""
+    import numpy as np
+    import torch
+    from cae_tools_b200.models.model_sizer import ModelSpec
+    from cae_tools_b200.models.unet import UNET
+    from cae_tools_b200.utils import xr_lite
+    n, E = 8 * B, 6
+    rng = np.random.RandomState(0)
+    ds, dt = xr_lite.Dataset(), xr_lite.Dataset()
+    for d, m in ((ds, n), (dt, B)):
+        d["lowres"] = xr_lite.DataArray(rng.rand(m, *IN_SHAPE).astype(np.float32), dims=("n", "chan", "y1", "x1"))
+        d["hires"] = xr_lite.DataArray(rng.rand(m, *OUT_SHAPE).astype(np.float32), dims=("n", "chan", "y2", "x2"))
+    spec = ModelSpec()
+    with open(UNET_SPEC) as f:
+        spec.load(json.load(f))
+    torch.manual_seed(0)
+    mdl = UNET(batch_size=B, nr_epochs=E, test_interval=E, encoded_dim_size=LATENT, fc_size=FC, dropout_rate=0.1)
+    mdl.verbose = False
+    mdl.spec = spec
+    t0 = time.perf_counter()
+    mdl.train(["lowres"], "hires", ds, dt)
+    torch.cuda.synchronize()
+    t_train = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mdl.apply(ds, ["lowres"], "est")
+    t_apply = time.perf_counter() - t0
+    return {"call": "UNET(batch_size=%d, dropout_rate=0.1).train(...) / .apply(...) on in-memory data sets" % B,
+            "train_samples_per_sec": n * E / t_train, "train_seconds": t_train, "cases": n, "epochs": E,
+            "apply_images_per_sec": n / t_apply, "apply_seconds": t_apply,
+            "note": "wall clock incl. min/max normalisation on the host, one H2D of all batches, the two post-training "
+                    "evaluate() passes (train) and the float64 de-normalised host array (apply)"}
+
+
+def run_apply_sweep(args):
+    """BASELINE configs[4]: N images sharded contiguously over the ranks (engine/dp.py:shard_bounds), no collective; every
+    rank streams its shard through the eval-mode program in micro-batches of 4096 with inputs device-resident; outputs stay
+    on the device (the engine's output buffer is the ring) - and, second number, are copied to pinned host memory."""
+    import torch
+    import torch.distributed as dist
+    from cae_tools_b200.engine.dp import shard_bounds
+    from cae_tools_b200.engine.unet import UNetEngine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    spec, enc, dec = build_modules("unet")
+    eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, device=dev)
+    lo, hi = shard_bounds(args.apply_sweep, rank, world)
+    n = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(2000 + rank)
+    X = torch.rand(n, *IN_SHAPE, device=dev, generator=gen)
+    AB = APPLY_BATCH
+    data = eng.bind(X, None, AB)
+    stage = [torch.empty(AB, *OUT_SHAPE).pin_memory() for _ in range(2)]
+    copy = torch.cuda.Stream(device=dev)
+
+    def sweep(d2h):
+        main = torch.cuda.current_stream(dev)
+        k = [0]
+
+        def sink(i, yh):
+            if d2h:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(copy):
+                    copy.wait_event(ev)
+                    stage[i & 1][:yh.shape[0]].copy_(yh, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy)
+                main.wait_event(done)
+            k[0] += yh.shape[0]
+        eng.score_batches(data, sink)
+        assert k[0] == n
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sweep(False)                                   # warm-up: graphs captured, eval BatchNorm folded
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms = min(timed(lambda: sweep(False)) for _ in range(3))
+    ms_d2h = timed(lambda: sweep(True)) if args.apply_sweep <= 200000 * world else None
+    clocks.stop()
+    _, b_apply = bytes_per_sample(spec, FC, LATENT)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    if rank == 0:
+        value = args.apply_sweep / (ms / 1e3)
+        line = {"metric": "apply_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": 3, "warmup": 1,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"apply() sweep over N={args.apply_sweep} images 1x16x16->1x256x256 unet (BASELINE configs[4]), "
+                                       f"sharded contiguously over {world} GPU(s), micro-batch {AB}, no collective; inputs device-resident, "
+                                       "outputs left in the engine's device buffer", "parallelism": f"shard{world}",
+                           "l2": f"{n * 1024 / 1e6:.0f} MB of inputs and 1 GB of outputs per micro-batch per GPU: nothing is reused from L2"},
+                "clocks": clocks.summary(),
+                "e2e": None if ms_d2h is None else {"value": args.apply_sweep / (ms_d2h / 1e3), "unit": "images/s",
+                                                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n * numel(OUT_SHAPE) * 4,
+                                                    "note": "outputs copied to pinned host memory (double-buffered); inputs resident"},
+                "gpu_launches": eng.program("score", data, AB).n_launches * ((n + AB - 1) // AB) * 3,
+                "roofline": {"bound": "hbm", "bytes_per_image": b_apply, "achieved": b_apply * args.apply_sweep / world / (ms / 1e3) / 1e9,
+                             "peak": hbm, "unit": "GB/s", "frac": b_apply * args.apply_sweep / world / (ms / 1e3) / 1e9 / hbm,
+                             "traffic": None, "note": "SURVEY 8(d) convention B_apply = in + 2*inter + out per image, per GPU"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -550,6 +733,8 @@ def main():
         os.execv(sys.executable, cmd)
     if args.impl == "reference":
         run_reference(args)
+    elif args.apply_sweep > 0:
+        run_apply_sweep(args)
     else:
         run_b200(args)
 

@@ -69,6 +69,9 @@ class ConvAEEngine:
     # arenas (26 MB).
     overlap_allreduce = False
 
+    # data-parallel exchange captured inside the step graph (CAE_CAPTURE_ALLREDUCE=0: eager NCCL between two graphs)
+    capture_allreduce = os.environ.get("CAE_CAPTURE_ALLREDUCE", "1") != "0"
+
     # fc bottleneck as one launch per direction (fc_stack.cu).  Correct and tested, but measured no faster than the
     # cae_gemm chain on B200 (unet batch 64: 25 + 40 us fused against 31 + 35 us; conv: 30 + 41 against 14 + 20): a
     # dependent launch costs only ~1 us inside a graph, while a single CTA pays every phase's latency serially.
@@ -453,6 +456,11 @@ class ConvAEEngine:
         return lambda: ops.bn_eval_prepare(self._bn_table, self._bn_count)
 
     # ------------------------------------------------------------------ execution
+    def program(self, kind, data, N):
+        """the step program (op list captured into a CUDA graph on first run) for one batch geometry: kind = "train" |
+        "test" | "score"; .run() executes one step, .n_launches / .sched describe it, .profile() / .timeline() time it"""
+        return self._program(kind, data, N)
+
     def _program(self, kind, data, N):
         """build (and cache on the binding) the op list / CUDA graph for one batch geometry"""
         key = (kind, N)
@@ -486,10 +494,12 @@ class ConvAEEngine:
             prog = _BucketedProgram(_Program(sched[:i], self.use_graphs, state), _Program(sched[i:j], self.use_graphs, state),
                                     _Program(sched[j + 1:], self.use_graphs, state), self.grad_hook_async,
                                     self.grads[e:], self.grads[:e])
+        elif "grad_allreduce" in names and self.capture_allreduce and self.use_graphs:
+            # the gradient all-reduce is captured INSIDE the step graph (NCCL collectives are capturable): one graph
+            # launch per step, no host round trip between the backward pass and the optimiser.  Round 1 launched NCCL
+            # eagerly between two graphs (+21 us at 2 GPUs, +39 us at 8 on a 330 us step).
+            prog = _Program(sched, self.use_graphs, state)
         elif "grad_allreduce" in names:
-            # the data-parallel exchange stays OUTSIDE the captured graphs (NCCL launched eagerly between the
-            # backward graph and the optimiser graph): robust against capture restrictions of the collective
-            # library, and a single 141 KB - 26 MB all-reduce per step is latency-, not launch-bound
             i = names.index("grad_allreduce")
             prog = _SplitProgram(_Program(sched[:i], self.use_graphs, state), sched[i][1],
                                  _Program(sched[i + 1:], self.use_graphs, state))
@@ -697,6 +707,33 @@ class _Program:
             for t, c in zip(self.state, saved):
                 t.copy_(c)
         return [(name, acc[i] / reps) for i, (name, _) in enumerate(self.sched)]
+
+    def timeline(self, reps=50, stride=1):
+        """in-graph cost of every op: the prefixes sched[:k] are captured as graphs and their replays timed; the
+        difference between consecutive prefixes is what op k adds to the critical path of the captured step (warm,
+        overlapped with the side streams - unlike eager per-op events or ncu's cold serialised durations).
+        -> [(name, microseconds added)]; state is restored."""
+        saved = [t.clone() for t in self.state]
+        out, prev = [], 0.0
+        ks = [k for k in range(1, len(self.sched) + 1) if k % stride == 0 or k == len(self.sched)]
+        for k in ks:
+            p = _Program(self.sched[:k], True, self.state)
+            for _ in range(3):
+                p.run()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                p.run()
+            b.record()
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) / reps * 1e3
+            out.append((self.sched[k - 1][0], us - prev))
+            prev = us
+        with torch.no_grad():
+            for t, c in zip(self.state, saved):
+                t.copy_(c)
+        return out
 
     def run(self):
         if not self.use_graph:

@@ -387,6 +387,7 @@ def run_b200(args):
             print(json.dumps({"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                               "steps": K, "warmup": W, "ms_per_step": ms / K, "launches_per_step": prog.n_launches,
                               "note": "--train-only run (profiling aid, not a bench line)"}), flush=True)
+        finish(world)
         return
 
     # ---- train end to end through the engine's host-fed entry point: every step's inputs come from pinned host
@@ -593,8 +594,7 @@ def run_b200(args):
             "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 def api_leg(B):
@@ -721,8 +721,20 @@ def run_apply_sweep(args):
                              "peak": hbm, "unit": "GB/s", "frac": b_apply * args.apply_sweep / world / (ms / 1e3) / 1e9 / hbm,
                              "traffic": None, "note": "SURVEY 8(d) convention B_apply = in + 2*inter + out per image, per GPU"}}
         print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """leave without tearing down NCCL communicators / CUDA graphs one by one (a teardown that hangs after the line was
+    printed would cost the whole run): every rank reaches the barrier, flushes, exits 0"""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -206,6 +206,10 @@ EXPORTS = {
     "cae_unet_stem_train_fwd": (C.c_int, [C.POINTER(CaeStemTrain), C.POINTER(CaeSrc), C.c_void_p]),
     "cae_unet_stem_train_profile": (C.c_int, [C.c_void_p]),
     "cae_unet_stem_train_bwd": (C.c_int, [C.POINTER(CaeStemTrain), C.POINTER(CaeSrc), C.c_void_p]),
+    "cae_minmax_partials_len": (C.c_longlong, []),
+    "cae_minmax": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cae_normalise_gather": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int,
+                                       C.c_void_p, C.c_longlong, C.c_void_p]),
     "cae_randn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
 }
 

@@ -69,8 +69,11 @@ class ConvAEEngine:
     # arenas (26 MB).
     overlap_allreduce = False
 
-    # data-parallel exchange captured inside the step graph (CAE_CAPTURE_ALLREDUCE=0: eager NCCL between two graphs)
-    capture_allreduce = os.environ.get("CAE_CAPTURE_ALLREDUCE", "1") != "0"
+    # Data-parallel exchange captured inside the step graph (CAE_CAPTURE_ALLREDUCE=1).  OFF by default - measured on 2 x B200
+    # (unet, batch 64 per GPU): 0.239 ms/step captured against 0.222 ms single-GPU, no better than the eager NCCL call
+    # between two graphs (the 21 us latency of a 157 KB all-reduce is on the critical path either way), and a process
+    # group destroyed while graphs that captured NCCL kernels are alive hung at exit.
+    capture_allreduce = os.environ.get("CAE_CAPTURE_ALLREDUCE", "0") == "1"
 
     # fc bottleneck as one launch per direction (fc_stack.cu).  Correct and tested, but measured no faster than the
     # cae_gemm chain on B200 (unet batch 64: 25 + 40 us fused against 31 + 35 us; conv: 30 + 41 against 14 + 20): a
@@ -495,9 +498,7 @@ class ConvAEEngine:
                                     _Program(sched[j + 1:], self.use_graphs, state), self.grad_hook_async,
                                     self.grads[e:], self.grads[:e])
         elif "grad_allreduce" in names and self.capture_allreduce and self.use_graphs:
-            # the gradient all-reduce is captured INSIDE the step graph (NCCL collectives are capturable): one graph
-            # launch per step, no host round trip between the backward pass and the optimiser.  Round 1 launched NCCL
-            # eagerly between two graphs (+21 us at 2 GPUs, +39 us at 8 on a 330 us step).
+            # opt-in: the gradient all-reduce captured INSIDE the step graph (see capture_allreduce above)
             prog = _Program(sched, self.use_graphs, state)
         elif "grad_allreduce" in names:
             i = names.index("grad_allreduce")

@@ -528,3 +528,25 @@ def stem_tape_view(st: CaeStemTrain, name):
     for d in shape:
         n *= d
     return st.t_tape[:, off:off + n].reshape(st.t_tape.shape[0], *shape)
+
+
+# ---- data ingest on the device ----------------------------------------------------------------------------------------------
+def minmax(x):
+    """(min, max, nan_count) of a fp32 CUDA tensor in one pass"""
+    x = x.contiguous()
+    part = torch.empty(int(lib().cae_minmax_partials_len()), dtype=torch.float32, device=x.device)
+    ticket = torch.zeros(1, dtype=torch.int32, device=x.device)
+    out = torch.empty(3, dtype=torch.float32, device=x.device)
+    check(lib().cae_minmax(_ptr(x), int(x.numel()), _ptr(part), _ptr(ticket), _ptr(out), _stream()), "cae_minmax")
+    lo, hi, nan = out.cpu().tolist()
+    return float(lo), float(hi), int(nan)
+
+
+def normalise_gather(src, order, lo, hi, normalise, dst, chan_offset=0):
+    """dst[i, chan_offset:chan_offset + C] = (src[order[i]] - lo) / (hi - lo); src [n, C, y, x], dst [n_out, Ctot, y, x]"""
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == torch.float32 and dst.dtype == torch.float32
+    elems = src[0].numel()
+    off = chan_offset * src.shape[2] * src.shape[3]
+    check(lib().cae_normalise_gather(_ptr(src), int(elems), _ptr(order), int(dst.shape[0]), float(lo), float(hi),
+                                     int(bool(normalise)), dst.data_ptr() + 4 * off, int(dst[0].numel()), _stream()),
+          "cae_normalise_gather")

@@ -284,10 +284,14 @@ class ConvAEModel(BaseModel):
         self.engine = eng = self._make_engine(device, dp)
         if dp is not None:
             dp.broadcast_([eng.arena] + [b for m in (self.encoder, self.decoder) for b in m.buffers()])
-        train_data = eng.bind(torch.from_numpy(train_ds.input_array(train_order)),
-                              torch.from_numpy(train_ds.output_array(train_order)), local_batch)
-        test_data = eng.bind(torch.from_numpy(test_ds.input_array(test_order)),
-                             torch.from_numpy(test_ds.output_array(test_order)), local_batch)
+        def bind(ds, order):
+            dev_arrays = ds.device_arrays(order)        # normalise + shuffle + batch assembly on the device (csrc/ingest.cu)
+            if dev_arrays is not None:
+                ds.release_device()
+                return eng.bind(dev_arrays[0], dev_arrays[1], local_batch)
+            return eng.bind(torch.from_numpy(ds.input_array(order)), torch.from_numpy(ds.output_array(order)), local_batch)
+
+        train_data, test_data = bind(train_ds, train_order), bind(test_ds, test_order)
         gather = (lambda t: dp.reduce_losses(t)) if dp is not None else (lambda t: t)
 
         train_loss = test_loss = 0.0

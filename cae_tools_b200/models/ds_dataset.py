@@ -31,17 +31,16 @@ class DSDataset(torch.utils.data.Dataset):
         self.input_y, self.input_x = first.shape[2], first.shape[3]
         self.mask_da = ds[mask_variable_name] if mask_variable_name is not None else None
 
+        self._raw = {}      # variable name -> raw fp32 CUDA tensor (device ingest path)
         out_values = np.asarray(ds[output_variable_name].values)
-        bad = int(np.isnan(out_values).sum())
+        out_lo, out_hi, bad = self._scan(output_variable_name, out_values)
         if bad > 0:
             raise ValueError(f"output variable contains {bad} NaN values")
 
         self.min_inputs, self.max_inputs = {}, {}
         for name, da in zip(input_variable_names, self.input_das):
             values = np.asarray(da.values)
-            self.min_inputs[name] = float(np.nanmin(values))
-            self.max_inputs[name] = float(np.nanmax(values))
-            bad = int(np.isnan(values).sum())
+            self.min_inputs[name], self.max_inputs[name], bad = self._scan(name, values)
             if bad > 0:
                 raise ValueError(f"input variable {name} contains {bad} NaN values")
             self.input_spec.append({"name": name, "shape": list(da.shape[1:])})
@@ -49,13 +48,57 @@ class DSDataset(torch.utils.data.Dataset):
         if output_variable_name:
             self.output_da = ds[output_variable_name]
             self.output_chan, self.output_y, self.output_x = self.output_da.shape[1:4]
-            self.min_output = float(np.nanmin(out_values))
-            self.max_output = float(np.nanmax(out_values))
+            self.min_output, self.max_output = out_lo, out_hi
             self.output_spec = {"name": output_variable_name, "shape": list(self.output_da.shape[1:])}
         else:
             self.output_da = None
             self.output_chan = self.output_y = self.output_x = None
             self.min_output = self.max_output = None
+
+    # ---- device ingest: raw fp32 arrays are uploaded once; the min / max / NaN scan, the min-max
+    # normalisation and the assembly of the shuffled batches run as HBM-bound kernels (csrc/ingest.cu) instead of numpy
+    # passes on the host.  Falls back to numpy without a CUDA device, for non-fp32 data and for arrays beyond DEVICE_BUDGET.
+    DEVICE_BUDGET = 16 << 30
+
+    def _device_ok(self, values):
+        return torch.cuda.is_available() and values.dtype == np.float32 and values.ndim == 4 and \
+            0 < values.nbytes <= self.DEVICE_BUDGET
+
+    def _scan(self, name, values):
+        """(min, max, NaN count) of one variable: reference ds_dataset.py:49-75 (np.nanmin / np.nanmax / isnan().sum())"""
+        if self._device_ok(values):
+            from ..engine import ops
+            if name not in self._raw:
+                self._raw[name] = torch.from_numpy(np.ascontiguousarray(values)).cuda()
+            return ops.minmax(self._raw[name])
+        return float(np.nanmin(values)), float(np.nanmax(values)), int(np.isnan(values).sum())
+
+    def device_arrays(self, order=None, device=None, with_mask=False):
+        """(X, Y, M) normalised fp32 CUDA tensors in `order` - the device-side equivalent of input_array / output_array /
+        mask_array followed by the H2D copy; bit-identical to them (fp32 subtract + IEEE divide).  None when the device
+        path does not apply (the caller then uses the numpy methods)."""
+        names = list(self.input_variable_names) + ([self.output_variable_name] if self.output_da is not None else [])
+        if not torch.cuda.is_available() or any(n not in self._raw for n in names):
+            return None
+        from ..engine import ops
+        dev = self._raw[names[0]].device
+        n_out = self.n if order is None else len(order)
+        idx = None if order is None else torch.as_tensor(np.asarray(order, dtype=np.int32), device=dev)
+        X = torch.empty(n_out, self.input_chan, self.input_y, self.input_x, dtype=torch.float32, device=dev)
+        c = 0
+        for name, da in zip(self.input_variable_names, self.input_das):
+            ops.normalise_gather(self._raw[name], idx, self.min_inputs[name], self.max_inputs[name], self.normalise_in, X, c)
+            c += da.shape[1]
+        Y = None
+        if self.output_da is not None:
+            Y = torch.empty(n_out, self.output_chan, self.output_y, self.output_x, dtype=torch.float32, device=dev)
+            ops.normalise_gather(self._raw[self.output_variable_name], idx, self.min_output, self.max_output,
+                                 self.normalise_out, Y, 0)
+        M = torch.from_numpy(self.mask_array(order)).to(dev) if with_mask else None
+        return X, Y, M
+
+    def release_device(self):
+        self._raw = {}
 
     # ---- configuration
     def set_normalise_output(self, normalise_out):

@@ -117,6 +117,10 @@ class UNET(ConvAEModel):
         has_mask = mask_variable_name is not None
 
         def bind(ds, order):
+            dev_arrays = ds.device_arrays(order, with_mask=has_mask)    # device ingest (csrc/ingest.cu) when possible
+            if dev_arrays is not None:
+                ds.release_device()
+                return eng.bind(dev_arrays[0], dev_arrays[1], local_batch, mask=dev_arrays[2])
             mask = torch.from_numpy(ds.mask_array(order)) if has_mask else None
             return eng.bind(torch.from_numpy(ds.input_array(order)), torch.from_numpy(ds.output_array(order)),
                             local_batch, mask=mask)

@@ -468,6 +468,17 @@ int cae_tc_convt_dgrad(const CaeTcConv* c, const float* weight, const CaeView* d
 /* grad[Cin][Cout][kh][kw] = weight gradient (split-K, slices summed in index order) */
 int cae_tc_convt_wgrad(const CaeTcConv* c, float* grad, void* stream);
 
+/* ---- data ingest on the device (ingest.cu): the host-side steps on either side of the hot path ------
+ * cae_minmax: out3 = {min, max, NaN count} of a raw fp32 array (DSDataset.__init__ scan, ds_dataset.py:49-75);
+ * partials: cae_minmax_partials_len() floats, ticket: one zeroed uint.
+ * cae_normalise_gather: dst[i][:] = (src[order[i]][:] - lo) / (hi - lo) (0 when hi == lo; copy when normalise == 0):
+ * min-max normalisation + batch assembly in the shuffled order (ds_dataset.py:99-113,137-159 + default collate), written
+ * into a channel slice of the batch tensor (dst_sample_stride >= sample_elems).  order == NULL: identity. */
+long long cae_minmax_partials_len(void);
+int cae_minmax(const float* x, long long n, float* partials, unsigned int* ticket, float* out3, void* stream);
+int cae_normalise_gather(const float* src, long long sample_elems, const int* order, int n_out, float lo, float hi,
+                         int normalise, float* dst, long long dst_sample_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

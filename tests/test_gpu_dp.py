@@ -77,3 +77,64 @@ def test_two_rank_nccl_equals_single_gpu(tmp_path, overlap):
             continue   # local BN: the unbiased correction M/(M-1) uses the per-rank element count
         if a.dtype.kind == "f":
             assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1e-3), k
+
+
+def _unet_models():
+    import json
+    from cae_tools_b200.models.model_sizer import ModelSpec
+    from cae_tools_b200.models.unet_modules import UNetDecoder, UNetEncoder
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = ModelSpec()
+    spec.load(json.load(open(os.path.join(root, "cae_tools_b200", "specs", "unet_16x16_256x256.json"))))
+    torch.manual_seed(31)
+    return UNetEncoder(spec.get_input_layers(), 4, 16, 0.0), UNetDecoder(spec.get_output_layers(), 4, 16, 0.0)
+
+
+def _unet_data():
+    g = torch.Generator().manual_seed(32)
+    return torch.rand(6, 1, 16, 16, generator=g), torch.rand(6, 1, 256, 256, generator=g)
+
+
+def _unet_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from cae_tools_b200.engine.dp import DPContext
+    from cae_tools_b200.engine.unet import UNetEngine
+    dp = DPContext.from_env()
+    enc, dec = _unet_models()
+    x, y = _unet_data()
+    eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5, device=torch.device("cuda", rank),
+                     grad_hook=dp.allreduce_grads, count_scale=1.0 / world)
+    data = eng.bind(x, y, 6)
+    losses = [float(dp.reduce_losses(eng.train_epoch(data)).cpu()[0]) for _ in range(3)]
+    assert eng._train_stem(6) is not None
+    if rank == 0:
+        sd = {k: v.detach().cpu().numpy() for k, v in list(enc.state_dict().items()) + list(dec.state_dict().items())}
+        np.savez(os.path.join(out_dir, "dpu.npz"), losses=np.array(losses), **{k.replace(".", "_"): v for k, v in sd.items()})
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_unet_fused_stem_equals_single_gpu(tmp_path):
+    """the fused (cooperative) training stem under data parallelism: both ranks hold the same shard, so the 2-rank run must
+    reproduce the single-GPU run on the duplicated batch"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_unet_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = dict(np.load(os.path.join(str(tmp_path), "dpu.npz")))
+    from cae_tools_b200.engine.unet import UNetEngine
+    enc, dec = _unet_models()
+    x, y = _unet_data()
+    eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5)
+    data = eng.bind(x.repeat(2, 1, 1, 1), y.repeat(2, 1, 1, 1), 12)
+    ref = [float(eng.train_epoch(data).cpu()[0]) for _ in range(3)]
+    np.testing.assert_allclose(got["losses"], ref, rtol=5e-5)
+    for k, v in list(enc.state_dict().items()) + list(dec.state_dict().items()):
+        a, b = got[k.replace(".", "_")], v.detach().cpu().numpy()
+        if k.endswith("running_var") or a.dtype.kind != "f":
+            continue
+        assert np.abs(a - b).max() <= 2e-4 * max(np.abs(b).max(), 1e-3), k

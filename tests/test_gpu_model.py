@@ -260,3 +260,38 @@ def test_train_stream_equals_resident_training(method):
         results.append((losses.numpy(), eng.arena.detach().cpu().numpy().copy()))
     np.testing.assert_array_equal(results[0][0], results[1][0])
     np.testing.assert_array_equal(results[0][1], results[1][1])
+
+
+def test_device_ingest_matches_dsdataset_host_path():
+    """csrc/ingest.cu (min / max / NaN scan, min-max normalisation + shuffled batch assembly on the device) against the
+    numpy methods of DSDataset (reference ds_dataset.py:49-75,99-113,137-159): bit-identical"""
+    from cae_tools_b200.engine import ops
+    from cae_tools_b200.models.ds_dataset import DSDataset
+    from cae_tools_b200.utils import xr_lite
+    rng = np.random.RandomState(3)
+    ds = xr_lite.Dataset()
+    ds["a"] = xr_lite.DataArray((288 + 10 * rng.rand(37, 2, 16, 16)).astype(np.float32), dims=("n", "c", "y", "x"))
+    ds["b"] = xr_lite.DataArray(rng.randn(37, 1, 16, 16).astype(np.float32), dims=("n", "c1", "y", "x"))
+    ds["const"] = xr_lite.DataArray(np.full((37, 1, 16, 16), 3.0, dtype=np.float32), dims=("n", "c1", "y", "x"))
+    ds["out"] = xr_lite.DataArray((5 * rng.rand(37, 1, 64, 64) - 2).astype(np.float32), dims=("n", "c1", "y2", "x2"))
+    d = DSDataset(ds, ["a", "b", "const"], "out")
+    assert set(d._raw) == {"a", "b", "const", "out"}                      # the device path was taken
+    vals = {k: np.asarray(ds[k].values) for k in ("a", "b", "const", "out")}
+    for k in ("a", "b", "const"):
+        assert d.min_inputs[k] == float(vals[k].min()) and d.max_inputs[k] == float(vals[k].max())
+    assert d.min_output == float(vals["out"].min()) and d.max_output == float(vals["out"].max())
+    order = list(rng.permutation(37))
+    X, Y, M = d.device_arrays(order, with_mask=True)
+    assert np.array_equal(X.cpu().numpy(), d.input_array(order))
+    assert np.array_equal(Y.cpu().numpy(), d.output_array(order))
+    assert M.shape == Y.shape and float(M.min()) == 1.0
+    X0, Y0, _ = d.device_arrays()
+    assert np.array_equal(X0.cpu().numpy(), d.input_array()) and np.array_equal(Y0.cpu().numpy(), d.output_array())
+    # NaN detection
+    bad = np.asarray(ds["a"].values).copy()
+    bad[5, 1, 3, 3] = np.nan
+    lo, hi, nan = ops.minmax(torch.from_numpy(bad).cuda())
+    assert nan == 1 and lo == float(np.nanmin(bad)) and hi == float(np.nanmax(bad))
+    ds["a"] = xr_lite.DataArray(bad, dims=("n", "c", "y", "x"))
+    with pytest.raises(ValueError):
+        DSDataset(ds, ["a", "b"], "out")

@@ -19,6 +19,12 @@
 #include "conv_family.cuh"
 
 #define PH_CIN 16
+// The Pearson statistics are accumulated on (yhat - PH_SHIFT, target - PH_SHIFT): single-pass raw moments of data that live in
+// [0, 1] around 0.5 lose ~2 digits in M_dd - mu^2 M (fp32 per-thread partial sums); every gradient behind the head then sat
+// 2-4e-5 (max-norm relative) from the float64 evaluation of the step - 20x the fp32 reference's own distance - and the 50-epoch
+// loss curve drifted 3x beyond the reference's thread-count spread (tools/grad_deviation.py, profiles/r02_parity_notes.md).
+// ph_finalize's algebra is unchanged: fed with shifted moments it returns the gradient coefficients of the shifted variables.
+#define PH_SHIFT 0.5f
 
 struct PhArgs {
     CaeSrc in;
@@ -51,6 +57,19 @@ __device__ __forceinline__ float4 ph_ld4(const float* p) { return __ldg(reinterp
 // reciprocal is a Newton iteration, ex2 without .ftz carries denormal scaling): ncu showed 127 instructions per 4-pixel
 // strip against 32 FFMA2 of useful work.
 __device__ __forceinline__ float ph_sigmoid(float v) { return cae_fast_sigmoid(v); }
+// Optional IEEE form for the training kernels (1 / (1 + expf(-v)), what torch evaluates).  Measured (tools/grad_deviation.py):
+// no effect on the distance of the gradients from the float64 evaluation, +8 us per step - the deviation came from the
+// un-centred loss moments (PH_SHIFT below), not from the SFU approximations.  Kept off.
+#ifndef CAE_PH_EXACT_TRAIN_SIGMOID
+#define CAE_PH_EXACT_TRAIN_SIGMOID 0
+#endif
+__device__ __forceinline__ float ph_sigmoid_train(float v) {
+#if CAE_PH_EXACT_TRAIN_SIGMOID
+    return 1.f / (1.f + expf(-v));
+#else
+    return cae_fast_sigmoid(v);
+#endif
+}
 
 // packed fp32 pairs: sm_100 issues two FMAs per FFMA2 instruction (fma.rn.f32x2), which halves the issue slots of the
 // three 16 x 4 FMA blocks these kernels are made of
@@ -283,25 +302,29 @@ __global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
                     upk(acc01, acc[0], acc[1]);
                     upk(acc23, acc[2], acc[3]);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) d[k] = ph_sigmoid(acc[k]);
+                    for (int k = 0; k < 4; ++k) d[k] = LOSS ? ph_sigmoid_train(acc[k]) : ph_sigmoid(acc[k]);
                     if (WRITE) __stcs(reinterpret_cast<float4*>(yp + j * K), make_float4(d[0], d[1], d[2], d[3]));
                     if (LOSS) {
+                        // first / second moments of (d - PH_SHIFT), (t - PH_SHIFT): variances and the covariance are shift
+                        // invariant, and centring the [0, 1] data removes most of the cancellation in M_dd - mu^2 M
                         const float t[4] = {t4[q].x, t4[q].y, t4[q].z, t4[q].w};
                         if (MASK) {
                             const float m[4] = {m4[q].x, m4[q].y, m4[q].z, m4[q].w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const float md = m[k] * d[k], mt = m[k] * t[k], e = (d[k] - t[k]) * m[k];
+                                const float ds = d[k] - PH_SHIFT, ts = t[k] - PH_SHIFT;
+                                const float md = m[k] * ds, mt = m[k] * ts, e = (d[k] - t[k]) * m[k];
                                 mo[0] += m[k]; mo[1] += md; mo[2] += mt;
-                                mo[3] = fmaf(md, d[k], mo[3]); mo[4] = fmaf(mt, t[k], mo[4]); mo[5] = fmaf(md, t[k], mo[5]);
+                                mo[3] = fmaf(md, ds, mo[3]); mo[4] = fmaf(mt, ts, mo[4]); mo[5] = fmaf(md, ts, mo[5]);
                                 mo[6] = fmaf(e, e, mo[6]);
                             }
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
+                                const float ds = d[k] - PH_SHIFT, ts = t[k] - PH_SHIFT;
                                 const float e = d[k] - t[k];
-                                mo[1] += d[k]; mo[2] += t[k];
-                                mo[3] = fmaf(d[k], d[k], mo[3]); mo[4] = fmaf(t[k], t[k], mo[4]); mo[5] = fmaf(d[k], t[k], mo[5]);
+                                mo[1] += ds; mo[2] += ts;
+                                mo[3] = fmaf(ds, ds, mo[3]); mo[4] = fmaf(ts, ts, mo[4]); mo[5] = fmaf(ds, ts, mo[5]);
                                 mo[6] = fmaf(e, e, mo[6]);
                             }
                         }
@@ -410,7 +433,8 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
                 const float* tp = tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + kx;
                 const float* mp = MASK ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx
                                        : nullptr;
-                // without a mask: g = c0 (d - t) + ca t + cb d + ce = gd d + gt t + ce
+                // without a mask: g = c0 (d - t) + ca t' + cb d' + ce = gd d' + gt t' + ce   (d' = d - PH_SHIFT, t' = t - PH_SHIFT;
+                // the coefficients are those of the shifted variables, see ph_finalize)
                 const float gd = c0 + cb2, gt = ca - c0;
                 for (int j0 = 0; j0 < a.Win; j0 += PF) {
                     float4 t4[PF], m4[PF];
@@ -432,13 +456,13 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
                             float dz[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const float d = ph_sigmoid(acc[k]);
+                                const float d = ph_sigmoid_train(acc[k]);
                                 float g;
                                 if (MASK) {
                                     const float m = k == 0 ? m4[q].x : (k == 1 ? m4[q].y : (k == 2 ? m4[q].z : m4[q].w));
-                                    g = m * fmaf(c0 * m, d - t[k], fmaf(ca, t[k], fmaf(cb2, d, ce)));
+                                    g = m * fmaf(c0 * m, d - t[k], fmaf(ca, t[k] - PH_SHIFT, fmaf(cb2, d - PH_SHIFT, ce)));
                                 } else {
-                                    g = fmaf(gd, d, fmaf(gt, t[k], ce));
+                                    g = fmaf(gd, d - PH_SHIFT, fmaf(gt, t[k] - PH_SHIFT, ce));
                                 }
                                 dz[k] = g * fmaf(-d, d, d);
                             }

@@ -97,9 +97,10 @@ def gen_layers(name, in_size, out_size, in_ch, out_ch, batch, latent=4, fc=16, s
         optim.zero_grad()
         loss.backward()
         if step == 0:
-            out.update(acts)
+            out.update({k: (v[:, :, ::light, ::light] if light and v.shape[-1] >= 128 else v) for k, v in acts.items()})
             out["z"] = z.detach().numpy().copy()
-            out["yhat"] = yhat.detach().numpy().copy()
+            yh = yhat.detach().numpy().copy()
+            out["yhat"] = yh[:, :, ::light, ::light] if light else yh
             for k, p in enc.named_parameters():
                 out["grad.enc." + k] = p.grad.detach().numpy().copy()
             for k, p in dec.named_parameters():
@@ -183,7 +184,9 @@ def unet_spec_with_head(k):
     return spec
 
 
-def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lambda_pearson=1.0, spec_dict=None):
+def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lambda_pearson=1.0, spec_dict=None, light=0):
+    # light > 0: the 256x256 fixtures of the shipped k32 spec - y / mask are regenerated by the test from `data_seed`
+    # (torch's CPU generator is platform-independent) and the full-resolution tensors are stored subsampled by `light`
     """the reference's unet Encoder / Decoder / masked_mse_loss / pearson_corr_torch + AdamW, dropout 0
     (UNET() itself cannot be constructed offline: its constructor downloads VGG weights - SURVEY section 0)"""
     from cae_tools.models import unet as ru
@@ -199,9 +202,16 @@ def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lamb
     x = torch.rand(batch, 1, 16, 16, generator=g)
     y = torch.rand(batch, 1, oh, ow, generator=g)
     mask = (torch.rand(batch, 1, oh, ow, generator=g) > 0.3).float() if with_mask else torch.ones(batch, 1, oh, ow)
-    out = {"x": x.numpy(), "y": y.numpy(), "mask": mask.numpy()}
+    out = {"x": x.numpy(), "data_seed": np.array(seed + 1), "batch": np.array(batch), "with_mask": np.array(int(with_mask))}
+    if not light:
+        out.update({"y": y.numpy(), "mask": mask.numpy()})
     out.update(sd_np(enc.state_dict(), "init.enc."))
     out.update(sd_np(dec.state_dict(), "init.dec."))
+    enc.eval(); dec.eval()
+    with torch.no_grad():                       # eval-mode prediction with the INITIAL weights / BatchNorm buffers
+        z0, skip0 = enc(x)
+        e0 = dec(z0, skip0).numpy().copy()
+        out["eval_yhat_init"] = e0[:, :, ::light, ::light] if light else e0
     acts, hooks = {}, []
     for prefix, seq in (("enc", enc.encoder_cnn), ("dec", dec.decoder_conv)):
         for idx, mod in enumerate(seq):
@@ -219,9 +229,10 @@ def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lamb
         pl = 1 - torch.mean(ru.UNET.pearson_corr_torch(None, yhat, y, mask))
         (mse + lambda_pearson * pl).backward()
         if step == 0:
-            out.update(acts)
+            out.update({k: (v[:, :, ::light, ::light] if light and v.shape[-1] >= 128 else v) for k, v in acts.items()})
             out["z"] = z.detach().numpy().copy()
-            out["yhat"] = yhat.detach().numpy().copy()
+            yh = yhat.detach().numpy().copy()
+            out["yhat"] = yh[:, :, ::light, ::light] if light else yh
             for k, p in enc.named_parameters():
                 out["grad.enc." + k] = p.grad.detach().numpy().copy()
             for k, p in dec.named_parameters():
@@ -236,11 +247,114 @@ def gen_unet(name, with_mask, batch=6, latent=8, fc=32, seed=4321, steps=3, lamb
     enc.eval(); dec.eval()
     with torch.no_grad():
         z, skip = enc(x)
-        out["eval_yhat"] = dec(z, skip).numpy().copy()
+        ey = dec(z, skip).numpy().copy()
+        out["eval_yhat"] = ey[:, :, ::light, ::light] if light else ey
+    out["light"] = np.array(light)
     out["spec_json"] = np.array(json.dumps(spec_dict))
     path = os.path.join(GOLD, f"unet_{name}.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path) // 1024, "KB", "mse", mses, "pearson", pls)
+
+
+def gen_unet_curve(name="unet_b64_e50", batch_size=64, nr_epochs=50, seed=1234, n=100, latent=4, fc=16, lambda_pearson=1.0):
+    """BASELINE configs[1]: the reference's UNET training loop (unet.py:388-529 setup, :295-337 train epoch, :339-372 test
+    epoch) on the seeded circle data with the shipped 16x16 -> 256x256 spec, dropout 0, batch 64 (64 + 36), 50 epochs,
+    test_interval 1.  UNET() itself cannot be constructed offline (VGG download in its constructor), so the loop is run on
+    the reference's own unet.Encoder / unet.Decoder / masked_mse_loss / pearson_corr_torch / AdamW with the reference's
+    DSDataset and torch DataLoader(shuffle=True) - module construction first, then the two loaders, like UNET.train."""
+    from cae_tools.models import unet as ru
+    from cae_tools.models.ds_dataset import DSDataset
+    from cae_tools.models.model_sizer import ModelSpec
+    spec_dict = unet_spec_with_head(32)
+    spec = ModelSpec()
+    spec.load(spec_dict)
+    tr, te = datagen.circle_datasets(n, n)
+    train_ds = DSDataset(tr, ["lowres"], "hires", normalise_in=True, normalise_out=True)
+    test_ds = DSDataset(te, ["lowres"], "hires", normalise_in=True, normalise_out=True)
+    test_ds.set_normalisation_parameters(train_ds.get_normalisation_parameters())
+    torch.manual_seed(seed)
+    enc = ru.Encoder(spec.get_input_layers(), encoded_space_dim=latent, fc_size=fc, dropout_rate=0.0)
+    dec = ru.Decoder(spec.get_output_layers(), encoded_space_dim=latent, fc_size=fc, dropout_rate=0.0)
+    train_loader = torch.utils.data.DataLoader(train_ds, batch_size=batch_size, shuffle=True)
+    test_loader = torch.utils.data.DataLoader(test_ds, batch_size=batch_size, shuffle=True)
+    optim = torch.optim.AdamW(list(enc.parameters()) + list(dec.parameters()), lr=1e-3, weight_decay=1e-5)
+    # the reference's default mask has the INPUT's shape (ds_dataset.py:157) and cannot broadcast against the output: the
+    # all-ones mask of the OUTPUT's shape is what "no mask" means (documented deviation, cae_tools_b200/models/unet.py)
+    fix = lambda b: (b[0], b[1], torch.ones_like(b[1]))
+    train_batches = [fix(b) for b in train_loader]
+    test_batches = [fix(b) for b in test_loader]
+    hist = {"train_loss": [], "test_loss": [], "train_pearson": [], "test_pearson": []}
+    for epoch in range(nr_epochs):
+        enc.train(); dec.train()
+        tl, tp = [], []
+        for x, y, m in train_batches:
+            optim.zero_grad()
+            z, skip = enc(x)
+            yhat = dec(z, skip)
+            mse = ru.UNET.masked_mse_loss(None, yhat, y, m)
+            pl = 1 - torch.mean(ru.UNET.pearson_corr_torch(None, yhat, y, m))
+            (mse + lambda_pearson * pl).backward()
+            optim.step()
+            tl.append(mse.item()); tp.append(pl.item())
+        enc.eval(); dec.eval()
+        el, ep = [], []
+        with torch.no_grad():
+            for x, y, m in test_batches:
+                z, skip = enc(x)
+                yhat = dec(z, skip)
+                el.append(ru.UNET.masked_mse_loss(None, yhat, y, m).numpy())
+                ep.append((1 - torch.mean(ru.UNET.pearson_corr_torch(None, yhat, y, m))).numpy())
+        hist["train_loss"].append(float(np.mean(tl))); hist["train_pearson"].append(float(np.mean(tp)))
+        hist["test_loss"].append(float(np.mean(el))); hist["test_pearson"].append(float(np.mean(ep)))
+    out = {k: np.array(v) for k, v in hist.items()}
+    enc.eval(); dec.eval()
+    with torch.no_grad():
+        x4 = torch.stack([torch.as_tensor(np.asarray(test_ds[i][0])) for i in range(4)])
+        z, skip = enc(x4)
+        pred = dec(z, skip).numpy()
+    out["pred_sub"] = pred[:, :, ::8, ::8].copy()
+    out.update(sd_np(enc.state_dict(), "final.enc."))
+    out.update(sd_np(dec.state_dict(), "final.dec."))
+    out["spec_json"] = np.array(json.dumps(spec_dict))
+    path = os.path.join(GOLD, f"curve_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path) // 1024, "KB", "train", hist["train_loss"][:2], hist["train_loss"][-1], "test", hist["test_loss"][-1])
+
+
+def gen_linear(name="linear_mini", seed=77, steps=3):
+    """the reference's Linear module (linear.py:33-49) + MSELoss + Adam(lr, weight_decay) (linear_model.py:236-247): losses,
+    gradients of step 0, weights after `steps`, prediction - pins oracle/torch_port.OracleLinear and the CUDA engine"""
+    from cae_tools.models.linear import Linear
+    torch.manual_seed(seed)
+    mod = Linear((1, 16, 16), (1, 64, 64))
+    g = torch.Generator().manual_seed(seed + 1)
+    x, y = torch.rand(8, 1, 16, 16, generator=g), torch.rand(8, 1, 64, 64, generator=g)
+    # (the 4 MB initial weight is not stored: torch.manual_seed(seed) + the same module tree regenerates it; 256 of its
+    #  4096 rows are kept to verify that)
+    out = {"x": x.numpy(), "y": y.numpy(), "seed": np.array(seed)}
+    out["init.weight_sub"] = mod.linear[1].weight.detach().numpy()[::16].copy()
+    out["init.bias"] = mod.linear[1].bias.detach().numpy().copy()
+    optim = torch.optim.Adam([{"params": mod.parameters()}], lr=1e-3, weight_decay=1e-5)
+    loss_fn = torch.nn.MSELoss()
+    losses = []
+    for step in range(steps):
+        loss = loss_fn(mod(x), y)
+        optim.zero_grad()
+        loss.backward()
+        if step == 0:
+            w = mod.linear[1].weight.grad.numpy()
+            out["grad.weight_sub"] = w[::16].copy()               # 256 of the 4096 rows
+            out["grad.bias"] = mod.linear[1].bias.grad.numpy().copy()
+        optim.step()
+        losses.append(float(loss.detach()))
+    out["losses"] = np.array(losses)
+    out["after.weight_sub"] = mod.linear[1].weight.detach().numpy()[::16].copy()
+    out["after.bias"] = mod.linear[1].bias.detach().numpy().copy()
+    with torch.no_grad():
+        out["pred"] = mod(x).numpy().copy()
+    path = os.path.join(GOLD, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path) // 1024, "KB", losses)
 
 
 def gen_chaos_envelope(seed=1234, nr_epochs=50, batch_size=10):
@@ -286,6 +400,13 @@ def gen_chaos_envelope(seed=1234, nr_epochs=50, batch_size=10):
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        # fixtures added in round 2 (the round-1 files are reproduced bit for bit by the full run below)
+        gen_unet_curve()
+        gen_unet("head32_mask_light", with_mask=True, batch=4, latent=4, fc=16, spec_dict=unet_spec_with_head(32), light=8)
+        gen_unet("head16_mask", with_mask=True, batch=3, spec_dict=unet_spec_with_head(16))
+        gen_linear()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "unet_head":
         # the fused kernel == stride head (patch_head.cu): k16 -> 128x128 output, masked, batch 3
         gen_unet("head16_mask", with_mask=True, batch=3, spec_dict=unet_spec_with_head(16))
@@ -300,3 +421,6 @@ if __name__ == "__main__":
     gen_unet("nomask", with_mask=False)
     gen_unet("mask", with_mask=True)
     gen_unet("head16_mask", with_mask=True, batch=3, spec_dict=unet_spec_with_head(16))
+    gen_unet_curve()
+    gen_unet("head32_mask_light", with_mask=True, batch=4, latent=4, fc=16, spec_dict=unet_spec_with_head(32), light=8)
+    gen_linear()

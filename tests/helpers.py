@@ -39,3 +39,17 @@ def pre_bn_bias_keys(sd_keys, prefix):
             if f"{k.split('.')[0]}.{idx + 1}.running_mean" in sd_keys:
                 out.append(k)
     return out
+
+
+def unet_light_data(g):
+    """x, y, mask of a `light` unet fixture: y / mask are regenerated from the recorded seed with torch's CPU generator
+    (platform-independent) exactly as oracle/gen_golden.py:gen_unet drew them"""
+    spec = spec_of(g)
+    oh, ow = spec["output_layers"][-1]["output_dimensions"][1:]
+    batch = int(g["batch"])
+    gen = torch.Generator().manual_seed(int(g["data_seed"]))
+    x = torch.rand(batch, 1, 16, 16, generator=gen)
+    y = torch.rand(batch, 1, oh, ow, generator=gen)
+    mask = (torch.rand(batch, 1, oh, ow, generator=gen) > 0.3).float() if int(g["with_mask"]) else torch.ones(batch, 1, oh, ow)
+    assert np.array_equal(x.numpy(), g["x"]), "the generator no longer reproduces the recorded inputs"
+    return x, y, mask

@@ -74,3 +74,24 @@ def test_linear_model_api_and_cli(tmp_path):
     out = str(tmp_path / "scores.nc")
     apply_cae.main([paths["test"], out, "--model-folder", cli_folder, "--prediction-variable", "est"])
     assert xr_lite.open_dataset(out)["est"].shape == (12, 1, 32, 32)
+
+
+def test_linear_engine_vs_reference_fixture():
+    """the CUDA LinearEngine against values the reference's Linear module + MSELoss + Adam produced (linear_mini.npz)"""
+    from helpers import load_npz
+    from cae_tools_b200.engine.linear import LinearEngine
+    from cae_tools_b200.models.linear import Linear
+    g = load_npz("linear_mini.npz")
+    torch.manual_seed(int(g["seed"]))
+    mod = Linear((1, 16, 16), (1, 64, 64))
+    assert np.array_equal(mod.linear[1].weight.detach().numpy()[::16], g["init.weight_sub"])
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    eng = LinearEngine(mod, lr=1e-3, weight_decay=1e-5)
+    data = eng.bind(x, y, 8)
+    losses = [float(eng.train_epoch(data).cpu()[0]) for _ in range(3)]
+    np.testing.assert_allclose(losses, g["losses"], rtol=2e-5)
+    assert rel_err(mod.linear[1].weight.detach().cpu().numpy()[::16], g["after.weight_sub"]) < 1e-4
+    assert rel_err(mod.linear[1].bias.detach().cpu().numpy(), g["after.bias"]) < 1e-4
+    out = []
+    eng.score_batches(eng.bind(x, None, 8), lambda i, yh: out.append(yh.cpu().numpy().copy()))
+    assert rel_err(np.concatenate(out), g["pred"]) < 1e-4

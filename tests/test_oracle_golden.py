@@ -198,3 +198,83 @@ def test_numpy_linear_and_adamw_match_torch():
     x, w, b = rng.randn(5, 7), rng.randn(4, 7), rng.randn(4)
     ref = torch.nn.functional.linear(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b)).numpy()
     np.testing.assert_allclose(npo.linear(x, w, b), ref, atol=1e-12)
+
+
+def test_unet_port_matches_reference_k32_fixture():
+    """the shipped 16x16 -> 256x256 spec (k32 s32 head) at reference-produced values: losses of 3 AdamW steps, gradients of
+    step 0, eval prediction at the initial and the trained weights (fixture stores the 256x256 tensors subsampled by 8)"""
+    from helpers import unet_light_data
+    from oracle.torch_port import OracleUNet
+    g = load_npz("unet_head32_mask_light.npz")
+    spec, L = spec_of(g), int(g["light"])
+    x, y, mask = unet_light_data(g)
+    m = OracleUNet(split_sd(g, "init.enc."), split_sd(g, "init.dec."), spec, lambda_pearson=1.0)
+    assert rel_err(m.score(x).numpy()[:, :, ::L, ::L], g["eval_yhat_init"]) < 1e-5
+    mses, pls = [], []
+    for step in range(3):
+        a, b = m.train_step(x, y, mask)
+        mses.append(a)
+        pls.append(b)
+        if step == 0:
+            for prefix, sd in (("enc.", m.enc), ("dec.", m.dec)):
+                for k, v in sd.items():
+                    gk = "grad." + prefix + k
+                    if gk in g:
+                        scale = max(np.abs(g[gk]).max(), 1e-7)
+                        assert np.abs(v.grad.numpy() - g[gk]).max() <= 2e-4 * scale + 1e-9, gk
+    np.testing.assert_allclose(mses, g["mse"], rtol=1e-5)
+    np.testing.assert_allclose(pls, g["pearson_loss"], rtol=1e-5)
+    assert rel_err(m.score(x).numpy()[:, :, ::L, ::L], g["eval_yhat"]) < 2e-4
+
+
+def test_unet_port_reproduces_reference_50_epoch_curve():
+    """BASELINE configs[1]: the port's loop against the reference's UNET training loop on the circle data, batch 64 (64 + 36),
+    50 epochs (fixture curve_unet_b64_e50.npz; init = same seed and module tree, shuffles = same RNG stream)"""
+    import json
+    import os
+    from cae_tools_b200.models.model_sizer import ModelSpec
+    from cae_tools_b200.models.unet_modules import UNetDecoder, UNetEncoder
+    from oracle.torch_port import OracleUNet
+    g = load_npz("curve_unet_b64_e50.npz")
+    spec_json = spec_of(g)
+    spec = ModelSpec()
+    spec.load(spec_json)
+    tr, te = datagen.circle_datasets(100, 100)
+    lo_min, lo_max = float(tr["lowres"].data.min()), float(tr["lowres"].data.max())
+    hi_min, hi_max = float(tr["hires"].data.min()), float(tr["hires"].data.max())
+    norm = lambda a, lo, hi: ((a - lo) / (hi - lo)).astype(np.float32)
+    torch.manual_seed(1234)
+    enc, dec = UNetEncoder(spec.get_input_layers(), 4, 16, 0.0), UNetDecoder(spec.get_output_layers(), 4, 16, 0.0)
+    otr, ote = shuffled_order(100, 64), shuffled_order(100, 64)
+    m = OracleUNet(enc.state_dict(), dec.state_dict(), spec_json, lambda_pearson=1.0)
+    btr = make_batches(norm(tr["lowres"].data, lo_min, lo_max), norm(tr["hires"].data, hi_min, hi_max), otr, 64)
+    bte = make_batches(norm(te["lowres"].data, lo_min, lo_max), norm(te["hires"].data, hi_min, hi_max), ote, 64)
+    tl, el = [], []
+    for epoch in range(12):                    # 12 of the 50 epochs keep the CPU suite short
+        tl.append(float(np.mean([m.train_step(x, y, torch.ones_like(y))[0] for x, y in btr])))
+        with torch.no_grad():
+            el.append(float(np.mean([float(m.losses(x, y, torch.ones_like(y), False)[0]) for x, y in bte])))
+    np.testing.assert_allclose(tl, g["train_loss"][:12], rtol=2e-5)
+    np.testing.assert_allclose(el, g["test_loss"][:12], rtol=2e-5)
+
+
+def test_linear_port_matches_reference():
+    """oracle/torch_port.OracleLinear pinned to the reference's Linear module + MSELoss + Adam (fixture linear_mini.npz)"""
+    from cae_tools_b200.models.linear import Linear
+    from oracle.torch_port import OracleLinear
+    g = load_npz("linear_mini.npz")
+    torch.manual_seed(int(g["seed"]))
+    mod = Linear((1, 16, 16), (1, 64, 64))
+    assert np.array_equal(mod.linear[1].weight.detach().numpy()[::16], g["init.weight_sub"])     # same init stream
+    assert np.array_equal(mod.linear[1].bias.detach().numpy(), g["init.bias"])
+    m = OracleLinear(mod.state_dict(), (1, 64, 64), lr=1e-3, weight_decay=1e-5)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    losses = []
+    for step in range(3):
+        losses.append(m.train_step(x, y))
+        if step == 0:
+            assert rel_err(m.w.grad.numpy()[::16], g["grad.weight_sub"]) < 1e-5
+            assert rel_err(m.b.grad.numpy(), g["grad.bias"]) < 1e-5
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-6)
+    assert rel_err(m.w.detach().numpy()[::16], g["after.weight_sub"]) < 1e-5
+    assert rel_err(m.score(x).numpy(), g["pred"]) < 1e-5

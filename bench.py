@@ -334,17 +334,21 @@ def run_b200(args):
     spec, enc, dec = build_modules(method)          # identical initial weights on every rank (seed 0)
     hook = (lambda g: dist.all_reduce(g)) if world > 1 else None
     hook_async = (lambda g: dist.all_reduce(g, async_op=True)) if world > 1 else None
+    dpc = None
+    if world > 1:
+        from cae_tools_b200.engine.dp import DPContext
+        dpc = DPContext()          # small arenas: all-reduce fused into the optimiser launch (csrc/dp_fused.cu)
     if method == "unet":
         from cae_tools_b200.engine.unet import UNetEngine
         eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5, device=dev,
-                         grad_hook=hook, grad_hook_async=hook_async, grad_scale=1.0 / world)
+                         grad_hook=hook, grad_hook_async=hook_async, grad_scale=1.0 / world, dp=dpc)
     elif method == "var":
         from cae_tools_b200.engine.varae import VarAEEngine
         eng = VarAEEngine(enc, dec, lambda_mse=1.0, lambda_kl=1.0, lr=1e-3, weight_decay=1e-5, device=dev,
-                          grad_hook=hook, grad_scale=1.0 / world)
+                          grad_hook=hook, grad_scale=1.0 / world, dp=dpc)
     else:
         eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=dev, grad_hook=hook, grad_hook_async=hook_async,
-                           grad_scale=1.0 / world)
+                           grad_scale=1.0 / world, dp=dpc)
 
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     NB = args.n_batches
@@ -561,9 +565,12 @@ def run_b200(args):
         for _ in range(5):
             dist.all_reduce(g)
         ms_ar = timed(lambda: dist.all_reduce(g), 50)
-        comm = {"allreduce_us": ms_ar / 50 * 1e3, "arena_bytes": g.numel() * 4,
-                "in_step_graph": bool(getattr(eng, "capture_allreduce", False)),
-                "note": "one NCCL all-reduce of the flat fp32 gradient arena per optimiser step"}
+        fused = getattr(eng, "_dp_peers", None) is not None
+        comm = {"nccl_allreduce_us": ms_ar / 50 * 1e3, "arena_bytes": g.numel() * 4, "fused_into_optimiser": fused,
+                "in_step_graph": fused or bool(getattr(eng, "capture_allreduce", False)),
+                "note": ("the gradient all-reduce runs inside the optimiser launch (peer reads over NVLink, cae_adam_allreduce); "
+                         "nccl_allreduce_us is what a standalone NCCL all-reduce of the same arena costs") if fused else
+                        "one NCCL all-reduce of the flat fp32 gradient arena per optimiser step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -122,6 +122,10 @@ class CaeStemTrain(C.Structure):
                 ("seed", C.c_ulonglong), ("step_count", C.c_void_p), ("bnpart", C.c_void_p), ("wpart", C.c_void_p)]
 
 
+class CaeDpPeers(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("grads", C.c_void_p * 8), ("flags", C.c_void_p * 8)]
+
+
 class CaeTcConv(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("Cin", "Cout", "kh", "kw", "stride", "N", "Hin", "Win", "Hout", "Wout")] + \
                [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_longlong), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
@@ -210,6 +214,10 @@ EXPORTS = {
     "cae_minmax": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cae_normalise_gather": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int,
                                        C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cae_dp_wait_done": (C.c_int, [C.POINTER(CaeDpPeers), C.c_void_p, C.c_void_p]),
+    "cae_adam_allreduce": (C.c_int, [C.c_void_p, C.POINTER(CaeDpPeers), C.c_void_p, C.c_void_p, C.c_longlong, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cae_randn": (C.c_int, [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p]),
 }
 

@@ -17,6 +17,7 @@ extern "C" long long cae_struct_size(int which) {
         case 9: return sizeof(CaeTcGemm);
         case 10: return sizeof(CaeTcConv);
         case 11: return sizeof(CaeStemTrain);
+        case 12: return sizeof(CaeDpPeers);
         default: return -1;
     }
 }

@@ -80,8 +80,13 @@ class ConvAEEngine:
     # dependent launch costs only ~1 us inside a graph, while a single CTA pays every phase's latency serially.
     use_fused_fc = False
 
+    # data parallel, small arenas: the gradient all-reduce runs INSIDE the optimiser launch (peer reads over NVLink,
+    # csrc/dp_fused.cu) instead of an NCCL call between the backward pass and Adam; larger arenas keep NCCL
+    DP_FUSED_MAX_BYTES = 1 << 20
+
     def __init__(self, encoder, decoder, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, decoupled=False,
-                 device="cuda", use_graphs=True, grad_hook=None, grad_scale=1.0, count_scale=1.0, grad_hook_async=None):
+                 device="cuda", use_graphs=True, grad_hook=None, grad_scale=1.0, count_scale=1.0, grad_hook_async=None,
+                 dp=None):
         require_cuda()
         self.device = torch.device(device)
         self.encoder = encoder.to(self.device)
@@ -96,6 +101,8 @@ class ConvAEEngine:
         self.count_scale = count_scale  # n_local / n_global when a batch is sharded over data-parallel ranks
         self.mse_weight = 1.0           # weight of the MSE term in the reported loss / gradient (VarAE: lambda_mse)
         self._keep = []                 # descriptors' tensors must outlive the graphs
+        self.dp = dp                    # engine/dp.py:DPContext (enables the fused exchange when the arena is small)
+        self._dp_peers = None
         self._build_arena()
         self.enc_layers = self.encoder.conv_layers()
         self.dec_layers = self.decoder.conv_layers()
@@ -120,7 +127,16 @@ class ConvAEEngine:
             total += _align(p.numel())
         dev = self.device
         self.arena = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads = None
+        if self.dp is not None and total * 4 <= self.DP_FUSED_MAX_BYTES:
+            sym = self.dp.symmetric_arena(total)
+            if sym is not None:
+                self.grads, self._dp_peers, keep = sym
+                self._keep.append(keep)
+                self._dp_epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+                self.grad_hook = self.grad_hook_async = None        # the exchange happens inside the optimiser launch
+        if self.grads is None:
+            self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
         self.adam_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.adam_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self._gview = {}
@@ -440,6 +456,13 @@ class ConvAEEngine:
         out = []
         if self.grad_hook is not None:
             out.append(("grad_allreduce", lambda: self.grad_hook(self.grads)))
+        if self._dp_peers is not None:
+            # gradient all-reduce (peer reads over NVLink) + optimiser + bookkeeping in one launch
+            out.append(("adam+allreduce", lambda t=self._ticket(): ops.adam_allreduce(
+                self.arena, self._dp_peers, self.adam_m, self.adam_v, self.n_params, self.lr, self.betas[0], self.betas[1],
+                self.eps, self.weight_decay, self.decoupled, self.grad_scale, self.step_count, data.cursor, data.n_batches,
+                self._dp_epoch, t)))
+            return out
         # optimiser + bookkeeping (step counter, batch cursor) in one launch
         out.append(("adam", lambda t=self._ticket(): ops.adam_advance(
             self.arena, self.grads, self.adam_m, self.adam_v, self.n_params, self.lr, self.betas[0], self.betas[1], self.eps,
@@ -473,6 +496,10 @@ class ConvAEEngine:
         if kind == "train":
             sched = self._forward_ops(b, N, data, True, "loss_grad") + self._backward_ops(b, N, data) + \
                 self._update_ops(data)
+            if self._dp_peers is not None:
+                # fused exchange: before anything of this step can overwrite a gradient, every peer must have finished
+                # reading the previous step's (flags published by its cae_adam_allreduce ~one forward pass ago: a free wait)
+                sched = [("dp.wait_peers", lambda: ops.dp_wait_done(self._dp_peers, self._dp_epoch))] + sched
         elif kind == "test":
             sched = self._forward_ops(b, N, data, False, "loss") + \
                 [("advance", lambda: ops.step_advance(None, data.cursor, data.n_batches))]
@@ -774,7 +801,7 @@ class _Program:
     # weight-gradient kernels only feed the optimiser: inside the captured graph they run on side streams,
     # concurrently with the input-gradient chain (most launches of this network fill a fraction of the GPU)
     SIDE_SUFFIXES = (".wgrad", ".dW")
-    JOIN_BEFORE = ("adam", "grad_allreduce")
+    JOIN_BEFORE = ("adam", "adam+allreduce", "grad_allreduce")
     N_SIDE = int(os.environ.get("CAE_SIDE_STREAMS", "3"))     # 0: everything on one stream
 
     def run_forked(self):

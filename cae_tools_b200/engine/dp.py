@@ -70,6 +70,43 @@ class DPContext:
         computing (the encoder backward) and calls .wait() on the handle before the optimiser"""
         return dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
+    def symmetric_arena(self, numel):
+        """A gradient arena every rank can read directly over NVLink (torch symmetric memory: a CUDA VMM allocation whose
+        handles are exchanged once, `buffer_ptrs[r]` = rank r's copy mapped into this process) + a flag array for the
+        in-kernel handshake of cae_adam_allreduce.  Returns (grads, peers descriptor, keep-alive) or None when symmetric
+        memory is unavailable (every rank then falls back to the NCCL all-reduce: the decision is taken collectively)."""
+        import os
+        ok = torch.tensor([1], dtype=torch.int32, device="cuda")
+        res = None
+        try:
+            if os.environ.get("CAE_DP_FUSED", "1") == "0" or dist.get_backend(self.group) != "nccl" or self.world > 8:
+                raise RuntimeError("fused exchange disabled / unsupported")
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self.group if self.group is not None else dist.group.WORLD
+            enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
+            if enable is not None:
+                try:
+                    enable(grp.group_name)
+                except Exception:
+                    pass
+            grads = symm_mem.empty(int(numel), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+            flags = symm_mem.empty(64, dtype=torch.int32, device=grads.device)
+            grads.zero_()
+            flags.zero_()
+            hg = symm_mem.rendezvous(grads, grp)
+            hf = symm_mem.rendezvous(flags, grp)
+            torch.cuda.synchronize()
+            from . import ops
+            peers = ops.make_dp_peers(self.world, self.rank, list(hg.buffer_ptrs), list(hf.buffer_ptrs))
+            res = (grads, peers, (flags, hg, hf))
+        except Exception as exc:  # noqa: BLE001 - any failure means "use NCCL"
+            ok.zero_()
+            self._symm_error = repr(exc)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none; also orders the flag zeroing
+        if int(ok.item()) == 0:
+            return None
+        return res
+
     def reduce_losses(self, losses):
         """per-batch losses were divided by the global count on every rank: SUM gives the global batch MSE"""
         out = losses.clone()

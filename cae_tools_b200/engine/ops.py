@@ -10,7 +10,7 @@ import ctypes as C
 
 import torch
 
-from .._lib import (CaeStemTrain, CaeStemTrainConv, CaeStemTrainFc, CaeStemTrainUp, CaeTcConv, CaeTcGemm, CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
+from .._lib import (CaeDpPeers, CaeStemTrain, CaeStemTrainConv, CaeStemTrainFc, CaeStemTrainUp, CaeTcConv, CaeTcGemm, CaeBN, CaeConvGeom, CaeEpilogue, CaeFcStack, CaeGemm, CaePatchHead, CaeSrc, CaeStemConv, CaeStemFc, CaeStemUp,
                     CaeUnetStem, CaeView, STEM_MAX, EPI_MASK, EPI_MASKSTATS, EPI_PLAIN,
                     EPI_SIGMOID, EPI_SIGMOID_MSE, EPI_STATS, check, lib)
 
@@ -550,3 +550,24 @@ def normalise_gather(src, order, lo, hi, normalise, dst, chan_offset=0):
     check(lib().cae_normalise_gather(_ptr(src), int(elems), _ptr(order), int(dst.shape[0]), float(lo), float(hi),
                                      int(bool(normalise)), dst.data_ptr() + 4 * off, int(dst[0].numel()), _stream()),
           "cae_normalise_gather")
+
+
+# ---- data-parallel exchange fused into the optimiser ------------------------------------------------------------------------
+def make_dp_peers(world, rank, grad_ptrs, flag_ptrs) -> CaeDpPeers:
+    p = CaeDpPeers()
+    p.world, p.rank = int(world), int(rank)
+    for r in range(world):
+        p.grads[r] = int(grad_ptrs[r])
+        p.flags[r] = int(flag_ptrs[r])
+    return p
+
+
+def adam_allreduce(p, peers: CaeDpPeers, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, grad_scale, step_count, cursor,
+                   n_batches, epoch, ticket):
+    check(lib().cae_adam_allreduce(_ptr(p), C.byref(peers), _ptr(m), _ptr(v), int(n), float(lr), float(beta1), float(beta2),
+                                   float(eps), float(weight_decay), int(bool(decoupled)), float(grad_scale), _ptr(step_count),
+                                   _ptr(cursor), int(n_batches), _ptr(epoch), _ptr(ticket), _stream()), "cae_adam_allreduce")
+
+
+def dp_wait_done(peers: CaeDpPeers, epoch):
+    check(lib().cae_dp_wait_done(C.byref(peers), _ptr(epoch), _stream()), "cae_dp_wait_done")

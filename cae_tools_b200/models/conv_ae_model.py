@@ -171,7 +171,7 @@ class ConvAEModel(BaseModel):
             return ConvAEEngine(self.encoder, self.decoder, lr=self.lr, weight_decay=self.weight_decay, device=device)
         return ConvAEEngine(self.encoder, self.decoder, lr=self.lr, weight_decay=self.weight_decay, device=device,
                             grad_hook=dp.allreduce_grads, grad_hook_async=dp.allreduce_grads_async,
-                      count_scale=1.0 / dp.world)
+                            count_scale=1.0 / dp.world, dp=dp)
 
     def _ensure_engine(self):
         if self.engine is None:

@@ -74,7 +74,7 @@ class UNET(ConvAEModel):
         seed = torch.initial_seed()
         if dp is not None:
             kw.update(grad_hook=dp.allreduce_grads, grad_hook_async=dp.allreduce_grads_async,
-                      count_scale=1.0 / dp.world)
+                      count_scale=1.0 / dp.world, dp=dp)
             seed ^= (dp.rank + 1) * 0x9E3779B97F4A7C15           # independent dropout masks on every rank's shard
         return UNetEngine(self.encoder, self.decoder, lambda_pearson=self.lambda_pearson,
                           dropout_rate=self.dropout_rate, seed=seed & 0xFFFFFFFFFFFFFFFF, **kw)

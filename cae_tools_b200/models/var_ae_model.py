@@ -48,7 +48,7 @@ class VarAEModel(ConvAEModel):
         seed = self.seed
         if dp is not None:
             kw.update(grad_hook=dp.allreduce_grads, count_scale=1.0 / dp.world,
-                      grad_hook_async=dp.allreduce_grads_async)
+                      grad_hook_async=dp.allreduce_grads_async, dp=dp)
             # every rank holds a different shard: its reparameterisation noise must be independent too
             seed = (seed ^ ((dp.rank + 1) * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
         return VarAEEngine(self.encoder, self.decoder, lambda_mse=self.lambda_mse, lambda_kl=self.lambda_kl,

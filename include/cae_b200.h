@@ -479,6 +479,24 @@ int cae_minmax(const float* x, long long n, float* partials, unsigned int* ticke
 int cae_normalise_gather(const float* src, long long sample_elems, const int* order, int n_out, float lo, float hi,
                          int normalise, float* dst, long long dst_sample_stride, void* stream);
 
+/* ---- data-parallel exchange fused into the optimiser (dp_fused.cu) -------------------------------------------------------
+ * One launch per rank: all-reduce of the flat gradient arena by peer reads over NVLink (summed in rank order: identical
+ * bits everywhere) + Adam / AdamW + step bookkeeping.  Replaces NCCL all-reduce + cae_adam_advance for small arenas (the
+ * exchange the reference does not have: SURVEY 2.3, 8e).  grads[r] / flags[r]: rank r's gradient arena / flag array
+ * (>= 16 uint32, zeroed once) as mapped into THIS process (e.g. torch symmetric memory buffer_ptrs); epoch: a private,
+ * zero-initialised device counter of this rank; every rank must call it the same number of times. */
+typedef struct CaeDpPeers {
+    int world, rank;
+    const float* grads[8];
+    unsigned int* flags[8];
+} CaeDpPeers;
+/* first launch of every step: returns (on the stream) once every peer has read this rank's gradients of the previous
+ * cae_adam_allreduce - the backward pass may then overwrite them */
+int cae_dp_wait_done(const CaeDpPeers* peers, const unsigned int* epoch, void* stream);
+int cae_adam_allreduce(float* p, const CaeDpPeers* peers, float* m, float* v, long long n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int decoupled, float grad_scale, int* step_count,
+                       int* cursor, int n_batches, unsigned int* epoch, unsigned int* ticket, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

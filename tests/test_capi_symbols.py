@@ -43,7 +43,7 @@ def test_struct_sizes_match_c_layout():
     # ... and every mirror has exactly the size the compiled library sees
     lib = _lib.lib()
     for which, cls in enumerate([_lib.CaeView, _lib.CaeSrc, _lib.CaeConvGeom, _lib.CaeBN, _lib.CaeEpilogue, _lib.CaeGemm,
-                                 _lib.CaePatchHead, _lib.CaeFcStack, _lib.CaeUnetStem, _lib.CaeTcGemm, _lib.CaeTcConv, _lib.CaeStemTrain]):
+                                 _lib.CaePatchHead, _lib.CaeFcStack, _lib.CaeUnetStem, _lib.CaeTcGemm, _lib.CaeTcConv, _lib.CaeStemTrain, _lib.CaeDpPeers]):
         assert lib.cae_struct_size(which) == ctypes.sizeof(cls), cls.__name__
     assert lib.cae_struct_size(99) == -1
 

@@ -33,7 +33,7 @@ def _data():
     return torch.rand(8, 1, 16, 16, generator=g), torch.rand(8, 1, 64, 64, generator=g)
 
 
-def _worker(rank, world, port, out_dir, overlap):
+def _worker(rank, world, port, out_dir, overlap, fused=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -44,7 +44,8 @@ def _worker(rank, world, port, out_dir, overlap):
     enc, dec = _models()
     x, y = _data()
     eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5, device=torch.device("cuda", rank),
-                       grad_hook=dp.allreduce_grads, grad_hook_async=dp.allreduce_grads_async, count_scale=1.0 / world)
+                       grad_hook=dp.allreduce_grads, grad_hook_async=dp.allreduce_grads_async, count_scale=1.0 / world,
+                       dp=dp if fused else None)
     eng.overlap_allreduce = overlap          # two buckets, the first one reduced while the encoder backward runs
     data = eng.bind(x, y, 8)
     losses = []
@@ -57,12 +58,15 @@ def _worker(rank, world, port, out_dir, overlap):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("overlap", [False, True, "fused"])
 def test_two_rank_nccl_equals_single_gpu(tmp_path, overlap):
+    """overlap False / True: NCCL all-reduce (one call / two overlapped buckets); "fused": the all-reduce inside the optimiser
+    launch over peer memory (csrc/dp_fused.cu)"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), overlap), nprocs=2, join=True)
+    fused = overlap == "fused"
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), overlap is True, fused), nprocs=2, join=True)
     got = dict(np.load(os.path.join(str(tmp_path), "dp.npz")))
     from cae_tools_b200.engine.convae import ConvAEEngine
     enc, dec = _models()
@@ -106,11 +110,13 @@ def _unet_worker(rank, world, port, out_dir):
     enc, dec = _unet_models()
     x, y = _unet_data()
     eng = UNetEngine(enc, dec, lambda_pearson=1.0, dropout_rate=0.0, lr=1e-3, weight_decay=1e-5, device=torch.device("cuda", rank),
-                     grad_hook=dp.allreduce_grads, count_scale=1.0 / world)
+                     grad_hook=dp.allreduce_grads, count_scale=1.0 / world, dp=dp)
     data = eng.bind(x, y, 6)
     losses = [float(dp.reduce_losses(eng.train_epoch(data)).cpu()[0]) for _ in range(3)]
     assert eng._train_stem(6) is not None
+    fused = eng._dp_peers is not None
     if rank == 0:
+        print("fused exchange:", fused, getattr(dp, "_symm_error", ""), flush=True)
         sd = {k: v.detach().cpu().numpy() for k, v in list(enc.state_dict().items()) + list(dec.state_dict().items())}
         np.savez(os.path.join(out_dir, "dpu.npz"), losses=np.array(losses), **{k.replace(".", "_"): v for k, v in sd.items()})
     torch.cuda.synchronize()

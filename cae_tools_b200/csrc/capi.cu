@@ -141,7 +141,7 @@ static int fill_conv_args(ConvArgs& a, const CaeSrc* in, const float* weight, co
 // =====================================================================================================
 static int default_mask() {
     const char* e = getenv("CAE_KERNEL_MASK");
-    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A | CAE_V3_DIRECT);
+    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A | CAE_V3_DIRECT | CAE_WGRAD_TILE);
 }
 int g_cae_mask = default_mask();
 extern "C" void cae_set_kernel_generation(int gen) { g_mask = (gen <= 1) ? 0 : (gen == 2 ? default_mask() : (gen >> 4)); }

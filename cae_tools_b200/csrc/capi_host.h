@@ -30,6 +30,9 @@ static const int kTileSmemMax = 100 * 1024;
 // than the tiled kernels (33 -> 14 us), but its 1000+ CTAs take the SMs away from the input-gradient chain that runs
 // beside it on the main stream - the whole step got slower (unet 341 -> 350 us, conv 492 -> 528 us).
 #define CAE_WGRAD_SMALL 32
+// tile-resident weight gradient of the wide thin layers (k_wgrad_tile): both operands are fetched once per CTA tile
+// instead of once per channel-tile pair
+#define CAE_WGRAD_TILE 64
 extern int g_cae_mask;                 // defined in capi.cu
 #define g_mask g_cae_mask
 #define g_use_v2 (g_mask & CAE_V2_UPDOWN)

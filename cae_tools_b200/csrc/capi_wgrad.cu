@@ -3,6 +3,7 @@
 #include "conv_family.cuh"
 #include "conv_tiled.cuh"
 #include "conv_direct.cuh"
+#include "conv_wgrad_tile.cuh"
 
 // ---- weight gradient -------------------------------------------------------------------
 #define CAE_WGRAD_MAX_CHUNKS 1024
@@ -42,7 +43,8 @@ static WgradPlan plan_wgrad(int Cs, int Cb, int kh, int kw, int s, int total) {
 
 // ---- v2 weight-gradient planning ----------------------------------------------------------------
 struct Wg2Choice {
-    int kind;          // 0: v1, 1: v2a (position parallel), 2: v2b (GEMM-like)
+    int kind;          // 0: v1, 1: v2a (position parallel), 2: v2b (GEMM-like), 3: v3 direct, 4: tile resident
+    WgTilePlan t;
     int cst, cbt, cx;
     Wg2Plan a;
     WgGemmPlan b;
@@ -53,10 +55,11 @@ struct Wg2Choice {
     int tiles_b;
 };
 
-static Wg2Choice plan_wgrad2(int N, int Cs, int Hs, int Ws, int Cb, int kh, int kw, int s, bool direct = false) {
+static Wg2Choice plan_wgrad2(int N, int Cs, int Hs, int Ws, int Cb, int kh, int kw, int s, bool direct = false,
+                             bool s_t1 = false, bool b_t1 = false) {
     Wg2Choice w{};
     w.kind = 0;
-    if (!(g_mask & (CAE_V2_WGRAD_A | CAE_V2_WGRAD_B | CAE_V3_DIRECT)) || s != 2 || kh != kw || (kh != 3 && kh != 4)) return w;
+    if (!(g_mask & (CAE_V2_WGRAD_A | CAE_V2_WGRAD_B | CAE_V3_DIRECT | CAE_WGRAD_TILE)) || s != 2 || kh != kw || (kh != 3 && kh != 4)) return w;
     const int KK = kh * kw;
     const long long nelem = (long long)Cs * Cb * KK;
     int cst = Cs >= 4 ? 4 : (Cs >= 2 ? 2 : 1);
@@ -66,6 +69,39 @@ static Wg2Choice plan_wgrad2(int N, int Cs, int Hs, int Ws, int Cb, int kh, int 
     if (cst == 1 && cbt == 2) cbt = 1;                      // instantiated: (4,2) (2,2) (2,1) (1,1)
     const int tiles_b = (Cb + cbt - 1) / cbt;
     const int G = ((Cs + cst - 1) / cst) * tiles_b;
+    if (direct && (g_mask & CAE_WGRAD_TILE) && Ws >= 64 && (long long)N * Hs * Ws >= (1ll << 20) && Cs % 4 == 0 && Cb % 4 == 0 &&
+        Cs <= 64 && Cb <= 32) {
+        // register tile (4,2) for 3x3, (2,2) for 4x4; 256 threads = n_cst * n_cbt tiles x PS position lanes (PS >= 4)
+        const int tcs = kh == 3 ? 4 : 2;
+        const int pt = (Cs / tcs) * (Cb / 2);
+        if (pt >= 1 && pt <= 64 && 256 % pt == 0) {
+            WgTilePlan t{};
+            t.CsP = Cs + 4; t.CbP = Cb + 2;
+            t.n_cst = Cs / tcs; t.n_cbt = Cb / 2;
+            t.PSH = 256 / pt / 4;
+            t.BC = 2 * WGT_TW + kh - 2;
+            for (int th = 8; th >= 2; th >>= 1) {
+                t.TH = th; t.BR = 2 * th + kh - 2;
+                t.TH_shift = ilog2(th); t.inv_BR = (65536 + t.BR - 1) / t.BR;
+                t.SCH = th * WGT_TW + 8;
+                t.BCH = t.BR * WGT_BCR + ((8 - (t.BR * WGT_BCR) % 32) + 32) % 32;
+                t.raw_s = Cs * t.SCH; t.raw_b = Cb * t.BCH;
+                t.cooked = (s_t1 ? 2 : 1) * t.raw_s + (b_t1 ? 2 : 1) * t.raw_b;
+                size_t fl = (size_t)t.cooked + (size_t)th * WGT_TW * t.CsP + (size_t)t.BR * t.BC * t.CbP;
+                size_t red = (size_t)64 * tcs * 2 * KK;
+                if (fl < red) fl = red;
+                if (fl * 4 <= (size_t)kTileSmemMax && (th * WGT_TW) % (4 * t.PSH) == 0) {
+                    t.tiles_y = (Hs + th - 1) / th; t.tiles_x = (Ws + WGT_TW - 1) / WGT_TW;
+                    t.ntiles = N * t.tiles_y * t.tiles_x;
+                    w.kind = 4; w.cst = tcs; w.cbt = 2; w.t = t; w.smem = fl * 4;
+                    w.grid_x = t.ntiles < 2 * CAE_NUM_SMS ? t.ntiles : 2 * CAE_NUM_SMS;
+                    w.grid_y = 1;
+                    w.partials = (long long)w.grid_x * nelem;
+                    return w;
+                }
+            }
+        }
+    }
     if (direct && Ws >= 24 && G <= 16 && (g_mask & CAE_V3_DIRECT)) {
         w.kind = 3; w.cst = cst; w.cbt = cbt;
         w.strip.RP = Hs; w.strip.NS = (Ws + 3) / 4; w.strip.units = N * Hs * w.strip.NS;
@@ -159,7 +195,8 @@ extern "C" long long cae_wgrad_partials_len(const CaeSrc* sm, const CaeSrc* bg, 
     WgradPlan p = plan_wgrad(sm->t0.C, bg->t0.C, g->kh, g->kw, g->stride, sm->t0.N * sm->t0.H * sm->t0.W);
     long long v1 = (long long)p.nchunks * sm->t0.C * bg->t0.C * g->kh * g->kw;
     Wg2Choice w = plan_wgrad2(sm->t0.N, sm->t0.C, sm->t0.H, sm->t0.W, bg->t0.C, g->kh, g->kw, g->stride);
-    Wg2Choice w3 = plan_wgrad2(sm->t0.N, sm->t0.C, sm->t0.H, sm->t0.W, bg->t0.C, g->kh, g->kw, g->stride, true);
+    Wg2Choice w3 = plan_wgrad2(sm->t0.N, sm->t0.C, sm->t0.H, sm->t0.W, bg->t0.C, g->kh, g->kw, g->stride, true, sm->t1 != nullptr,
+                               bg->t1 != nullptr);
     long long need = v1;
     if (w.kind != 0 && w.partials > need) need = w.partials;
     if (w3.kind != 0 && w3.partials > need) need = w3.partials;
@@ -202,7 +239,17 @@ extern "C" int cae_conv_wgrad(const CaeSrc* sm, const CaeSrc* bg, const CaeConvG
         }
     }
     const bool direct = g->pad == 0 && src_aligned(*sm) && src_aligned(*bg);
-    Wg2Choice w2 = plan_wgrad2(sm->t0.N, a.Cs, sm->t0.H, sm->t0.W, a.Cb, a.kh, a.kw, a.s, direct);
+    Wg2Choice w2 = plan_wgrad2(sm->t0.N, a.Cs, sm->t0.H, sm->t0.W, a.Cb, a.kh, a.kw, a.s, direct, sm->t1 != nullptr, bg->t1 != nullptr);
+    if (w2.kind == 4) {
+        if (a.kh == 3) {
+            ensure_smem(k_wgrad_tile<3, 4, 2>);
+            k_wgrad_tile<3, 4, 2><<<w2.grid_x, CAE_NT, w2.smem, st>>>(a, w2.t);
+        } else {
+            ensure_smem(k_wgrad_tile<4, 2, 2>);
+            k_wgrad_tile<4, 2, 2><<<w2.grid_x, CAE_NT, w2.smem, st>>>(a, w2.t);
+        }
+        return cae_check_launch("cae_conv_wgrad(tile)");
+    }
     if (w2.kind == 3) {
         dim3 grid(w2.grid_x, w2.grid_y);
 #define CAE_WG3(KK_, S_, B_) k_wgrad3<KK_, S_, B_><<<grid, CAE_NT, 0, st>>>(a, w2.strip, w2.tiles_b)

@@ -212,3 +212,63 @@ def test_direct_v3_kernels_on_padded_buffers(case):
     ref = F.conv_transpose2d(xin, w.double().cpu(), b.double().cpu(), stride=2)
     close(res[16][0], ref, 2e-5, "y vs torch")
     close(res[16][2], torch.sigmoid(ref), 2e-5, "sigmoid vs torch")
+
+
+def pitched(t, dev):
+    """copy of a 4-D tensor whose rows are padded to a multiple of 4 floats (what the engines allocate)"""
+    N, C, H, W = t.shape
+    ld = (W + 3) // 4 * 4
+    buf = torch.zeros(N, C, H, ld, dtype=torch.float32, device=dev)
+    buf[..., :W] = t.to(dev)
+    return buf[..., :W]
+
+
+TILE = [
+    # N, Cin, Cout, k, H, W: >= 2^20 positions, wide planes, few channels (BASELINE configs[3]'s last three layers, cropped)
+    (9, 8, 4, 4, 350, 341),
+    (5, 16, 8, 3, 470, 450),
+    (3, 32, 16, 3, 600, 590),
+]
+
+
+@pytest.mark.parametrize("case", TILE)
+def test_wgrad_tile_resident(case):
+    """k_wgrad_tile (both operands staged once per CTA tile) against torch fp64 autograd and against the direct kernel it
+    replaces, with the on-load transforms of the training step on both operands (BN+ReLU on the small one, the
+    two-tensor BN-backward affine on the big one)."""
+    from cae_tools_b200.engine import ops
+    dev = torch.device("cuda")
+    N, Ci, Co, k, H, W = case
+    x = rnd(N, Ci, H, W, seed=1).float()
+    k0, k2 = (rnd(Ci, seed=4).abs() + 0.5).float(), rnd(Ci, seed=5).float()
+    Hb, Wb = 2 * H + k - 2, 2 * W + k - 2
+    up, t1 = rnd(N, Co, Hb, Wb, seed=6).float(), rnd(N, Co, Hb, Wb, seed=7).float()
+    b0, b1, b2 = (rnd(Co, seed=8).abs() + 0.5).float(), rnd(Co, seed=9).float(), (rnd(Co, seed=10) * 0.1).float()
+    xin = F.relu(x.double() * k0.double().view(1, -1, 1, 1) + k2.double().view(1, -1, 1, 1))
+    big = up.double() * b0.double().view(1, -1, 1, 1) + t1.double() * b1.double().view(1, -1, 1, 1) + \
+        b2.double().view(1, -1, 1, 1)
+    wd = torch.zeros(Ci, Co, k, k, dtype=torch.float64, requires_grad=True)
+    (F.conv_transpose2d(xin, wd, None, stride=2) * big).sum().backward()
+    xd, upd, t1d = pitched(x, dev), pitched(up, dev), pitched(t1, dev)
+    src = ops.make_src(xd, k0=k0.to(dev), k2=k2.to(dev), relu=True)
+    dy = ops.make_src(upd, t1=t1d, k0=b0.to(dev), k1=b1.to(dev), k2=b2.to(dev))
+    g = ops.geom(k, 2, 0)
+    got = {}
+    for mask in (1 | 2 | 16 | 64, 1 | 2 | 16):          # with / without CAE_WGRAD_TILE (capi_host.h)
+        ops.set_kernel_generation(mask << 4)
+        gw = torch.full(wd.shape, float("nan"), dtype=torch.float32, device=dev)
+        part = torch.zeros(ops.wgrad_partials_len(src, dy, g), dtype=torch.float32, device=dev)
+        ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        for _ in range(2):
+            ops.conv_wgrad(src, dy, g, gw, part, ticket)
+        torch.cuda.synchronize()
+        close(gw, wd.grad, 2e-5, f"wgrad mask {mask} {case}")
+        assert int(ticket.item()) == 0
+        got[mask] = gw.clone()
+    # same launch twice gives the same bits (fixed-order reduction)
+    gw2 = torch.empty_like(got[83])
+    ops.set_kernel_generation(83 << 4)
+    part = torch.zeros(ops.wgrad_partials_len(src, dy, g), dtype=torch.float32, device=dev)
+    ops.conv_wgrad(src, dy, g, gw2, part, torch.zeros(1, dtype=torch.int32, device=dev))
+    torch.cuda.synchronize()
+    assert torch.equal(gw2, got[83])

@@ -64,9 +64,8 @@ def build_parser():
     p.add_argument("--mask-variable", type=str, help="name of the mask variable", default=None)
     # not in the reference (it has no multi-GPU path): batch-sharded data parallelism, one process per GPU
     p.add_argument("--gpus", type=int, default=1, help="data-parallel training on N GPUs of this node (one process per "
-                   "GPU, NCCL gradient all-reduce); under torchrun the environment decides and this flag is ignored")
-    p.add_argument("--sync-bn", action="store_true", help="with --gpus > 1: BatchNorm statistics over the GLOBAL batch "
-                   "(all-reduced), so the loss curve matches a single-GPU run of the same global batch")
+                   "GPU, gradient all-reduce; BatchNorm uses each rank's local statistics); under torchrun the environment "
+                   "decides and this flag is ignored")
     return p
 
 
@@ -158,8 +157,6 @@ def main(argv=None):
 
     if ctx is not None and not lead:
         mt.verbose = False
-    if args.sync_bn:
-        mt.sync_bn = True
     start_time = time.time()
     if lead:
         print("Ready for training process")

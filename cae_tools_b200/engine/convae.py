@@ -635,10 +635,6 @@ class ConvAEEngine:
                 sink(idx, self.output_buffer(b)[:N])
                 idx += 1
 
-    def encode_decode(self, data):
-        """like score_batches but also exposes the latent z per batch: yields (yhat, z)"""
-        raise NotImplementedError
-
 
 class _BucketedProgram:
     """graph A -> async all-reduce of the first bucket, overlapped with graph B -> second bucket -> optimiser graph"""

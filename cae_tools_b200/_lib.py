@@ -151,6 +151,8 @@ EXPORTS = {
     "cae_wgrad_partials_len": (C.c_longlong, [C.POINTER(CaeSrc), C.POINTER(CaeSrc), C.POINTER(CaeConvGeom)]),
     "cae_ew_epilogue": (C.c_int, [C.POINTER(CaeSrc), C.POINTER(CaeView), C.POINTER(CaeEpilogue), C.c_void_p]),
     "cae_gemm": (C.c_int, [C.POINTER(CaeGemm), C.c_void_p]),
+    "cae_gemm_tc_workspace": (C.c_longlong, [C.POINTER(CaeGemm)]),
+    "cae_gemm_tc": (C.c_int, [C.POINTER(CaeGemm), C.c_void_p, C.c_longlong, C.c_void_p]),
     "cae_bn_eval_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "cae_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                           C.c_void_p]),

@@ -255,7 +255,11 @@ static bool direct_ok(const ConvArgs& a, int width_in) {
     if (a.epi.mode == CAE_EPI_SIGMOID_MSE && (!src_aligned(a.epi.target) || a.epi.target.t1 || a.epi.target.relu)) return false;
     return true;
 }
-static int direct_cot(int Cout) { return Cout >= 4 ? 4 : (Cout >= 2 ? 2 : 1); }
+static int direct_cot(int Cout) {
+    static const int cap = [] { const char* e = getenv("CAE_DIRECT_COT"); return e ? atoi(e) : 4; }();   // tuning knob
+    const int c = Cout >= 4 ? 4 : (Cout >= 2 ? 2 : 1);
+    return c < cap ? c : cap;
+}
 
 template <int K>
 static int launch_up3(ConvArgs& a, cudaStream_t st, bool& handled) {
@@ -391,6 +395,12 @@ extern "C" int cae_ew_epilogue(const CaeSrc* in, const CaeView* out, const CaeEp
     a.total = out->N * out->H * out->W;
     a.inv_count = (float)((a.epi.count_scale > 0.f ? (double)a.epi.count_scale : 1.0) /
                           ((double)out->N * out->C * out->H * out->W));
+    if (out->H == 1 && out->W == 1 && out->C >= 64 && in->t0.sC == 1 && out->sC == 1 &&
+        (a.epi.mode != CAE_EPI_MASKSTATS || a.epi.act.sC == 1) && a.epi.mode != CAE_EPI_SIGMOID_MSE &&
+        (a.epi.addend.t0.p == nullptr || a.epi.addend.t0.sC == 1)) {
+        k_ew_rows<<<ceil_div(out->C, 32), CAE_NT, 0, (cudaStream_t)stream>>>(a);
+        return cae_check_launch("cae_ew_epilogue(rows)");
+    }
     dim3 grid(min(ceil_div(a.total, CAE_NT), CAE_MAX_GRID_X), out->C);
     k_ew_epilogue<<<grid, CAE_NT, 0, (cudaStream_t)stream>>>(a);
     return cae_check_launch("cae_ew_epilogue");

@@ -179,43 +179,49 @@ __device__ __forceinline__ void for_each_channel_sums(const double* part, int ro
 
 // BatchNorm forward statistics (training): reference semantics of nn.BatchNorm2d
 // (biased variance for normalisation, unbiased for running_var, momentum update).
+// one channel of the BatchNorm forward statistics: S = sum x, Q = sum x^2 over `count` elements
+__device__ __forceinline__ void bn_forward_channel(const CaeBN& bn, int c, double S, double Q, double count) {
+    double mean = S / count;
+    double var = Q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double invstd = rsqrt(var + (double)bn.eps);
+    float g = bn.gamma ? bn.gamma[c] : 1.f;
+    float b = bn.beta ? bn.beta[c] : 0.f;
+    bn.scale[c] = (float)((double)g * invstd);
+    bn.shift[c] = (float)((double)b - mean * (double)g * invstd);
+    bn.mean[c] = (float)mean;
+    bn.invstd[c] = (float)invstd;
+    if (bn.running_mean) {
+        double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        double m = (double)bn.momentum;
+        bn.running_mean[c] = (float)((1.0 - m) * (double)bn.running_mean[c] + m * mean);
+        bn.running_var[c] = (float)((1.0 - m) * (double)bn.running_var[c] + m * unbiased);
+    }
+}
+
 __device__ __forceinline__ void finalize_bn_forward(const CaeBN& bn, const double* part, int rows, double count) {
-    for_each_channel_sums(part, rows, bn.C, [&](int c, double S, double Q) {
-        double mean = S / count;
-        double var = Q / count - mean * mean;
-        if (var < 0.0) var = 0.0;
-        double invstd = rsqrt(var + (double)bn.eps);
-        float g = bn.gamma ? bn.gamma[c] : 1.f;
-        float b = bn.beta ? bn.beta[c] : 0.f;
-        bn.scale[c] = (float)((double)g * invstd);
-        bn.shift[c] = (float)((double)b - mean * (double)g * invstd);
-        bn.mean[c] = (float)mean;
-        bn.invstd[c] = (float)invstd;
-        if (bn.running_mean) {
-            double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-            double m = (double)bn.momentum;
-            bn.running_mean[c] = (float)((1.0 - m) * (double)bn.running_mean[c] + m * mean);
-            bn.running_var[c] = (float)((1.0 - m) * (double)bn.running_var[c] + m * unbiased);
-        }
-    });
+    for_each_channel_sums(part, rows, bn.C, [&](int c, double S, double Q) { bn_forward_channel(bn, c, S, Q, count); });
     if (threadIdx.x == 0 && bn.num_batches_tracked) bn.num_batches_tracked[0] += 1;
 }
 
 // BatchNorm backward sums -> dgamma, dbeta and the coefficients of dL/dy = A*dz + B*y + C
+// one channel of the BatchNorm backward sums: S1 = sum dz, S2 = sum dz * xhat
+__device__ __forceinline__ void bn_backward_channel(const CaeBN& bn, int c, double S1, double S2, double count) {
+    double g = bn.gamma ? (double)bn.gamma[c] : 1.0;
+    double invstd = (double)bn.invstd[c], mean = (double)bn.mean[c];
+    double A = g * invstd;
+    double B = -A * invstd * S2 / count;
+    double Cc = -A * S1 / count - B * mean;
+    bn.bwdA[c] = (float)A;
+    bn.bwdB[c] = (float)B;
+    bn.bwdC[c] = (float)Cc;
+    if (bn.dgamma) bn.dgamma[c] = (float)S2;
+    if (bn.dbeta) bn.dbeta[c] = (float)S1;
+    // the bias of a conv that feeds a training-mode BN has an identically zero gradient
+    // (sum_y dL/dy = 0); autograd returns rounding noise here.
+    if (bn.dbias) bn.dbias[c] = 0.f;
+}
+
 __device__ __forceinline__ void finalize_bn_backward(const CaeBN& bn, const double* part, int rows, double count) {
-    for_each_channel_sums(part, rows, bn.C, [&](int c, double S1, double S2) {   // sum dz, sum dz * xhat
-        double g = bn.gamma ? (double)bn.gamma[c] : 1.0;
-        double invstd = (double)bn.invstd[c], mean = (double)bn.mean[c];
-        double A = g * invstd;
-        double B = -A * invstd * S2 / count;
-        double Cc = -A * S1 / count - B * mean;
-        bn.bwdA[c] = (float)A;
-        bn.bwdB[c] = (float)B;
-        bn.bwdC[c] = (float)Cc;
-        if (bn.dgamma) bn.dgamma[c] = (float)S2;
-        if (bn.dbeta) bn.dbeta[c] = (float)S1;
-        // the bias of a conv that feeds a training-mode BN has an identically zero gradient
-        // (sum_y dL/dy = 0); autograd returns rounding noise here.
-        if (bn.dbias) bn.dbias[c] = 0.f;
-    });
+    for_each_channel_sums(part, rows, bn.C, [&](int c, double S1, double S2) { bn_backward_channel(bn, c, S1, S2, count); });
 }

@@ -50,41 +50,7 @@ struct PhArgs {
     float* grad_w;
     float* grad_b;
     int rows;
-    int tgt_bulk;              // the target rows of a patch row arrive as ONE bulk copy into shared memory, two patch rows ahead
 };
-
-// ---- bulk prefetch of the target (K == 32: one CTA slot).  The K rows x ld floats behind patch row (n, co, i) are contiguous
-// (32 KB at 256 x 256): thread 0 issues cp.async.bulk for the CTA's first two patch rows before anything else happens and
-// for patch row k + 2 as soon as patch row k is done, so the only HBM round trip the streaming loop ever waits for is the
-// very first one - and that overlaps the weight loads and the input staging.  ncu before: long_scoreboard the top stall
-// (2.3 - 3.0 warps per issue), issue slots 27 - 39 % busy, 17 MB in 23 / 26 us (profiles/r01_head_ncu.md).
-__device__ __forceinline__ uint32_t ph_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ph_bar_init(uint64_t* bars, int n) {
-    for (int i = 0; i < n; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ph_smem_u32(bars + i)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void ph_bulk_fetch(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
-    const uint32_t b = ph_smem_u32(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(ph_smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(b) : "memory");
-}
-__device__ __forceinline__ void ph_bar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t b = ph_smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(b), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ float4 ph_lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 __device__ __forceinline__ float4 ph_ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // sigmoid: cae_fast_sigmoid (common.cuh) - __expf + __frcp_rn still expand to ~16 instructions (the IEEE-rounded
@@ -290,21 +256,6 @@ __global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
     const PhRange rg = ph_range(a.N * a.Hin, SLOTS);
     const int usz = a.Win * PH_CIN * 2;                         // duplicated pairs
     float* sa0 = s_a + slot * PH_UC * usz;
-    constexpr bool BULK = LOSS && SLOTS == 1;
-    __shared__ uint64_t s_bar[2];
-    float* slab = s_a + SLOTS * PH_UC * usz;                    // [2][K * ld] target rows of two patch rows
-    const bool bulk = BULK && a.tgt_bulk;
-    const int slab_fl = K * tv.ld;
-    auto fetch_unit = [&](int u) {                              // thread 0
-        const int k = u - rg.ub, n = u / a.Hin, i = u - n * a.Hin;
-        ph_bulk_fetch(slab + (k & 1) * slab_fl, tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)i * K * tv.ld,
-                      (uint32_t)slab_fl * 4u, &s_bar[k & 1]);
-    };
-    if (bulk && tid == 0) {
-        ph_bar_init(s_bar, 2);
-        if (rg.ub < rg.ue) fetch_unit(rg.ub);
-        if (rg.ub + 1 < rg.ue) fetch_unit(rg.ub + 1);
-    }
     // moments of the current plane, per thread, across all of its patch rows that this slot handles (flushed when the
     // plane changes): M (mask only), Md, Mt, Mdd, Mtt, Mdt, E
     float mo[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -365,17 +316,11 @@ __global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
             const float* tp = LOSS ? tv.p + tbase + (long long)n * tv.sN + (long long)co * tv.sC + (long long)oy * tv.ld + kx : nullptr;
             const float* mp = MASK ? mv.p + mbase + (long long)n * mv.sN + (long long)mc * mv.sC + (long long)oy * mv.ld + kx : nullptr;
             float* yp = WRITE ? a.yhat.p + (long long)n * a.yhat.sN + (long long)co * a.yhat.sC + (long long)oy * a.yhat.ld + kx : nullptr;
-            const float* ts = nullptr;
-            if (bulk) {
-                const int k = u - rg.ub;
-                ph_bar_wait(&s_bar[k & 1], (k >> 1) & 1);
-                ts = slab + (k & 1) * slab_fl + ky * tv.ld + kx;
-            }
             for (int j0 = 0; j0 < a.Win; j0 += PF) {
                 float4 t4[PF], m4[PF];
 #pragma unroll
                 for (int q = 0; q < PF; ++q) {
-                    if (LOSS) t4[q] = (BULK && bulk) ? ph_lds4(ts + (j0 + q) * K) : ph_ld4(tp + (j0 + q) * K);
+                    if (LOSS) t4[q] = ph_ld4(tp + (j0 + q) * K);
                     if (MASK) m4[q] = ph_ld4(mp + (j0 + q) * K);
                 }
 #pragma unroll
@@ -421,10 +366,6 @@ __global__ void __launch_bounds__(CAE_NT, 2) k_ph_fwd(const PhArgs a) {
                 const int un = u + SLOTS;
                 const bool last = un >= rg.ue || un / a.Hin != n;
                 flush(n, i, last);
-            }
-            if (bulk && u + 2 < rg.ue) {                        // (one slot: u is CTA-uniform)
-                __syncthreads();                                // everyone is done with this slab
-                if (tid == 0) fetch_unit(u + 2);
             }
         }
     }
@@ -491,22 +432,6 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
     const size_t nelem = (size_t)a.Cin * a.Cout * KK;
     const int row = blockIdx.x * SLOTS + slot;
     const PhRange rg = ph_range(a.N * a.Hin, SLOTS);
-    constexpr bool BULK = SLOTS == 1;
-    __shared__ uint64_t s_bar[2];
-    float* slab = s_red + (size_t)SLOTS * PH_UC * WPS * usz;    // [2][K * ld] target rows of two (co, patch row) steps
-    const bool bulk = BULK && a.tgt_bulk;
-    const int slab_fl = K * tv.ld;
-    const int nu = max(rg.ue - rg.ub, 0), nsteps = nu * a.Cout;  // step s = co * nu + (u - ub)
-    auto fetch_step = [&](int sidx) {                           // thread 0
-        const int co_ = sidx / nu, u = rg.ub + (sidx - co_ * nu), n = u / a.Hin, i = u - n * a.Hin;
-        ph_bulk_fetch(slab + (sidx & 1) * slab_fl, tv.p + tbase + (long long)n * tv.sN + (long long)co_ * tv.sC + (long long)i * K * tv.ld,
-                      (uint32_t)slab_fl * 4u, &s_bar[sidx & 1]);
-    };
-    if (bulk && tid == 0) {
-        ph_bar_init(s_bar, 2);
-        if (0 < nsteps) fetch_step(0);
-        if (1 < nsteps) fetch_step(1);
-    }
     for (int co = 0; co < a.Cout; ++co) {
         W4 w[PH_CIN], gw[PH_CIN];
 #pragma unroll
@@ -541,17 +466,11 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
                 // without a mask: g = c0 (d - t) + ca t' + cb d' + ce = gd d' + gt t' + ce   (d' = d - PH_SHIFT, t' = t - PH_SHIFT;
                 // the coefficients are those of the shifted variables, see ph_finalize)
                 const float gd = c0 + cb2, gt = ca - c0;
-                const int sidx = co * nu + (u - rg.ub);
-                const float* ts = nullptr;
-                if (bulk) {
-                    ph_bar_wait(&s_bar[sidx & 1], (sidx >> 1) & 1);
-                    ts = slab + (sidx & 1) * slab_fl + ky * tv.ld + kx;
-                }
                 for (int j0 = 0; j0 < a.Win; j0 += PF) {
                     float4 t4[PF], m4[PF];
 #pragma unroll
                     for (int q = 0; q < PF; ++q) {
-                        t4[q] = (BULK && bulk) ? ph_lds4(ts + (j0 + q) * K) : ph_ld4(tp + (j0 + q) * K);
+                        t4[q] = ph_ld4(tp + (j0 + q) * K);
                         if (MASK) m4[q] = ph_ld4(mp + (j0 + q) * K);
                     }
 #pragma unroll
@@ -592,10 +511,6 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
                             if (!(lane & 1)) sr[j * PH_CIN + ((lane >> 1) & 15)] = r;
                         }
                     }
-                }
-                if (bulk && sidx + 2 < nsteps) {                // (one slot: the step is CTA-uniform)
-                    __syncthreads();                            // everyone is done with this slab
-                    if (tid == 0) fetch_step(sidx + 2);
                 }
             }
             __syncthreads();
@@ -732,15 +647,6 @@ static int ph_fill(PhArgs& a, const CaePatchHead* h) {
     return CAE_OK;
 }
 
-// bulk prefetch of the target: one slot per CTA (K == 32), the two slabs fit beside the kernel's other shared memory, and a
-// slab (K rows x ld) is 16-byte granular (src_aligned() is required of the target anyway)
-static bool ph_bulk_ok(const PhArgs& a, int K, size_t base_smem) {
-    if (K != 32 || !a.target.t0.p) return false;
-    if (getenv("CAE_PH_NO_BULK")) return false;
-    const size_t slab = (size_t)K * a.target.t0.ld * 4;
-    return base_smem % 16 == 0 && slab % 16 == 0 && base_smem + 2 * slab <= (size_t)kTileSmemMax;
-}
-
 // CTAs: every CTA gets the same number of patch rows (a multiple of the slot count), at most one CTA per SM
 static int ph_grid(const PhArgs& a, int K, int per_sm = 1) {
     const int slots = CAE_NT / (K * K / 4);
@@ -768,21 +674,17 @@ extern "C" int cae_patch_head_fwd(const CaePatchHead* h, const CaeView* yhat, vo
     CAE_REQUIRE(a.yhat.p || a.target.t0.p, "patch_head_fwd: nothing to do (no yhat, no target)");
     cudaStream_t st = (cudaStream_t)stream;
     const int slots = CAE_NT / (K * K / 4);
-    size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 2 * 4;
+    const size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 2 * 4;
     dim3 grid(ph_grid(a, K, 2), a.Cout);
     const bool loss = a.target.t0.p != nullptr, mask = loss && a.mask.t0.p != nullptr, write = a.yhat.p != nullptr;
-    if (loss && ph_bulk_ok(a, K, smem)) {
-        a.tgt_bulk = 1;
-        smem += (size_t)2 * K * a.target.t0.ld * 4;
-    }
     CAE_REQUIRE(!(loss && write), "patch_head_fwd: writing yhat and computing the loss in one call is not supported "
                                   "(score writes, train / test reduce)");
     const bool pf2 = a.Win % 2 == 0, pf4 = write && a.Win % 4 == 0;     // the write-only variant has registers to spare
 #define PH_FWD(K_, L_, M_, W_)                                                                      \
     do {                                                                                            \
-        if (W_ && pf4) { ensure_smem(k_ph_fwd<K_, L_, M_, W_, (W_ ? 4 : 2)>); k_ph_fwd<K_, L_, M_, W_, (W_ ? 4 : 2)><<<grid, CAE_NT, smem, st>>>(a); } \
-        else if (pf2) { ensure_smem(k_ph_fwd<K_, L_, M_, W_, 2>); k_ph_fwd<K_, L_, M_, W_, 2><<<grid, CAE_NT, smem, st>>>(a); }                   \
-        else { ensure_smem(k_ph_fwd<K_, L_, M_, W_, 1>); k_ph_fwd<K_, L_, M_, W_, 1><<<grid, CAE_NT, smem, st>>>(a); }                            \
+        if (W_ && pf4) k_ph_fwd<K_, L_, M_, W_, (W_ ? 4 : 2)><<<grid, CAE_NT, smem, st>>>(a);       \
+        else if (pf2) k_ph_fwd<K_, L_, M_, W_, 2><<<grid, CAE_NT, smem, st>>>(a);                   \
+        else k_ph_fwd<K_, L_, M_, W_, 1><<<grid, CAE_NT, smem, st>>>(a);                            \
     } while (0)
     if (K == 32) {
         if (write) PH_FWD(32, false, false, true);
@@ -837,11 +739,7 @@ extern "C" int cae_patch_head_bwd(const CaePatchHead* h, const CaeView* din, con
     a.partials = partials;
     a.dbpart = partials + (long long)CAE_NUM_SMS * slots * nelem;
     cudaStream_t st = (cudaStream_t)stream;
-    size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 4 * (2 + wps);
-    if (ph_bulk_ok(a, K, smem)) {
-        a.tgt_bulk = 1;
-        smem += (size_t)2 * K * a.target.t0.ld * 4;
-    }
+    const size_t smem = (size_t)slots * PH_UC * a.Win * PH_CIN * 4 * (2 + wps);
     const bool mask = a.mask.t0.p != nullptr, pf4 = a.Win % 2 == 0;     // two strips in flight (four spill at 255 registers)
 #define PH_BWD(K_, M_, P_)                                        \
     do {                                                          \

@@ -128,11 +128,28 @@ def ew_epilogue(src: CaeSrc, out: CaeView, epi: CaeEpilogue):
     check(lib().cae_ew_epilogue(C.byref(src), C.byref(out), C.byref(epi), _stream()), "cae_ew_epilogue")
 
 
+USE_TC_DENSE = True       # tests switch it off to compare against the SIMT kernel
+_gemm_ws = {}
+
+
 def gemm(M, N, K, A, sAm, sAk, B, sBk, sBn, Cout, sCm, sCn, a_k0=None, a_k2=None, a_hw=1, a_relu=False, b_k0=None,
          b_k2=None, b_hw=1, b_relu=False, bias=None, relu_out=False, mask=None, rowsum_A=None):
     g = CaeGemm(int(M), int(N), int(K), _ptr(A), int(sAm), int(sAk), _ptr(B), int(sBk), int(sBn), _ptr(Cout),
                 int(sCm), int(sCn), _ptr(a_k0), _ptr(a_k2), int(a_hw), int(bool(a_relu)), _ptr(b_k0), _ptr(b_k2),
                 int(b_hw), int(bool(b_relu)), _ptr(bias), int(bool(relu_out)), _ptr(mask), _ptr(rowsum_A))
+    # genuinely dense contractions (both free dimensions >= 128: the large-fc regimes) go to the tensor cores; the scratch
+    # for the split operands and the split-K slices is owned per call site (keyed by the output: weight-gradient GEMMs run
+    # on side streams beside the input-gradient ones) and allocated on the eager warm-up pass that precedes graph capture
+    need = lib().cae_gemm_tc_workspace(C.byref(g)) if USE_TC_DENSE else 0
+    if need > 0:
+        key = (_ptr(Cout), int(M), int(N), int(K))
+        ws = _gemm_ws.get(key)
+        if ws is None or ws.numel() < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("cae_gemm_tc: workspace must exist before graph capture (run the op once eagerly)")
+            ws = _gemm_ws[key] = torch.empty(need, dtype=torch.float32, device=Cout.device)
+        check(lib().cae_gemm_tc(C.byref(g), _ptr(ws), int(ws.numel()), _stream()), "cae_gemm_tc")
+        return
     check(lib().cae_gemm(C.byref(g), _stream()), "cae_gemm")
 
 

@@ -169,6 +169,12 @@ typedef struct CaeGemm {
     float*       rowsum_A;    /* if non-NULL: rowsum_A[m] = sum_k A(m,k)  (bias gradient when A = dy^T) */
 } CaeGemm;
 int cae_gemm(const CaeGemm* g, void* stream);
+/* The same contraction on the tensor cores (tc_dense.cu: split -> cae_tc_gemm 3xTF32 -> epilogue), for the nn.Linear layers
+ * of the large-fc regimes (unet.py:92-100,121-129 at fc 3200 / latent 800 and batch 256; linear.py:43 at large batches).
+ * cae_gemm_tc_workspace: floats of caller-owned scratch the call needs, 0 when the problem is not eligible (min(M,N) < 128,
+ * K < 32, < 0.1 GFLOP, an operand contiguous along neither axis, C not row-major): the caller then uses cae_gemm. */
+long long cae_gemm_tc_workspace(const CaeGemm* g);
+int cae_gemm_tc(const CaeGemm* g, float* workspace, long long workspace_len, void* stream);
 
 /* ---- batch norm helpers ------------------------------------------------------------------ */
 /* eval mode: scale/shift from running statistics for `count` layers (table lives on the DEVICE) */

@@ -8,7 +8,8 @@ Composed from existing entry points of libcae_b200, launched eagerly per batch (
     cae_gemm          dW = dz^T x, db = row sums of dz^T
     cae_adam          both parameters through the flat arena
     cae_step_advance
-The GEMMs run on the generic 32x32-tile fp32 kernel; the tcgen05 path SURVEY 8(f) row 3 asks for is not built."""
+ops.gemm sends both contractions to the tensor cores (tc_dense.cu: split -> tcgen05 3xTF32 -> epilogue) when the batch is
+>= 128; below that the layer is bound by one read of its weight (67 MB at 256 -> 65 536) and stays on the fp32 tile kernel."""
 
 from __future__ import annotations
 

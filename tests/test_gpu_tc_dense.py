@@ -125,3 +125,38 @@ def test_unet_large_fc_training_step_vs_oracle():
                 if err > 1e-4 * scale + 1e-9:
                     e_gpu, e_cpu = np.abs(got - r64).max(), np.abs(r - r64).max()
                     assert e_gpu <= 2.0 * e_cpu + 1e-9 and err <= 1e-3 * scale, (k, tc, err, scale, e_gpu, e_cpu)
+
+
+def test_linear_model_large_batch_on_tensor_cores_vs_oracle():
+    """LinearModel at a batch that makes its 256 -> 4096 contraction dense (both GEMMs eligible for
+    tcgen05): three optimiser steps against the oracle port"""
+    from cae_tools_b200.engine import ops
+    from cae_tools_b200.engine.linear import LinearEngine
+    from cae_tools_b200.models.linear import Linear
+    from oracle.torch_port import OracleLinear
+    torch.manual_seed(5)
+    mod = Linear((1, 16, 16), (1, 64, 64))
+    oracle = OracleLinear(mod.state_dict(), (1, 64, 64), lr=1e-3, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(6)
+    B = 384
+    X, Y = torch.rand(B, 1, 16, 16, generator=g), torch.rand(B, 1, 64, 64, generator=g)
+    eng = LinearEngine(mod, lr=1e-3, weight_decay=1e-5)
+    data = eng.bind(X, Y, B)
+    before = len(ops._gemm_ws)
+    for step in range(3):
+        got = float(eng.train_epoch(data).cpu()[0])
+        want = oracle.train_step(X, Y)
+        assert abs(got - want) <= 2e-5 * want, (step, got, want)
+        if step == 0:
+            for got_g, ref_g, what in ((mod.linear[1].weight.grad, oracle.w.grad, "dW"), (mod.linear[1].bias.grad, oracle.b.grad, "db")):
+                assert _maxrel(got_g, ref_g) < 2e-5, (what, _maxrel(got_g, ref_g))
+    assert len(ops._gemm_ws) >= before + 2          # forward and weight-gradient GEMMs took the tensor-core route
+    # Weights after three Adam steps.  The gradients carry the 1 / (B * 4096) of the mean: 1e-6 ... 1e-5, and the few elements
+    # whose gradient cancels to below Adam's eps = 1e-8 turn a 1e-10 summation difference (3xTF32 vs MKL, both ~1e-6 of the sum
+    # of magnitudes) into a visible fraction of the lr-sized step.  Typical element tight, 99.9 % within 1e-4, none beyond 5 %
+    # of the three steps.
+    for got_p, ref_p in ((mod.linear[1].weight, oracle.w), (mod.linear[1].bias, oracle.b)):
+        dev = (got_p.detach().cpu() - ref_p.detach()).abs().numpy()
+        scale = float(ref_p.detach().abs().max())
+        assert np.median(dev) <= 1e-5 * scale and np.quantile(dev, 0.999) <= 1e-4 * scale and dev.max() <= 0.05 * 3e-3, \
+            (float(np.median(dev)), float(np.quantile(dev, 0.999)), float(dev.max()), scale)

@@ -26,7 +26,10 @@ def main():
     ap.add_argument("--latent", type=int, default=800)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--linear", action="store_true", help="LinearModel 16x16 -> 256x256 (256 -> 65 536) instead of the unet")
     a = ap.parse_args()
+    if a.linear:
+        return linear(a)
     spec = ModelSpec()
     with open(os.path.join(ROOT, "cae_tools_b200", "specs", "unet_16x16_256x256.json")) as f:
         spec.load(json.load(f))
@@ -61,6 +64,34 @@ def main():
                 if "fc" in name or t / tot > 0.03:
                     print(f"  {name:30s} {t * 1e3:10.1f} us {100 * t / tot:5.1f}%")
             print(f"  sum {tot:.3f} ms")
+    ops.USE_TC_DENSE = True
+
+
+def linear(a):
+    from cae_tools_b200.engine.linear import LinearEngine
+    from cae_tools_b200.models.linear import Linear
+    dev = torch.device("cuda")
+    B = a.batch
+    gen = torch.Generator(device=dev).manual_seed(1)
+    X = torch.rand(2 * B, 1, 16, 16, device=dev, generator=gen)
+    Y = torch.rand(2 * B, 1, 256, 256, device=dev, generator=gen)
+    for tc in (True, False):
+        ops.USE_TC_DENSE = tc
+        torch.manual_seed(0)
+        eng = LinearEngine(Linear((1, 16, 16), (1, 256, 256)), lr=1e-3, weight_decay=1e-5, device=dev)
+        data = eng.bind(X, Y, B)
+        for _ in range(2):
+            eng.train_epoch(data)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            eng.train_epoch(data)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (a.steps * 2)
+        print(f"linear 256 -> 65536 batch {B}, GEMMs on {'tcgen05 (tc_dense)' if tc else 'SIMT k_gemm'}: {ms:.3f} ms/step, "
+              f"{B / ms * 1e3:.0f} samples/s, loss {float(data.losses[0]):.6f}", flush=True)
     ops.USE_TC_DENSE = True
 
 

@@ -214,6 +214,8 @@ EXPORTS = {
     "cae_unet_stem_train_bwd": (C.c_int, [C.POINTER(CaeStemTrain), C.POINTER(CaeSrc), C.c_void_p]),
     "cae_minmax_partials_len": (C.c_longlong, []),
     "cae_minmax": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cae_case_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_double,
+                                  C.c_double, C.c_void_p, C.c_void_p]),
     "cae_normalise_gather": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int,
                                        C.c_void_p, C.c_longlong, C.c_void_p]),
     "cae_dp_wait_done": (C.c_int, [C.POINTER(CaeDpPeers), C.c_void_p, C.c_void_p]),

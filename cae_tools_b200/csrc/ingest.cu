@@ -95,3 +95,45 @@ extern "C" int cae_normalise_gather(const float* src, long long sample_elems, co
                                                                  dst_sample_stride);
     return cae_check_launch("cae_normalise_gather");
 }
+
+// ---- post-training metrics on the device (reference model_metric.py:19-71, base_model.py:116-125) ----------
+// One row of eight float64 sums per case over its kept pixels (mask > 0 or no mask): count, sum a, sum e, sum a*a, sum e*e,
+// sum a*e, sum |a - e|, sum (a - e)^2 with a = actual (raw fp32) and e = lo + yhat * scale evaluated in float64 exactly as the
+// reference de-normalises its float32 predictions (ds_dataset.py:122-125).  The host turns the rows into mse / rmse / mae and
+// the mean per-case Pearson correlation.  One CTA per case; per-thread float64 partial sums, fixed-order CTA reduction.
+__global__ void __launch_bounds__(CAE_NT) k_case_metrics(const float* __restrict__ yhat, const float* __restrict__ actual,
+                                                         const float* __restrict__ mask, long long per_case, long long mask_per_case,
+                                                         double lo, double scale, double* __restrict__ out) {
+    __shared__ double red[CAE_NWARP][8];
+    const long long n = blockIdx.x;
+    const float* y = yhat + n * per_case;
+    const float* a = actual + n * per_case;
+    const float* m = mask ? mask + n * mask_per_case : nullptr;
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long i = threadIdx.x; i < per_case; i += CAE_NT) {
+        if (m && !(m[i % mask_per_case] != 0.f)) continue;
+        const double av = (double)a[i], ev = lo + (double)y[i] * scale, d = av - ev;
+        s[0] += 1.0; s[1] += av; s[2] += ev; s[3] += av * av; s[4] += ev * ev; s[5] += av * ev; s[6] += fabs(d); s[7] += d * d;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double t = warp_sum_d(s[k]);
+        if (lane == 0) red[warp][k] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < CAE_NWARP; ++w) t += red[w][threadIdx.x];
+        out[n * 8 + threadIdx.x] = t;
+    }
+}
+
+extern "C" int cae_case_metrics(const float* yhat, const float* actual, const float* mask, int n_cases, long long per_case,
+                                long long mask_per_case, double lo, double scale, double* out, void* stream) {
+    CAE_REQUIRE(yhat && actual && out && n_cases > 0 && per_case > 0, "case_metrics: bad argument");
+    CAE_REQUIRE(!mask || (mask_per_case > 0 && per_case % mask_per_case == 0), "case_metrics: the mask must tile a case");
+    k_case_metrics<<<n_cases, CAE_NT, 0, (cudaStream_t)stream>>>(yhat, actual, mask, per_case, mask ? mask_per_case : per_case, lo, scale, out);
+    return cae_check_launch("cae_case_metrics");
+}

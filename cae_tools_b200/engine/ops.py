@@ -570,6 +570,17 @@ def normalise_gather(src, order, lo, hi, normalise, dst, chan_offset=0):
 
 
 # ---- data-parallel exchange fused into the optimiser ------------------------------------------------------------------------
+def case_metrics(yhat, actual, mask, lo, scale, out):
+    """rows of eight float64 sums per case (count, sum a, sum e, sum aa, sum ee, sum ae, sum |a-e|, sum (a-e)^2) for the
+    post-training metrics; yhat / actual [n, ...] fp32, mask [n, 1 or C, H, W] fp32 or None, out [n, 8] float64"""
+    n = yhat.shape[0]
+    per_case = yhat[0].numel()
+    assert actual.shape == yhat.shape and yhat.is_contiguous() and actual.is_contiguous() and out.shape == (n, 8)
+    mpc = mask[0].numel() if mask is not None else per_case
+    check(lib().cae_case_metrics(_ptr(yhat), _ptr(actual), _ptr(mask), int(n), int(per_case), int(mpc), float(lo), float(scale),
+                                 _ptr(out), _stream()), "cae_case_metrics")
+
+
 def make_dp_peers(world, rank, grad_ptrs, flag_ptrs) -> CaeDpPeers:
     p = CaeDpPeers()
     p.world, p.rank = int(world), int(rank)

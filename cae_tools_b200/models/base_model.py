@@ -114,8 +114,14 @@ class BaseModel:
         return lo, hi, ds.denormalise_output(scores.astype(np.float64))
 
     def evaluate(self, dataset, device=None):
-        """mse / rmse / mae / mean Pearson of de-normalised predictions against the data set's output"""
+        """mse / rmse / mae / mean Pearson of de-normalised predictions against the data set's output (reference:
+        base_model.py:116-125 + model_metric.py).  With an engine on a CUDA device the per-case sums are formed on the device
+        next to the predictions (`cae_case_metrics`, float64) and only eight numbers per case come back; the host numpy path
+        below is what runs otherwise and what the device path is tested against."""
         dataset.set_normalise_output(False)
+        got = self._evaluate_device(dataset)
+        if got is not None:
+            return got
         scores = dataset.denormalise_output(self.predict_array(dataset.input_array()).astype(np.float64), force=True)
         actual = np.asarray(dataset.output_da.values)
         mask = dataset.mask_array()
@@ -123,6 +129,46 @@ class BaseModel:
         for i in range(actual.shape[0]):
             mm.accumulate(actual[i], scores[i], mask[i])
         return mm.get_metrics()
+
+    device_metrics = True
+
+    def _evaluate_device(self, dataset):
+        if not (self.device_metrics and torch.cuda.is_available() and hasattr(self, "_ensure_engine")):
+            return None
+        actual = np.asarray(dataset.output_da.values)
+        if actual.dtype != np.float32 or actual.ndim != 4:
+            return None
+        from ..engine import ops
+        eng = self._ensure_engine()
+        dev = eng.device
+        n = actual.shape[0]
+        bs = max(1, min(getattr(self, "apply_batch_size", n), n))
+        data = eng.bind(torch.from_numpy(np.ascontiguousarray(dataset.input_array(), dtype=np.float32)), None, bs)
+        raw = getattr(dataset, "_raw", {}).get(dataset.output_variable_name)          # uploaded by the ingest scan
+        act = raw if raw is not None and raw.device == dev else torch.from_numpy(np.ascontiguousarray(actual)).to(dev)
+        mask = None
+        if dataset.mask_da is not None and dataset.mask_da.size > 0:
+            mask = torch.from_numpy(np.ascontiguousarray(dataset.mask_array(like_output=False), dtype=np.float32)).to(dev)
+        rows = torch.zeros(n, 8, dtype=torch.float64, device=dev)
+        lo, hi = float(dataset.min_output), float(dataset.max_output)
+
+        def sink(i, yhat):
+            a, b = i * bs, i * bs + yhat.shape[0]
+            ops.case_metrics(yhat.contiguous(), act[a:b], None if mask is None else mask[a:b], lo, hi - lo, rows[a:b])
+
+        eng.score_batches(data, sink)
+        r = rows.cpu().numpy()
+        cnt, sa, se, saa, see, sae, ab, sq = (r[:, k] for k in range(8))
+        if cnt.sum() == 0:
+            raise ValueError("No data accumulated to calculate metrics.")
+        live = cnt > 0
+        with np.errstate(invalid="ignore", divide="ignore"):
+            cov = sae[live] - sa[live] * se[live] / cnt[live]
+            den = np.sqrt((saa[live] - sa[live] ** 2 / cnt[live]) * (see[live] - se[live] ** 2 / cnt[live]))
+            corr = np.where(den > 0, cov / den, np.nan)
+        mse = float(sq.sum() / cnt.sum())
+        return {"mse": mse, "rmse": float(np.sqrt(mse)), "mae": float(ab.sum() / cnt.sum()),
+                "mean_pearson_correlation": float(np.mean(corr)) if corr.size else 0.0}
 
     def dump_metrics(self, title, metrics):
         print("\n" + title)

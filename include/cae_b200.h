@@ -484,6 +484,12 @@ long long cae_minmax_partials_len(void);
 int cae_minmax(const float* x, long long n, float* partials, unsigned int* ticket, float* out3, void* stream);
 int cae_normalise_gather(const float* src, long long sample_elems, const int* order, int n_out, float lo, float hi,
                          int normalise, float* dst, long long dst_sample_stride, void* stream);
+/* post-training metrics on the device (model_metric.py:19-71 as used by base_model.py:116-125): out[n*8 + {0..7}] = count,
+ * sum a, sum e, sum a^2, sum e^2, sum a*e, sum |a-e|, sum (a-e)^2 over the kept pixels of case n (mask > 0; mask == NULL:
+ * all), a = actual[n] (raw fp32), e = lo + yhat[n] * scale in float64 (the reference's de-normalisation of its float32
+ * predictions, ds_dataset.py:122-125).  mask_per_case elements of mask per case, tiled over the case (1 or C channels). */
+int cae_case_metrics(const float* yhat, const float* actual, const float* mask, int n_cases, long long per_case,
+                     long long mask_per_case, double lo, double scale, double* out, void* stream);
 
 /* ---- data-parallel exchange fused into the optimiser (dp_fused.cu) -------------------------------------------------------
  * One launch per rank: all-reduce of the flat gradient arena by peer reads over NVLink (summed in rank order: identical

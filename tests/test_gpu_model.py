@@ -295,3 +295,30 @@ def test_device_ingest_matches_dsdataset_host_path():
     ds["a"] = xr_lite.DataArray(bad, dims=("n", "c", "y", "x"))
     with pytest.raises(ValueError):
         DSDataset(ds, ["a", "b"], "out")
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_device_metrics_match_the_host_model_metric(masked):
+    """BaseModel.evaluate (reference base_model.py:116-125 + model_metric.py): the per-case float64 sums formed on the device
+    (cae_case_metrics) give the same mse / rmse / mae / mean Pearson as the host ModelMetric loop over the same predictions"""
+    from cae_tools_b200.models.ds_dataset import DSDataset
+    m, tr, te = _circle_model(64, 2)
+    mask_name = None
+    if masked:
+        rng = np.random.RandomState(2)
+        mk = (rng.rand(100, 1, 256, 256) > 0.3).astype(np.float32)
+        mk[7] = 0.0                                            # a case without any kept pixel contributes nothing
+        te.add("mask", mk)
+        mask_name = "mask"
+    d = DSDataset(te, ["lowres"], "hires", normalise_in=m.normalise_input, mask_variable_name=mask_name)
+    d.set_normalisation_parameters(m.normalisation_parameters)
+    res = {}
+    for on in (True, False):
+        m.device_metrics = on
+        res[on] = m.evaluate(d)
+    m.device_metrics = True
+    assert set(res[True]) == {"mse", "rmse", "mae", "mean_pearson_correlation"}
+    for k in res[False]:
+        # (correlations live in [-1, 1]: absolute 1e-9; the trained-for-2-epochs model's mean correlation is ~1e-3)
+        atol = 1e-9 if k == "mean_pearson_correlation" else 1e-12
+        assert abs(res[True][k] - res[False][k]) <= 1e-9 * abs(res[False][k]) + atol, (k, res[True][k], res[False][k])

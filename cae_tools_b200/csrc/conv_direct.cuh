@@ -13,6 +13,15 @@ struct StripPlan {
     int units;       // N * RP * NS
 };
 
+// software prefetch into L1: these kernels hold 16 warps per SM (128 registers) and every channel iteration used to start with
+// an L1 miss (ncu: long_scoreboard 2.2 - 5.7 warps per issue, issue slots 40 - 55 % busy).  The rows of the NEXT channel are
+// requested while the current one is accumulated; no registers are held.
+__device__ __forceinline__ void pf_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void pf_src(const CaeSrc& s, long long off) {
+    pf_l1(s.t0.p + off);
+    if (s.t1) pf_l1(s.t1 + off);
+}
+
 __device__ __forceinline__ float xf1(float v, const ChanCoef& k, bool relu) {
     v = fmaf(v, k.k0, k.k2);
     return relu ? fmaxf(v, 0.f) : v;
@@ -161,6 +170,13 @@ __global__ void __launch_bounds__(CAE_NT) k_up3(const ConvArgs a, const StripPla
             const bool vec_ok = qx0 < Win;            // the aligned float4 starts inside the row (rows are padded to 4)
             for (int ci = 0; ci < a.Cin; ++ci) {
                 const ChanCoef kc = load_coef(a.in, ci);
+                if (ci + 1 < a.Cin && vec_ok) {
+#pragma unroll
+                    for (int jy = 0; jy < 2; ++jy) {
+                        const int iy = qy - jy;
+                        if (iy >= 0 && iy < Hin) pf_src(a.in, nbase + (long long)(ci + 1) * iv.sC + (long long)iy * iv.ld + qx0);
+                    }
+                }
                 float v[2][5];                         // [jy][x - (qx0-1)]
 #pragma unroll
                 for (int jy = 0; jy < 2; ++jy) {
@@ -264,6 +280,11 @@ __global__ void __launch_bounds__(CAE_NT) k_down3(const ConvArgs a, const StripP
             for (int ci = 0; ci < a.Cin; ++ci) {
                 const ChanCoef kc = load_coef(a.in, ci);
                 const float* wp = s_w + ci * KK * COT;
+                if (ci + 1 < a.Cin && xb < Win) {
+#pragma unroll
+                    for (int ky = 0; ky < K; ++ky)
+                        if (2 * oy + ky < Hin) pf_src(a.in, nbase + (long long)(ci + 1) * iv.sC + (long long)(2 * oy + ky) * iv.ld);
+                }
 #pragma unroll
                 for (int ky = 0; ky < K; ++ky) {
                     const int r = 2 * oy + ky;

@@ -3,6 +3,7 @@
 #include "conv_family.cuh"
 #include "conv_tiled.cuh"
 #include "conv_direct.cuh"
+#include "conv_down_tile.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -141,7 +142,7 @@ static int fill_conv_args(ConvArgs& a, const CaeSrc* in, const float* weight, co
 // =====================================================================================================
 static int default_mask() {
     const char* e = getenv("CAE_KERNEL_MASK");
-    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A | CAE_V3_DIRECT | CAE_WGRAD_TILE);
+    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A | CAE_V3_DIRECT | CAE_WGRAD_TILE | CAE_DOWN_TILE);
 }
 int g_cae_mask = default_mask();
 extern "C" void cae_set_kernel_generation(int gen) { g_mask = (gen <= 1) ? 0 : (gen == 2 ? default_mask() : (gen >> 4)); }
@@ -281,10 +282,37 @@ static int launch_up3(ConvArgs& a, cudaStream_t st, bool& handled) {
     return cae_check_launch("cae_conv_up(v3)");
 }
 
+template <int K, int COT>
+static int launch_down_tile_t(ConvArgs& a, const DownTilePlan& p, dim3 grid, size_t smem, cudaStream_t st) {
+    ensure_smem(k_down_tile<K, COT>);
+    k_down_tile<K, COT><<<grid, CAE_NT, smem, st>>>(a, p);
+    return cae_check_launch("cae_conv_down(tile)");
+}
+
 template <int K>
 static int launch_down3(ConvArgs& a, cudaStream_t st, bool& handled) {
     handled = false;
     if (!direct_ok(a, a.out.W)) return CAE_OK;
+    if ((g_mask & CAE_DOWN_TILE) && a.out.W >= 64 && (long long)a.out.N * a.out.H * a.out.W >= (1ll << 19) && a.Cout % 4 == 0 &&
+        a.Cin <= 64) {
+        const int cot = a.Cout % 8 == 0 ? 8 : 4;
+        DownTilePlan p{};
+        p.tiles_y = ceil_div(a.out.H, DT_ROWS);
+        p.tiles_x = ceil_div(a.out.W, DT_STRIPS * 4);
+        p.ntiles = a.out.N * p.tiles_y * p.tiles_x;
+        p.IR = 2 * DT_ROWS + K - 2;
+        p.ntens = a.in.t1 ? 2 : 1;
+        p.stage_fl = p.ntens * p.IR * DT_IW;
+        const size_t smem = ((size_t)a.Cin * K * K * cot + roundup4(a.Cin * 4) + 2 * (size_t)p.stage_fl) * 4;
+        if (smem <= (size_t)kTileSmemMax) {
+            const int gy = a.Cout / cot;
+            int gx = (2 * CAE_NUM_SMS + gy - 1) / gy;
+            if (gx > p.ntiles) gx = p.ntiles;
+            handled = true;
+            if (cot == 8) return launch_down_tile_t<K, 8>(a, p, dim3(gx, gy), smem, st);
+            return launch_down_tile_t<K, 4>(a, p, dim3(gx, gy), smem, st);
+        }
+    }
     const int cot = direct_cot(a.Cout);
     const size_t smem = (size_t)a.Cin * K * K * cot * 4;
     if (smem > 48 * 1024) return CAE_OK;

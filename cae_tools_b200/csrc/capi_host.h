@@ -33,6 +33,8 @@ static const int kTileSmemMax = 100 * 1024;
 // tile-resident weight gradient of the wide thin layers (k_wgrad_tile): both operands are fetched once per CTA tile
 // instead of once per channel-tile pair
 #define CAE_WGRAD_TILE 64
+// cp.async tile pipeline for the strided conv of the wide thin layers (k_down_tile) instead of the direct-load k_down3
+#define CAE_DOWN_TILE 128
 extern int g_cae_mask;                 // defined in capi.cu
 #define g_mask g_cae_mask
 #define g_use_v2 (g_mask & CAE_V2_UPDOWN)

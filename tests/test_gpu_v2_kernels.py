@@ -272,3 +272,69 @@ def test_wgrad_tile_resident(case):
     ops.conv_wgrad(src, dy, g, gw2, part, torch.zeros(1, dtype=torch.int32, device=dev))
     torch.cuda.synchronize()
     assert torch.equal(gw2, got[83])
+
+
+DOWN_TILE = [
+    # N, C_small (conv output channels), C_big (conv input channels), k, H, W of the small plane; >= 2^19 output positions
+    (9, 8, 4, 4, 240, 250),
+    (5, 16, 8, 3, 330, 322),
+    (3, 12, 8, 3, 420, 430),
+]
+
+
+@pytest.mark.parametrize("mode", ["plain", "maskstats"])
+@pytest.mark.parametrize("case", DOWN_TILE)
+def test_down_tile_pipeline(case, mode):
+    """k_down_tile (cp.async stages of raw rows, on-load affine at the shared -> register move) as the input gradient of a wide
+    thin ConvTranspose2d: against torch fp64 and against the direct kernel, two-tensor BN-backward affine on the operand,
+    plain and ReLU-mask + BatchNorm-backward-sums epilogues"""
+    from cae_tools_b200.engine import ops
+    dev = torch.device("cuda")
+    N, Cs, Cb, k, H, W = case
+    Hb, Wb = 2 * H + k - 2, 2 * W + k - 2
+    w = (rnd(Cs, Cb, k, k, seed=2) * 0.2).float()
+    up, t1 = rnd(N, Cb, Hb, Wb, seed=6).float(), rnd(N, Cb, Hb, Wb, seed=7).float()
+    b0, b1, b2 = (rnd(Cb, seed=8).abs() + 0.5).float(), rnd(Cb, seed=9).float(), (rnd(Cb, seed=10) * 0.1).float()
+    big = up.double() * b0.double().view(1, -1, 1, 1) + t1.double() * b1.double().view(1, -1, 1, 1) + b2.double().view(1, -1, 1, 1)
+    ref = F.conv2d(big, w.double(), None, stride=2)                        # [N, Cs, H, W]
+    assert ref.shape == (N, Cs, H, W)
+    ysm = rnd(N, Cs, H, W, seed=11).float()
+    sc, sh = (rnd(Cs, seed=12).abs() + 0.5).float(), rnd(Cs, seed=13).float() * 0.3
+    mean, invstd = rnd(Cs, seed=14).float() * 0.1, (rnd(Cs, seed=15).abs() + 0.5).float()
+    if mode == "maskstats":
+        keepm = (ysm.double() * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1)) > 0
+        ref = ref * keepm
+        want_db = ref.sum((0, 2, 3))
+        want_dg = (ref * (ysm.double() - mean.double().view(1, -1, 1, 1)) * invstd.double().view(1, -1, 1, 1)).sum((0, 2, 3))
+    upd, t1d, wd, ysd = pitched(up, dev), pitched(t1, dev), w.to(dev), pitched(ysm, dev)
+    src = ops.make_src(upd, t1=t1d, k0=b0.to(dev), k1=b1.to(dev), k2=b2.to(dev))
+    g = ops.geom(k, 2, 0)
+    outs = {}
+    for mask in (1 | 2 | 16 | 64 | 128, 1 | 2 | 16 | 64):               # with / without CAE_DOWN_TILE (capi_host.h)
+        ops.set_kernel_generation(mask << 4)
+        out = pitched(torch.full((N, Cs, H, W), float("nan")), dev)
+        if mode == "plain":
+            epi = ops.make_epilogue(ops.EPI_PLAIN)
+        else:
+            st = torch.zeros(7, Cs, device=dev)
+            st[0], st[1], st[2], st[3] = sc.to(dev), sh.to(dev), mean.to(dev), invstd.to(dev)
+            dg, db = torch.zeros(Cs, device=dev), torch.zeros(Cs, device=dev)
+            bn = ops.make_bn(Cs, 1e-5, 0.1, torch.ones(Cs, device=dev), torch.zeros(Cs, device=dev), scale=st[0], shift=st[1],
+                             mean=st[2], invstd=st[3], dgamma=dg, dbeta=db, bwdA=st[4], bwdB=st[5], bwdC=st[6])
+            part = torch.zeros(ops.partials_len(Cs), dtype=torch.float64, device=dev)
+            tick = torch.zeros(1, dtype=torch.int32, device=dev)
+            epi = ops.make_epilogue(ops.EPI_MASKSTATS, partials=part, ticket=tick, bn=bn, act=ysd)
+        for _ in range(2):
+            ops.conv_down(src, wd, g, ops.view4(out), epi)
+        torch.cuda.synchronize()
+        close(out, ref, 2e-5, f"down mask {mask} {case} {mode}")
+        if mode == "maskstats":
+            close(db, want_db, 2e-5, "dbeta")
+            close(dg, want_dg, 2e-5, "dgamma")
+            assert int(tick.item()) == 0
+        outs[mask] = out.clone()
+    assert _maxdiff(outs[211], outs[83]) <= 2e-5
+
+
+def _maxdiff(a, b):
+    return float((a.double() - b.double()).abs().max()) / max(float(b.double().abs().max()), 1e-12)

@@ -4,6 +4,7 @@
 #include "conv_tiled.cuh"
 #include "conv_direct.cuh"
 #include "conv_down_tile.cuh"
+#include "conv_up_tile.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -142,7 +143,7 @@ static int fill_conv_args(ConvArgs& a, const CaeSrc* in, const float* weight, co
 // =====================================================================================================
 static int default_mask() {
     const char* e = getenv("CAE_KERNEL_MASK");
-    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A | CAE_V3_DIRECT | CAE_WGRAD_TILE | CAE_DOWN_TILE);
+    return e ? atoi(e) : (CAE_V2_UPDOWN | CAE_V2_WGRAD_A | CAE_V3_DIRECT | CAE_WGRAD_TILE | CAE_DOWN_TILE | CAE_UP_TILE);
 }
 int g_cae_mask = default_mask();
 extern "C" void cae_set_kernel_generation(int gen) { g_mask = (gen <= 1) ? 0 : (gen == 2 ? default_mask() : (gen >> 4)); }
@@ -262,10 +263,37 @@ static int direct_cot(int Cout) {
     return c < cap ? c : cap;
 }
 
+template <int K, int COT>
+static int launch_up_tile_t(ConvArgs& a, const UpTilePlan& p, dim3 grid, size_t smem, cudaStream_t st) {
+    ensure_smem(k_up_tile<K, COT>);
+    k_up_tile<K, COT><<<grid, CAE_NT, smem, st>>>(a, p);
+    return cae_check_launch("cae_conv_up(tile)");
+}
+
 template <int K>
 static int launch_up3(ConvArgs& a, cudaStream_t st, bool& handled) {
     handled = false;
     if (!direct_ok(a, a.in.t0.W)) return CAE_OK;
+    if ((g_mask & CAE_UP_TILE) && a.in.t0.W >= 64 && a.in.t1 == nullptr && a.Cin <= 64 &&
+        (long long)a.out.N * a.out.H * a.out.W >= (1ll << 21)) {
+        const int cot = direct_cot(a.Cout);
+        UpTilePlan p{};
+        const int QH = (a.out.H - 1) / 2 + 1, QW = (a.out.W - 1) / 2 + 1;
+        p.tiles_y = ceil_div(QH, UT_ROWS);
+        p.tiles_x = ceil_div(QW, UT_STRIPS * 4);
+        p.ntiles = a.out.N * p.tiles_y * p.tiles_x;
+        p.nchunks = ceil_div(a.Cin, UT_CC);
+        const size_t smem = ((size_t)a.Cin * K * K * cot + roundup4(a.Cin * 4) + 2 * (size_t)UT_CC * UT_IR * UT_IW) * 4;
+        if (smem <= (size_t)kTileSmemMax) {
+            const int gy = ceil_div(a.Cout, cot);
+            int gx = (2 * CAE_NUM_SMS + gy - 1) / gy;
+            if (gx > p.ntiles) gx = p.ntiles;
+            handled = true;
+            if (cot == 4) return launch_up_tile_t<K, 4>(a, p, dim3(gx, gy), smem, st);
+            if (cot == 2) return launch_up_tile_t<K, 2>(a, p, dim3(gx, gy), smem, st);
+            return launch_up_tile_t<K, 1>(a, p, dim3(gx, gy), smem, st);
+        }
+    }
     const int cot = direct_cot(a.Cout);
     const size_t smem = (size_t)a.Cin * K * K * cot * 4;
     if (smem > 48 * 1024) return CAE_OK;

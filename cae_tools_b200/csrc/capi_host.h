@@ -35,6 +35,7 @@ static const int kTileSmemMax = 100 * 1024;
 #define CAE_WGRAD_TILE 64
 // cp.async tile pipeline for the strided conv of the wide thin layers (k_down_tile) instead of the direct-load k_down3
 #define CAE_DOWN_TILE 128
+#define CAE_UP_TILE 256      // the same for the transposed conv (k_up_tile instead of k_up3)
 extern int g_cae_mask;                 // defined in capi.cu
 #define g_mask g_cae_mask
 #define g_use_v2 (g_mask & CAE_V2_UPDOWN)

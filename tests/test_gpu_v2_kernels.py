@@ -338,3 +338,69 @@ def test_down_tile_pipeline(case, mode):
 
 def _maxdiff(a, b):
     return float((a.double() - b.double()).abs().max()) / max(float(b.double().abs().max()), 1e-12)
+
+
+UP_TILE = [
+    # N, Cin, Cout, k, H, W of the input plane; >= 2^21 output pixels
+    (4, 8, 4, 4, 250, 243),
+    (3, 16, 8, 3, 300, 290),
+    (2, 32, 16, 3, 270, 260),
+    (3, 8, 3, 3, 330, 341),
+]
+
+
+@pytest.mark.parametrize("mode", ["stats", "sigmoid_mse"])
+@pytest.mark.parametrize("case", UP_TILE)
+def test_up_tile_pipeline(case, mode):
+    """k_up_tile (cp.async stages of raw rows; affine + ReLU + bounds mask at the shared -> register move) as the forward pass of
+    a wide thin ConvTranspose2d: against torch fp64 and against the direct kernel, with the BatchNorm-statistics epilogue
+    and with the fused sigmoid + MSE (+ dL/dz) epilogue"""
+    from cae_tools_b200.engine import ops
+    dev = torch.device("cuda")
+    N, Ci, Co, k, H, W = case
+    x = rnd(N, Ci, H, W, seed=1).float()
+    w = (rnd(Ci, Co, k, k, seed=2) * 0.2).float()
+    b = rnd(Co, seed=3).float()
+    k0, k2 = (rnd(Ci, seed=4).abs() + 0.5).float(), rnd(Ci, seed=5).float()
+    xin = F.relu(x.double() * k0.double().view(1, -1, 1, 1) + k2.double().view(1, -1, 1, 1))
+    v = F.conv_transpose2d(xin, w.double(), b.double(), stride=2).requires_grad_(True)
+    Ho, Wo = v.shape[2], v.shape[3]
+    if mode == "sigmoid_mse":
+        Y = torch.rand(N, Co, Ho, Wo, generator=torch.Generator().manual_seed(64))
+        loss = F.mse_loss(torch.sigmoid(v), Y.double())
+        loss.backward()
+    xd, wd, bd = pitched(x, dev), w.to(dev), b.to(dev)
+    src = ops.make_src(xd, k0=k0.to(dev), k2=k2.to(dev), relu=True)
+    g = ops.geom(k, 2, 0)
+    outs = {}
+    for mask in (1 | 2 | 16 | 64 | 128 | 256, 1 | 2 | 16 | 64 | 128):        # with / without CAE_UP_TILE (capi_host.h)
+        ops.set_kernel_generation(mask << 4)
+        out = pitched(torch.full((N, Co, Ho, Wo), float("nan")), dev)
+        part = torch.zeros(ops.partials_len(Co), dtype=torch.float64, device=dev)
+        tick = torch.zeros(1, dtype=torch.int32, device=dev)
+        if mode == "stats":
+            st = torch.zeros(7, Co, device=dev)
+            bn = ops.make_bn(Co, 1e-5, 0.1, torch.ones(Co, device=dev), torch.zeros(Co, device=dev), scale=st[0], shift=st[1],
+                             mean=st[2], invstd=st[3], bwdA=st[4], bwdB=st[5], bwdC=st[6])
+            epi = ops.make_epilogue(ops.EPI_STATS, bias=bd, partials=part, ticket=tick, bn=bn)
+        else:
+            Yd = pitched(Y, dev)
+            losses, dbias = torch.zeros(1, device=dev), torch.zeros(Co, device=dev)
+            epi = ops.make_epilogue(ops.EPI_SIGMOID_MSE, bias=bd, partials=part, ticket=tick, target=ops.make_src(Yd),
+                                    loss_out=losses, dbias=dbias, write_mode=0)
+        for _ in range(2):
+            ops.conv_up(src, wd, g, ops.view4(out), epi)
+        torch.cuda.synchronize()
+        assert int(tick.item()) == 0
+        if mode == "stats":
+            close(out, v, 2e-5, f"up mask {mask} {case}")
+            mean = v.detach().mean((0, 2, 3))
+            var = v.detach().var((0, 2, 3), unbiased=False)
+            close(st[2], mean, 2e-5, "batch mean")
+            close(st[3], 1.0 / torch.sqrt(var + 1e-5), 2e-5, "invstd")
+        else:
+            close(out, v.grad, 1e-4, f"dL/dz mask {mask} {case}")
+            assert abs(float(losses[0]) - float(loss)) <= 1e-5 * float(loss)
+            close(dbias, v.grad.sum(dim=(0, 2, 3)), 1e-4, "dbias")
+        outs[mask] = out.clone()
+    assert _maxdiff(outs[467], outs[211]) <= 2e-5

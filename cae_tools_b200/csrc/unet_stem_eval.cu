@@ -3,19 +3,27 @@
 //   fc stack Linear - BatchNorm1d(eval) - ReLU - Linear - ReLU, twice  (unet.py:92-100,121-129)
 //   decoder  [ConvTranspose2d, ChannelAttention gate, concat with the encoder skip, BatchNorm2d(eval), ReLU] x n_up
 //            (unet.py:23-39,131-163)
-// In eval mode BatchNorm is a per-channel affine, so nothing couples the samples of a batch: a CTA takes STEM_S samples
-// through the whole stem with every activation in shared memory (<= 3 K floats per sample for the shipped spec); each
-// layer's weights are staged through shared memory as well (every weight load is shared by the STEM_S samples) and only
-// the final activated concat tensor is written to global memory.  Replaces the 11 launches before the head.
-// Measured (B200): 150 us against 218 us for the chain at batch 1024, 577 against 537 us at 4096 - the inner loops are
-// plain per-thread loops with run-time geometry (~1 TFLOP/s); the engine uses this kernel for batches <= 2048.
+// In eval mode BatchNorm is a per-channel affine, so nothing couples the samples of a batch: a CTA takes STEM_ST = 8 samples
+// (two thread halves x 4 samples in registers) through the whole stem with every activation in shared memory (<= 3 K floats
+// per sample for the shipped spec); the weights of all layers stay in shared memory for the whole kernel when they fit
+// (89 KB for the shipped spec; otherwise they are staged layer by layer) and only the final activated concat tensor is
+// written to global memory.  Replaces the 11 launches before the head.
+// Measured (B200, stem alone at batch 4096): 577 us with run-time tap loops (round 1) -> ~230 us with compile-time-K loops
+// (stem_conv_k / stem_up_s2: ~14 instructions per (channel, tap) for 4 FMAs, issue-bound at 16 warps per SM); the per-layer
+// chain needs ~520 us, so the engine uses this kernel at every batch size.
 #include "capi_host.h"
 
-#define STEM_S 4
-#define STEM_NT 256
+#define STEM_S 4             // samples per thread (register block)
+#define STEM_H 2             // thread halves: half h takes samples h*STEM_S .. of the pass through the conv / fc / up loops
+#define STEM_ST (STEM_S * STEM_H)   // samples per CTA pass
+#define STEM_NT 512
+#define STEM_HT (STEM_NT / STEM_H)  // threads per half
+#define STEM_SMEM_MAX ((size_t)200 * 1024)
 
-struct StemSmem {            // offsets in floats, per CTA (all STEM_S samples)
+struct StemSmem {            // offsets in floats, per CTA (all STEM_ST samples)
     int in0, enc[CAE_STEM_MAX], va, vb, y, cat, small, wbuf;
+    int resident;            // 1: every layer's weights live in shared memory for the whole kernel (offsets below), 0: staged per layer
+    int w_conv[CAE_STEM_MAX], w_fc[CAE_STEM_MAX], w_up[CAE_STEM_MAX];
     int total;
 };
 
@@ -35,7 +43,7 @@ __device__ __forceinline__ float stem_bn_relu(float v, const float* scale, const
 __device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* wsm, const float* in, float* outp, int in_pitch,
                                           int out_pitch) {
     const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, KK = L.k * L.k;
-    for (int e = threadIdx.x; e < total; e += STEM_NT) {
+    for (int e = (threadIdx.x & (STEM_HT - 1)); e < total; e += STEM_HT) {
         const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
         float acc[STEM_S];
         const float b = L.b ? __ldg(L.b + co) : 0.f;
@@ -63,12 +71,96 @@ __device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* wsm
     }
 }
 
+// Compile-time kernel size: the K*K taps are unrolled, their bounds checks become per-thread masks computed once per layer, and
+// the 9 / 16 independent (weight, S inputs) load groups of one input channel are in flight together.  The generic loop above
+// re-evaluates the bounds inside a run-time triple loop: one dependent shared-memory round trip per FMA group (~70 cycles per
+// tap measured through the whole kernel: 577 us per 4096 samples).
+template <int K>
+__device__ __forceinline__ void stem_conv_k(const CaeStemConv& L, const float* wsm, const float* in, float* outp, int in_pitch,
+                                            int out_pitch) {
+    constexpr int KK = K * K;
+    const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, HWi = L.Hin * L.Win;
+    for (int e = (threadIdx.x & (STEM_HT - 1)); e < total; e += STEM_HT) {
+        const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
+        const int iy0 = oy * L.stride - L.pad, ix0 = ox * L.stride - L.pad;
+        int off[KK];
+        bool ok[KK];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int iy = iy0 + ky, ix = ix0 + kx;
+                ok[ky * K + kx] = iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
+                off[ky * K + kx] = ok[ky * K + kx] ? iy * L.Win + ix : 0;
+            }
+        float acc[STEM_S];
+        const float b = L.b ? __ldg(L.b + co) : 0.f;
+#pragma unroll
+        for (int s = 0; s < STEM_S; ++s) acc[s] = b;
+        const float* wp = wsm + co * L.Cin * KK;
+#pragma unroll 2
+        for (int ci = 0; ci < L.Cin; ++ci) {
+            const float* ip = in + ci * HWi;
+#pragma unroll
+            for (int t = 0; t < KK; ++t) {
+                const float wv = ok[t] ? wp[ci * KK + t] : 0.f;
+                const float* q = ip + off[t];
+#pragma unroll
+                for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(q[s * in_pitch], wv, acc[s]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < STEM_S; ++s) outp[s * out_pitch + e] = stem_bn_relu(acc[s], L.scale, L.shift, co);
+    }
+}
+
+// transposed convolution with stride 2 and k <= 4: every output pixel has at most 2 x 2 taps (ky = (oy + pad) mod 2 + 2a);
+// they are located once per layer and thread - the generic gather below pays a modulo and a division per tap and channel
+__device__ __forceinline__ void stem_up_s2(const CaeStemUp& L, const float* wsm, const float* in, float* outp, int in_pitch,
+                                           int out_pitch) {
+    const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, KK = L.k * L.k, HWi = L.Hin * L.Win, wci = L.Cout * KK;
+    for (int e = (threadIdx.x & (STEM_HT - 1)); e < total; e += STEM_HT) {
+        const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
+        int pos[4], tap[4];
+        bool ok[4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+                const int ky = ((oy + L.pad) & 1) + 2 * a, kx = ((ox + L.pad) & 1) + 2 * b2;
+                const int iy = ((oy + L.pad) >> 1) - a, ix = ((ox + L.pad) >> 1) - b2;
+                const bool v = ky < L.k && kx < L.k && iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
+                ok[a * 2 + b2] = v;
+                pos[a * 2 + b2] = v ? iy * L.Win + ix : 0;
+                tap[a * 2 + b2] = v ? co * KK + ky * L.k + kx : 0;
+            }
+        float acc[STEM_S];
+        const float b = L.b ? __ldg(L.b + co) : 0.f;
+#pragma unroll
+        for (int s = 0; s < STEM_S; ++s) acc[s] = b;
+#pragma unroll 2
+        for (int ci = 0; ci < L.Cin; ++ci) {
+            const float* wp = wsm + ci * wci;
+            const float* ip = in + ci * HWi;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float wv = ok[t] ? wp[tap[t]] : 0.f;
+                const float* q = ip + pos[t];
+#pragma unroll
+                for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(q[s * in_pitch], wv, acc[s]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < STEM_S; ++s) outp[s * out_pitch + e] = acc[s];
+    }
+}
+
 // v_out[s][o] = act((W v_in[s] + b) * scale + shift)
 __device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* wsm, const float* in, float* outp, int in_pitch,
                                         int out_pitch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ht = threadIdx.x & (STEM_HT - 1), lane = ht & 31, warp = ht >> 5;
     if (L.in >= 64) {                                   // long rows: one warp per output, lanes over k
-        for (int o = warp; o < L.out; o += STEM_NT / 32) {
+        for (int o = warp; o < L.out; o += STEM_HT / 32) {
             float acc[STEM_S];
 #pragma unroll
             for (int s = 0; s < STEM_S; ++s) acc[s] = 0.f;
@@ -89,7 +181,7 @@ __device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* wsm, co
             }
         }
     } else {
-        for (int o = threadIdx.x; o < L.out; o += STEM_NT) {
+        for (int o = ht; o < L.out; o += STEM_HT) {
             float acc[STEM_S];
             const float b = L.b ? __ldg(L.b + o) : 0.f;
 #pragma unroll
@@ -113,7 +205,7 @@ __device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* wsm, co
 __device__ __forceinline__ void stem_up(const CaeStemUp& L, const float* wsm, const float* in, float* outp, int in_pitch,
                                         int out_pitch) {
     const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, KK = L.k * L.k;
-    for (int e = threadIdx.x; e < total; e += STEM_NT) {
+    for (int e = (threadIdx.x & (STEM_HT - 1)); e < total; e += STEM_HT) {
         const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
         float acc[STEM_S];
         const float b = L.b ? __ldg(L.b + co) : 0.f;
@@ -155,15 +247,28 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
     const long long xbase = src_cursor_offset(a.x);
     const int N = xv.N;
     float* wsm = sm + m.wbuf;
-    // layer weights go through shared memory: with ~190 KB of the SM carved out for activations the L1 keeps almost
-    // nothing, and weight loads that miss it cost an L2 round trip per tap (first version: 747 us per 4096 samples)
-    auto stage_w = [&](const float* w, int n) {
-        for (int e = tid; e < n; e += STEM_NT) wsm[e] = __ldg(w + e);
+    const int h = tid / STEM_HT;                           // thread half -> samples h * STEM_S ..
+    // Layer weights go through shared memory (with the SM carved out for activations the L1 keeps almost nothing, and weight
+    // loads that miss it cost an L2 round trip per tap).  When everything fits they are staged ONCE per CTA (`resident`);
+    // otherwise layer by layer into one buffer, as the first version of this kernel did for every pass of 4 samples.
+    auto stage = [&](float* dst, const float* w, int n) {
+        for (int e = tid; e < n; e += STEM_NT) dst[e] = __ldg(w + e);
     };
-    for (int n0 = blockIdx.x * STEM_S; n0 < N; n0 += gridDim.x * STEM_S) {
+    if (m.resident) {
+        for (int l = 0; l < S.n_conv; ++l) stage(sm + m.w_conv[l], S.conv[l].w, S.conv[l].Cout * S.conv[l].Cin * S.conv[l].k * S.conv[l].k);
+        for (int l = 0; l < S.n_fc; ++l) stage(sm + m.w_fc[l], S.fc[l].w, S.fc[l].in * S.fc[l].out);
+        for (int j = 0; j < S.n_up; ++j) stage(sm + m.w_up[j], S.up[j].w, S.up[j].Cin * S.up[j].Cout * S.up[j].k * S.up[j].k);
+    }
+    auto weights = [&](int off, const float* w, int n) -> const float* {
+        if (m.resident) return sm + off;
+        stage(wsm, w, n);
+        __syncthreads();
+        return wsm;
+    };
+    for (int n0 = blockIdx.x * STEM_ST; n0 < N; n0 += gridDim.x * STEM_ST) {
         __syncthreads();
         // ---- input (samples beyond N are zero-filled; their results are never written)
-        for (int e = tid; e < STEM_S * in_elems; e += STEM_NT) {
+        for (int e = tid; e < STEM_ST * in_elems; e += STEM_NT) {
             const int s = e / in_elems, r = e - s * in_elems;
             const int c = r / (c0.Hin * c0.Win), q = r - c * c0.Hin * c0.Win, yy = q / c0.Win, xx = q - yy * c0.Win;
             float v = 0.f;
@@ -180,9 +285,12 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
         for (int l = 0; l < S.n_conv; ++l) {
             const CaeStemConv& L = S.conv[l];
             const int op = L.Cout * L.Hout * L.Wout;
-            stage_w(L.w, L.Cout * L.Cin * L.k * L.k);
-            __syncthreads();
-            stem_conv(L, wsm, cur, sm + m.enc[l], cur_pitch, op);
+            const float* w = weights(m.w_conv[l], L.w, L.Cout * L.Cin * L.k * L.k);
+            const float* in = cur + h * STEM_S * cur_pitch;
+            float* outp = sm + m.enc[l] + h * STEM_S * op;
+            if (L.k == 3) stem_conv_k<3>(L, w, in, outp, cur_pitch, op);
+            else if (L.k == 4) stem_conv_k<4>(L, w, in, outp, cur_pitch, op);
+            else stem_conv(L, w, in, outp, cur_pitch, op);
             __syncthreads();
             cur = sm + m.enc[l];
             cur_pitch = op;
@@ -193,9 +301,8 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
         for (int l = 0; l < S.n_fc; ++l) {
             const CaeStemFc& L = S.fc[l];
             float* dst = (l & 1) ? vb : va;
-            stage_w(L.w, L.in * L.out);
-            __syncthreads();
-            stem_fc(L, wsm, cur, dst, cur_pitch, L.out);
+            const float* w = weights(m.w_fc[l], L.w, L.in * L.out);
+            stem_fc(L, w, cur + h * STEM_S * cur_pitch, dst + h * STEM_S * L.out, cur_pitch, L.out);
             __syncthreads();
             cur = dst;
             cur_pitch = L.out;
@@ -206,15 +313,15 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
             const int C = L.Cout, HW = L.Hout * L.Wout, yp = C * HW, cp = 2 * yp;
             float* y = sm + m.y;
             float* cat = sm + m.cat;
-            stage_w(L.w, L.Cin * L.Cout * L.k * L.k);
+            const float* w = weights(m.w_up[j], L.w, L.Cin * L.Cout * L.k * L.k);
+            if (L.stride == 2 && L.k <= 4) stem_up_s2(L, w, cur + h * STEM_S * cur_pitch, y + h * STEM_S * yp, cur_pitch, yp);
+            else stem_up(L, w, cur + h * STEM_S * cur_pitch, y + h * STEM_S * yp, cur_pitch, yp);
             __syncthreads();
-            stem_up(L, wsm, cur, y, cur_pitch, yp);
-            __syncthreads();
-            float* avg = sm + m.small;                     // [S][C]
-            float* mx = avg + STEM_S * C;                  // [S][C]
-            float* hid = mx + STEM_S * C;                  // [S][2][Cr]
-            float* att = hid + STEM_S * 2 * L.Cr;          // [S][C]
-            for (int e = tid; e < STEM_S * C; e += STEM_NT) {
+            float* avg = sm + m.small;                     // [ST][C]
+            float* mx = avg + STEM_ST * C;                 // [ST][C]
+            float* hid = mx + STEM_ST * C;                 // [ST][2][Cr]
+            float* att = hid + STEM_ST * 2 * L.Cr;         // [ST][C]
+            for (int e = tid; e < STEM_ST * C; e += STEM_NT) {
                 const int s = e / C, c = e - s * C;
                 const float* q = y + s * yp + c * HW;
                 float sum = 0.f, mxx = -INFINITY;
@@ -223,7 +330,7 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
                 mx[e] = mxx;
             }
             __syncthreads();
-            for (int e = tid; e < STEM_S * 2 * L.Cr; e += STEM_NT) {
+            for (int e = tid; e < STEM_ST * 2 * L.Cr; e += STEM_NT) {
                 const int s = e / (2 * L.Cr), r2 = e - s * 2 * L.Cr, which = r2 / L.Cr, r = r2 - which * L.Cr;
                 const float* src = (which ? mx : avg) + s * C;
                 float v = 0.f;
@@ -231,18 +338,18 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
                 hid[e] = fmaxf(v, 0.f);
             }
             __syncthreads();
-            for (int e = tid; e < STEM_S * C; e += STEM_NT) {
+            for (int e = tid; e < STEM_ST * C; e += STEM_NT) {
                 const int s = e / C, c = e - s * C;
-                const float* h = hid + s * 2 * L.Cr;
+                const float* hd = hid + s * 2 * L.Cr;
                 float v = 0.f;
-                for (int r = 0; r < L.Cr; ++r) v = fmaf(__ldg(L.W2 + c * L.Cr + r), h[r] + h[L.Cr + r], v);
+                for (int r = 0; r < L.Cr; ++r) v = fmaf(__ldg(L.W2 + c * L.Cr + r), hd[r] + hd[L.Cr + r], v);
                 att[e] = 1.f / (1.f + expf(-v));
             }
             __syncthreads();
             // cat = relu(bn([att * y ; skip]))
             const float* skip = sm + m.enc[L.skip];
             const bool last = j == S.n_up - 1;
-            for (int e = tid; e < STEM_S * cp; e += STEM_NT) {
+            for (int e = tid; e < STEM_ST * cp; e += STEM_NT) {
                 const int s = e / cp, r = e - s * cp, c2 = r / HW, i = r - c2 * HW;
                 float v = c2 < C ? att[s * C + c2] * y[s * yp + r] : skip[s * yp + (r - yp)];
                 v = stem_bn_relu(v, L.scale, L.shift, c2);
@@ -265,7 +372,7 @@ static int stem_plan(const CaeUnetStem& s, StemSmem& m, char* why, size_t why_le
         STEM_FAIL("layer counts %d/%d/%d outside 1..%d", s.n_conv, s.n_fc, s.n_up, CAE_STEM_MAX);
     int off = 0;
     auto take = [&](int floats) { int o = off; off += (floats + 3) & ~3; return o; };
-    m.in0 = take(STEM_S * s.conv[0].Cin * s.conv[0].Hin * s.conv[0].Win);
+    m.in0 = take(STEM_ST * s.conv[0].Cin * s.conv[0].Hin * s.conv[0].Win);
     int prev = s.conv[0].Cin * s.conv[0].Hin * s.conv[0].Win;
     for (int l = 0; l < s.n_conv; ++l) {
         const CaeStemConv& L = s.conv[l];
@@ -273,7 +380,7 @@ static int stem_plan(const CaeUnetStem& s, StemSmem& m, char* why, size_t why_le
         if ((L.Hin + 2 * L.pad - L.k) / L.stride + 1 != L.Hout || (L.Win + 2 * L.pad - L.k) / L.stride + 1 != L.Wout)
             STEM_FAIL("encoder layer %d geometry", l);
         prev = L.Cout * L.Hout * L.Wout;
-        m.enc[l] = take(STEM_S * prev);
+        m.enc[l] = take(STEM_ST * prev);
     }
     int vmax = 0;
     for (int l = 0; l < s.n_fc; ++l) {
@@ -281,8 +388,8 @@ static int stem_plan(const CaeUnetStem& s, StemSmem& m, char* why, size_t why_le
         prev = s.fc[l].out;
         vmax = max(vmax, prev);
     }
-    m.va = take(STEM_S * vmax);
-    m.vb = take(STEM_S * vmax);
+    m.va = take(STEM_ST * vmax);
+    m.vb = take(STEM_ST * vmax);
     int ymax = 0, smallmax = 0;
     for (int j = 0; j < s.n_up; ++j) {
         const CaeStemUp& L = s.up[j];
@@ -296,16 +403,26 @@ static int stem_plan(const CaeUnetStem& s, StemSmem& m, char* why, size_t why_le
         smallmax = max(smallmax, 3 * L.Cout + 2 * L.Cr);
         prev = 2 * L.Cout * L.Hout * L.Wout;
     }
-    m.y = take(STEM_S * ymax);
-    m.cat = take(STEM_S * 2 * ymax);
-    m.small = take(STEM_S * smallmax);
-    int wmax = 0;
-    for (int l = 0; l < s.n_conv; ++l) wmax = max(wmax, s.conv[l].Cout * s.conv[l].Cin * s.conv[l].k * s.conv[l].k);
-    for (int l = 0; l < s.n_fc; ++l) wmax = max(wmax, s.fc[l].in * s.fc[l].out);
-    for (int j = 0; j < s.n_up; ++j) wmax = max(wmax, s.up[j].Cin * s.up[j].Cout * s.up[j].k * s.up[j].k);
-    m.wbuf = take(wmax);
+    m.y = take(STEM_ST * ymax);
+    m.cat = take(STEM_ST * 2 * ymax);
+    m.small = take(STEM_ST * smallmax);
+    int wmax = 0, wsum = 0;
+    auto wsize = [&](int n) { wmax = max(wmax, n); wsum += (n + 3) & ~3; };
+    for (int l = 0; l < s.n_conv; ++l) wsize(s.conv[l].Cout * s.conv[l].Cin * s.conv[l].k * s.conv[l].k);
+    for (int l = 0; l < s.n_fc; ++l) wsize(s.fc[l].in * s.fc[l].out);
+    for (int j = 0; j < s.n_up; ++j) wsize(s.up[j].Cin * s.up[j].Cout * s.up[j].k * s.up[j].k);
+    m.resident = (size_t)(off + wsum) * 4 <= STEM_SMEM_MAX;
+    if (m.resident) {
+        for (int l = 0; l < s.n_conv; ++l) m.w_conv[l] = take(s.conv[l].Cout * s.conv[l].Cin * s.conv[l].k * s.conv[l].k);
+        for (int l = 0; l < s.n_fc; ++l) m.w_fc[l] = take(s.fc[l].in * s.fc[l].out);
+        for (int j = 0; j < s.n_up; ++j) m.w_up[j] = take(s.up[j].Cin * s.up[j].Cout * s.up[j].k * s.up[j].k);
+        m.wbuf = off;
+    } else {
+        m.wbuf = take(wmax);
+    }
     m.total = off;
-    if ((size_t)off * 4 > 160 * 1024) STEM_FAIL("activations of %d samples need %d KB of shared memory (> 160)", STEM_S, off * 4 / 1024);
+    if ((size_t)off * 4 > STEM_SMEM_MAX)
+        STEM_FAIL("activations of %d samples need %d KB of shared memory (> %d)", STEM_ST, off * 4 / 1024, (int)(STEM_SMEM_MAX / 1024));
     return 1;
 #undef STEM_FAIL
 }
@@ -339,11 +456,11 @@ extern "C" int cae_unet_stem_eval(const CaeUnetStem* s, const CaeSrc* x, const C
     const size_t smem = (size_t)a.m.total * 4;
     static bool opted = false;
     if (!opted) {
-        cudaFuncSetAttribute(k_unet_stem_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_unet_stem_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_SMEM_MAX);
         opted = true;
     }
-    const int passes = ceil_div(x->t0.N, STEM_S);
-    const int per_sm = max(1, min(8, (int)((200 * 1024) / (smem + 1024))));
+    const int passes = ceil_div(x->t0.N, STEM_ST);
+    const int per_sm = max(1, min(4, (int)((220 * 1024) / (smem + 1024))));
     const int grid = min(passes, CAE_NUM_SMS * per_sm);
     k_unet_stem_eval<<<grid, STEM_NT, smem, (cudaStream_t)stream>>>(a);
     return cae_check_launch("cae_unet_stem_eval");

@@ -131,11 +131,12 @@ class UNetEngine(ConvAEEngine):
             return ops.make_epilogue(ops.EPI_STATS, bias=bias, partials=self._partials(Cn), ticket=self._ticket(), bn=blk)
         return ops.make_epilogue(ops.EPI_PLAIN, bias=bias)
 
-    # eval mode: every layer before the last one in ONE launch (unet_stem_eval.cu), used up to `fused_stem_max_batch`
-    # samples per batch.  Measured (B200, shipped spec): batch 1024 - 150 us against 218 us for the 11-launch chain;
-    # batch 4096 - 577 us against 537 us (its plain per-thread loops run at ~1 TFLOP/s, the chain's tiled kernels at ~3).
+    # eval mode: every layer before the last one in ONE launch (unet_stem_eval.cu).  Measured (B200, shipped spec, whole score
+    # batch incl. the head, tools/eval_stem_probe.py): batch 256 - 90 us against 156 us for the 11-launch chain; 1024 - 144
+    # against 296; 4096 - 540 against 825.  (Round 1's version of the kernel lost to the chain at 4096 - 577 us for the stem
+    # alone - and was capped at 2048 samples; its run-time tap loops were replaced by compile-time-K ones.)
     use_fused_stem = True
-    fused_stem_max_batch = 2048
+    fused_stem_max_batch = 1 << 30
     use_fused_attention = True  # one launch per decoder block and direction (attention_block.cu); False = unfused chain
     use_patch_head = True       # fused kernel==stride last layer (patch_head.cu); False = generic conv + loss kernels
 

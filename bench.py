@@ -326,7 +326,10 @@ def run_b200(args):
         os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (NCCL prints its version there)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None
     if world > 1:
+        from cae_tools_b200.engine.dp import bind_to_local_numa
+        numa_node = bind_to_local_numa(local)     # pinned staging buffers of this rank on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
@@ -570,7 +573,8 @@ def run_b200(args):
                 "in_step_graph": fused or bool(getattr(eng, "capture_allreduce", False)),
                 "note": ("the gradient all-reduce runs inside the optimiser launch (peer reads over NVLink, cae_adam_allreduce); "
                          "nccl_allreduce_us is what a standalone NCCL all-reduce of the same arena costs") if fused else
-                        "one NCCL all-reduce of the flat fp32 gradient arena per optimiser step"}
+                        "one NCCL all-reduce of the flat fp32 gradient arena per optimiser step",
+                "rank0_numa_node": numa_node}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -3,21 +3,21 @@
 //   fc stack Linear - BatchNorm1d(eval) - ReLU - Linear - ReLU, twice  (unet.py:92-100,121-129)
 //   decoder  [ConvTranspose2d, ChannelAttention gate, concat with the encoder skip, BatchNorm2d(eval), ReLU] x n_up
 //            (unet.py:23-39,131-163)
-// In eval mode BatchNorm is a per-channel affine, so nothing couples the samples of a batch: a CTA takes STEM_ST = 8 samples
-// (two thread halves x 4 samples in registers) through the whole stem with every activation in shared memory (<= 3 K floats
-// per sample for the shipped spec); the weights of all layers stay in shared memory for the whole kernel when they fit
-// (89 KB for the shipped spec; otherwise they are staged layer by layer) and only the final activated concat tensor is
-// written to global memory.  Replaces the 11 launches before the head.
-// Measured (B200, stem alone at batch 4096): 577 us with run-time tap loops (round 1) -> ~230 us with compile-time-K loops
-// (stem_conv_k / stem_up_s2: ~14 instructions per (channel, tap) for 4 FMAs, issue-bound at 16 warps per SM); the per-layer
-// chain needs ~520 us, so the engine uses this kernel at every batch size.
+// In eval mode BatchNorm is a per-channel affine, so nothing couples the samples of a batch: a CTA of 512 threads takes
+// STEM_ST = 8 samples through the whole stem with every activation in shared memory (<= 3 K floats per sample for the
+// shipped spec); the weights of all layers stay in shared memory for the whole kernel when they fit (89 KB for the shipped
+// spec; otherwise they are staged layer by layer) and only the final activated concat tensor is written to global memory.
+// Replaces the 11 launches before the head.
+// Measured (B200, stem alone at batch 4096; tools/eval_stem_probe.py): 577 us with run-time tap loops (round 1) -> 230 us
+// with compile-time-K loops, one output x 4 samples per thread (4 bytes of shared-memory traffic per FMA: the loops ran at
+// the shared-memory bandwidth, and neither resident weights nor 16-byte loads changed the time) -> 190 us with the current
+// item = (sample, position, 4 output channels) mapping, which is issue-bound (~2.3 instructions per FMA plus ~200 of index
+// arithmetic per item).  The per-layer chain needs ~520 us, so the engine uses this kernel at every batch size.
 #include "capi_host.h"
 
-#define STEM_S 4             // samples per thread (register block)
-#define STEM_H 2             // thread halves: half h takes samples h*STEM_S .. of the pass through the conv / fc / up loops
-#define STEM_ST (STEM_S * STEM_H)   // samples per CTA pass
+#define STEM_ST 8            // samples per CTA pass
 #define STEM_NT 512
-#define STEM_HT (STEM_NT / STEM_H)  // threads per half
+#define STEM_COB 4           // output channels per thread (register block) in the fast conv / up paths
 #define STEM_SMEM_MAX ((size_t)200 * 1024)
 
 struct StemSmem {            // offsets in floats, per CTA (all STEM_ST samples)
@@ -39,200 +39,167 @@ __device__ __forceinline__ float stem_bn_relu(float v, const float* scale, const
     return fmaxf(v, 0.f);
 }
 
-// y[s][e] for e = (co, oy, ox): strided convolution with padding, BN(eval) + ReLU
-__device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* wsm, const float* in, float* outp, int in_pitch,
-                                          int out_pitch) {
-    const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, KK = L.k * L.k;
-    for (int e = (threadIdx.x & (STEM_HT - 1)); e < total; e += STEM_HT) {
-        const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
-        float acc[STEM_S];
-        const float b = L.b ? __ldg(L.b + co) : 0.f;
-#pragma unroll
-        for (int s = 0; s < STEM_S; ++s) acc[s] = b;
-        const int iy0 = oy * L.stride - L.pad, ix0 = ox * L.stride - L.pad;
-        for (int ci = 0; ci < L.Cin; ++ci) {
-            const float* wp = wsm + (co * L.Cin + ci) * KK;
-            const float* ip = in + ci * L.Hin * L.Win;
-            for (int ky = 0; ky < L.k; ++ky) {
-                const int iy = iy0 + ky;
-                if (iy < 0 || iy >= L.Hin) continue;
-                for (int kx = 0; kx < L.k; ++kx) {
-                    const int ix = ix0 + kx;
-                    if (ix < 0 || ix >= L.Win) continue;
-                    const float wv = wp[ky * L.k + kx];
-                    const float* q = ip + iy * L.Win + ix;
-#pragma unroll
-                    for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(q[s * in_pitch], wv, acc[s]);
-                }
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < STEM_S; ++s) outp[s * out_pitch + e] = stem_bn_relu(acc[s], L.scale, L.shift, co);
-    }
-}
+// Layouts in shared memory.
+//   activations: the STEM_ST samples of the pass are INNERMOST - element e of sample s at base + e * STEM_ST + s;
+//   conv / up weights: [ci][tap][co] (re-laid-out while staging), fc weights [out][in] as stored.
+// Work item of the conv / up loops = (sample s, output position, group of COB output channels), s fastest: the 8 lanes of
+// a position read 8 consecutive floats, the COB weights of a tap arrive as one broadcast 16-byte load, and every input value
+// that leaves shared memory feeds COB FMAs.
+__device__ __forceinline__ int stem_idx(int s, int e) { return e * STEM_ST + s; }
 
-// Compile-time kernel size: the K*K taps are unrolled, their bounds checks become per-thread masks computed once per layer, and
-// the 9 / 16 independent (weight, S inputs) load groups of one input channel are in flight together.  The generic loop above
-// re-evaluates the bounds inside a run-time triple loop: one dependent shared-memory round trip per FMA group (~70 cycles per
-// tap measured through the whole kernel: 577 us per 4096 samples).
-template <int K>
-__device__ __forceinline__ void stem_conv_k(const CaeStemConv& L, const float* wsm, const float* in, float* outp, int in_pitch,
-                                            int out_pitch) {
-    constexpr int KK = K * K;
-    const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, HWi = L.Hin * L.Win;
-    for (int e = (threadIdx.x & (STEM_HT - 1)); e < total; e += STEM_HT) {
-        const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
-        const int iy0 = oy * L.stride - L.pad, ix0 = ox * L.stride - L.pad;
-        int off[KK];
-        bool ok[KK];
-#pragma unroll
-        for (int ky = 0; ky < K; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-                const int iy = iy0 + ky, ix = ix0 + kx;
-                ok[ky * K + kx] = iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
-                off[ky * K + kx] = ok[ky * K + kx] ? iy * L.Win + ix : 0;
-            }
-        float acc[STEM_S];
-        const float b = L.b ? __ldg(L.b + co) : 0.f;
-#pragma unroll
-        for (int s = 0; s < STEM_S; ++s) acc[s] = b;
-        const float* wp = wsm + co * L.Cin * KK;
-#pragma unroll 2
-        for (int ci = 0; ci < L.Cin; ++ci) {
-            const float* ip = in + ci * HWi;
-#pragma unroll
-            for (int t = 0; t < KK; ++t) {
-                const float wv = ok[t] ? wp[ci * KK + t] : 0.f;
-                const float* q = ip + off[t];
-#pragma unroll
-                for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(q[s * in_pitch], wv, acc[s]);
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < STEM_S; ++s) outp[s * out_pitch + e] = stem_bn_relu(acc[s], L.scale, L.shift, co);
-    }
-}
-
-// transposed convolution with stride 2 and k <= 4: every output pixel has at most 2 x 2 taps (ky = (oy + pad) mod 2 + 2a);
-// they are located once per layer and thread - the generic gather below pays a modulo and a division per tap and channel
-__device__ __forceinline__ void stem_up_s2(const CaeStemUp& L, const float* wsm, const float* in, float* outp, int in_pitch,
-                                           int out_pitch) {
-    const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, KK = L.k * L.k, HWi = L.Hin * L.Win, wci = L.Cout * KK;
-    for (int e = (threadIdx.x & (STEM_HT - 1)); e < total; e += STEM_HT) {
-        const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
-        int pos[4], tap[4];
-        bool ok[4];
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b2 = 0; b2 < 2; ++b2) {
-                const int ky = ((oy + L.pad) & 1) + 2 * a, kx = ((ox + L.pad) & 1) + 2 * b2;
-                const int iy = ((oy + L.pad) >> 1) - a, ix = ((ox + L.pad) >> 1) - b2;
-                const bool v = ky < L.k && kx < L.k && iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
-                ok[a * 2 + b2] = v;
-                pos[a * 2 + b2] = v ? iy * L.Win + ix : 0;
-                tap[a * 2 + b2] = v ? co * KK + ky * L.k + kx : 0;
-            }
-        float acc[STEM_S];
-        const float b = L.b ? __ldg(L.b + co) : 0.f;
-#pragma unroll
-        for (int s = 0; s < STEM_S; ++s) acc[s] = b;
-#pragma unroll 2
-        for (int ci = 0; ci < L.Cin; ++ci) {
-            const float* wp = wsm + ci * wci;
-            const float* ip = in + ci * HWi;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float wv = ok[t] ? wp[tap[t]] : 0.f;
-                const float* q = ip + pos[t];
-#pragma unroll
-                for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(q[s * in_pitch], wv, acc[s]);
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < STEM_S; ++s) outp[s * out_pitch + e] = acc[s];
-    }
-}
-
-// v_out[s][o] = act((W v_in[s] + b) * scale + shift)
-__device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* wsm, const float* in, float* outp, int in_pitch,
-                                        int out_pitch) {
-    const int ht = threadIdx.x & (STEM_HT - 1), lane = ht & 31, warp = ht >> 5;
-    if (L.in >= 64) {                                   // long rows: one warp per output, lanes over k
-        for (int o = warp; o < L.out; o += STEM_HT / 32) {
-            float acc[STEM_S];
-#pragma unroll
-            for (int s = 0; s < STEM_S; ++s) acc[s] = 0.f;
-            for (int k = lane; k < L.in; k += 32) {
-                const float wv = wsm[o * L.in + k];
-#pragma unroll
-                for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(in[s * in_pitch + k], wv, acc[s]);
-            }
-#pragma unroll
-            for (int s = 0; s < STEM_S; ++s) acc[s] = warp_sum(acc[s]);
-            if (lane < STEM_S) {
-                float v = acc[0];
-#pragma unroll
-                for (int s = 1; s < STEM_S; ++s) if (lane == s) v = acc[s];
-                v += L.b ? __ldg(L.b + o) : 0.f;
-                if (L.scale) v = fmaf(v, __ldg(L.scale + o), __ldg(L.shift + o));
-                outp[lane * out_pitch + o] = L.relu ? fmaxf(v, 0.f) : v;
-            }
-        }
+template <int COB>
+__device__ __forceinline__ void stem_ldw(const float* p, float (&w)[COB]) {
+    if constexpr (COB == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
     } else {
-        for (int o = ht; o < L.out; o += STEM_HT) {
-            float acc[STEM_S];
-            const float b = L.b ? __ldg(L.b + o) : 0.f;
 #pragma unroll
-            for (int s = 0; s < STEM_S; ++s) acc[s] = b;
-            for (int k = 0; k < L.in; ++k) {
-                const float wv = wsm[o * L.in + k];
-#pragma unroll
-                for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(in[s * in_pitch + k], wv, acc[s]);
-            }
-#pragma unroll
-            for (int s = 0; s < STEM_S; ++s) {
-                float v = acc[s];
-                if (L.scale) v = fmaf(v, __ldg(L.scale + o), __ldg(L.shift + o));
-                outp[s * out_pitch + o] = L.relu ? fmaxf(v, 0.f) : v;
-            }
-        }
+        for (int j = 0; j < COB; ++j) w[j] = p[j];
     }
 }
 
-// transposed convolution (gather form, padding), raw output + bias
-__device__ __forceinline__ void stem_up(const CaeStemUp& L, const float* wsm, const float* in, float* outp, int in_pitch,
-                                        int out_pitch) {
-    const int HWo = L.Hout * L.Wout, total = L.Cout * HWo, KK = L.k * L.k;
-    for (int e = (threadIdx.x & (STEM_HT - 1)); e < total; e += STEM_HT) {
-        const int co = e / HWo, r = e - co * HWo, oy = r / L.Wout, ox = r - oy * L.Wout;
-        float acc[STEM_S];
-        const float b = L.b ? __ldg(L.b + co) : 0.f;
+// strided convolution with padding, BN(eval) + ReLU; K > 0: compile-time kernel size (taps unrolled, bounds as per-thread masks
+// computed once per item), K == 0: any kernel size (run-time loops)
+template <int K, int COB>
+__device__ __forceinline__ void stem_conv(const CaeStemConv& L, const float* wsm, const float* in, float* outp) {
+    const int k = K ? K : L.k, KK = k * k;
+    const int HWo = L.Hout * L.Wout, HWi = L.Hin * L.Win, total = (L.Cout / COB) * HWo * STEM_ST;
+    for (int i = threadIdx.x; i < total; i += STEM_NT) {
+        const int s = i % STEM_ST, rest = i / STEM_ST, pos = rest % HWo, co0 = (rest / HWo) * COB;
+        const int oy = pos / L.Wout, ox = pos - oy * L.Wout;
+        const int iy0 = oy * L.stride - L.pad, ix0 = ox * L.stride - L.pad;
+        float acc[COB];
 #pragma unroll
-        for (int s = 0; s < STEM_S; ++s) acc[s] = b;
-        for (int ky = 0; ky < L.k; ++ky) {
-            const int ty = oy + L.pad - ky;
-            if (ty < 0 || ty % L.stride) continue;
-            const int iy = ty / L.stride;
-            if (iy >= L.Hin) continue;
-            for (int kx = 0; kx < L.k; ++kx) {
-                const int tx = ox + L.pad - kx;
-                if (tx < 0 || tx % L.stride) continue;
-                const int ix = tx / L.stride;
-                if (ix >= L.Win) continue;
-                const float* wp = wsm + co * KK + ky * L.k + kx;                    // + ci * Cout * KK
-                const float* q = in + iy * L.Win + ix;                              // + ci * Hin * Win
-#pragma unroll 4
-                for (int ci = 0; ci < L.Cin; ++ci) {
-                    const float wv = wp[ci * L.Cout * KK];
+        for (int j = 0; j < COB; ++j) acc[j] = L.b ? __ldg(L.b + co0 + j) : 0.f;
+        const float* ip0 = in + s;
+        const float* wp0 = wsm + co0;
+        if constexpr (K > 0) {
+            int off[K * K];
+            bool ok[K * K];
 #pragma unroll
-                    for (int s = 0; s < STEM_S; ++s) acc[s] = fmaf(q[s * in_pitch + ci * L.Hin * L.Win], wv, acc[s]);
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const int iy = iy0 + ky, ix = ix0 + kx;
+                    ok[ky * K + kx] = iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
+                    off[ky * K + kx] = ok[ky * K + kx] ? (iy * L.Win + ix) * STEM_ST : 0;
+                }
+#pragma unroll 2
+            for (int ci = 0; ci < L.Cin; ++ci) {
+                const float* ip = ip0 + ci * HWi * STEM_ST;
+                const float* wp = wp0 + ci * KK * L.Cout;
+#pragma unroll
+                for (int t = 0; t < K * K; ++t) {
+                    const float x = ok[t] ? ip[off[t]] : 0.f;
+                    float w[COB];
+                    stem_ldw<COB>(wp + t * L.Cout, w);
+#pragma unroll
+                    for (int j = 0; j < COB; ++j) acc[j] = fmaf(x, w[j], acc[j]);
+                }
+            }
+        } else {
+            for (int ci = 0; ci < L.Cin; ++ci)
+                for (int ky = 0; ky < k; ++ky) {
+                    const int iy = iy0 + ky;
+                    if (iy < 0 || iy >= L.Hin) continue;
+                    for (int kx = 0; kx < k; ++kx) {
+                        const int ix = ix0 + kx;
+                        if (ix < 0 || ix >= L.Win) continue;
+                        const float x = ip0[(ci * HWi + iy * L.Win + ix) * STEM_ST];
+                        float w[COB];
+                        stem_ldw<COB>(wp0 + (ci * KK + ky * k + kx) * L.Cout, w);
+#pragma unroll
+                        for (int j = 0; j < COB; ++j) acc[j] = fmaf(x, w[j], acc[j]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < COB; ++j) outp[stem_idx(s, (co0 + j) * HWo + pos)] = stem_bn_relu(acc[j], L.scale, L.shift, co0 + j);
+    }
+}
+
+// transposed convolution (gather form, padding), raw output + bias.  S2: stride 2 and k <= 4 - every output pixel has at most
+// 2 x 2 taps (ky = (oy + pad) mod 2 + 2a), located once per item; otherwise run-time loops with a modulo per tap.
+template <bool S2, int COB>
+__device__ __forceinline__ void stem_up(const CaeStemUp& L, const float* wsm, const float* in, float* outp) {
+    const int KK = L.k * L.k, HWo = L.Hout * L.Wout, HWi = L.Hin * L.Win, total = (L.Cout / COB) * HWo * STEM_ST;
+    for (int i = threadIdx.x; i < total; i += STEM_NT) {
+        const int s = i % STEM_ST, rest = i / STEM_ST, pos = rest % HWo, co0 = (rest / HWo) * COB;
+        const int oy = pos / L.Wout, ox = pos - oy * L.Wout;
+        float acc[COB];
+#pragma unroll
+        for (int j = 0; j < COB; ++j) acc[j] = L.b ? __ldg(L.b + co0 + j) : 0.f;
+        const float* ip0 = in + s;
+        const float* wp0 = wsm + co0;
+        if constexpr (S2) {
+            int off[4], tap[4];
+            bool ok[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    const int ky = ((oy + L.pad) & 1) + 2 * a, kx = ((ox + L.pad) & 1) + 2 * b2;
+                    const int iy = ((oy + L.pad) >> 1) - a, ix = ((ox + L.pad) >> 1) - b2;
+                    const bool v = ky < L.k && kx < L.k && iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
+                    ok[a * 2 + b2] = v;
+                    off[a * 2 + b2] = v ? (iy * L.Win + ix) * STEM_ST : 0;
+                    tap[a * 2 + b2] = v ? (ky * L.k + kx) * L.Cout : 0;
+                }
+#pragma unroll 2
+            for (int ci = 0; ci < L.Cin; ++ci) {
+                const float* ip = ip0 + ci * HWi * STEM_ST;
+                const float* wp = wp0 + ci * KK * L.Cout;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float x = ok[t] ? ip[off[t]] : 0.f;
+                    float w[COB];
+                    stem_ldw<COB>(wp + tap[t], w);
+#pragma unroll
+                    for (int j = 0; j < COB; ++j) acc[j] = fmaf(x, w[j], acc[j]);
+                }
+            }
+        } else {
+            for (int ky = 0; ky < L.k; ++ky) {
+                const int ty = oy + L.pad - ky;
+                if (ty < 0 || ty % L.stride) continue;
+                const int iy = ty / L.stride;
+                if (iy >= L.Hin) continue;
+                for (int kx = 0; kx < L.k; ++kx) {
+                    const int tx = ox + L.pad - kx;
+                    if (tx < 0 || tx % L.stride) continue;
+                    const int ix = tx / L.stride;
+                    if (ix >= L.Win) continue;
+                    for (int ci = 0; ci < L.Cin; ++ci) {
+                        const float x = ip0[(ci * HWi + iy * L.Win + ix) * STEM_ST];
+                        float w[COB];
+                        stem_ldw<COB>(wp0 + (ci * KK + ky * L.k + kx) * L.Cout, w);
+#pragma unroll
+                        for (int j = 0; j < COB; ++j) acc[j] = fmaf(x, w[j], acc[j]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int s = 0; s < STEM_S; ++s) outp[s * out_pitch + e] = acc[s];
+        for (int j = 0; j < COB; ++j) outp[stem_idx(s, (co0 + j) * HWo + pos)] = acc[j];
+    }
+}
+
+// v_out[o][s] = act((W v_in[.][s] + b) * scale + shift): item = (s, o)
+__device__ __forceinline__ void stem_fc(const CaeStemFc& L, const float* wsm, const float* in, float* outp) {
+    for (int i = threadIdx.x; i < L.out * STEM_ST; i += STEM_NT) {
+        const int s = i % STEM_ST, o = i / STEM_ST;
+        const float* wp = wsm + o * L.in;
+        const float* ip = in + s;
+        float a0 = L.b ? __ldg(L.b + o) : 0.f, a1 = 0.f;
+        int k = 0;
+        for (; k + 1 < L.in; k += 2) {
+            a0 = fmaf(ip[k * STEM_ST], wp[k], a0);
+            a1 = fmaf(ip[(k + 1) * STEM_ST], wp[k + 1], a1);
+        }
+        if (k < L.in) a0 = fmaf(ip[k * STEM_ST], wp[k], a0);
+        float v = a0 + a1;
+        if (L.scale) v = fmaf(v, __ldg(L.scale + o), __ldg(L.shift + o));
+        outp[stem_idx(s, o)] = L.relu ? fmaxf(v, 0.f) : v;
     }
 }
 
@@ -247,21 +214,31 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
     const long long xbase = src_cursor_offset(a.x);
     const int N = xv.N;
     float* wsm = sm + m.wbuf;
-    const int h = tid / STEM_HT;                           // thread half -> samples h * STEM_S ..
-    // Layer weights go through shared memory (with the SM carved out for activations the L1 keeps almost nothing, and weight
-    // loads that miss it cost an L2 round trip per tap).  When everything fits they are staged ONCE per CTA (`resident`);
-    // otherwise layer by layer into one buffer, as the first version of this kernel did for every pass of 4 samples.
-    auto stage = [&](float* dst, const float* w, int n) {
-        for (int e = tid; e < n; e += STEM_NT) dst[e] = __ldg(w + e);
+    // Layer weights go through shared memory, re-laid-out to [ci][tap][co] for the conv / up layers.  When everything fits
+    // they are staged ONCE per CTA (`resident`); otherwise layer by layer into one buffer.
+    // kind 0: conv weights [co][ci][KK]; 1: transposed-conv weights [ci][co][KK]; 2: fc weights (copied as they are)
+    auto stage = [&](float* dst, const float* w, int kind, int Cout, int Cin, int KK) {
+        const int n = Cout * Cin * KK;
+        for (int e = tid; e < n; e += STEM_NT) {
+            int d = e;
+            if (kind == 0) {
+                const int co = e / (Cin * KK), r = e - co * Cin * KK;          // r = ci * KK + t
+                d = r * Cout + co;
+            } else if (kind == 1) {
+                const int ci = e / (Cout * KK), r = e - ci * Cout * KK, co = r / KK, t = r - co * KK;
+                d = (ci * KK + t) * Cout + co;
+            }
+            dst[d] = __ldg(w + e);
+        }
     };
     if (m.resident) {
-        for (int l = 0; l < S.n_conv; ++l) stage(sm + m.w_conv[l], S.conv[l].w, S.conv[l].Cout * S.conv[l].Cin * S.conv[l].k * S.conv[l].k);
-        for (int l = 0; l < S.n_fc; ++l) stage(sm + m.w_fc[l], S.fc[l].w, S.fc[l].in * S.fc[l].out);
-        for (int j = 0; j < S.n_up; ++j) stage(sm + m.w_up[j], S.up[j].w, S.up[j].Cin * S.up[j].Cout * S.up[j].k * S.up[j].k);
+        for (int l = 0; l < S.n_conv; ++l) stage(sm + m.w_conv[l], S.conv[l].w, 0, S.conv[l].Cout, S.conv[l].Cin, S.conv[l].k * S.conv[l].k);
+        for (int l = 0; l < S.n_fc; ++l) stage(sm + m.w_fc[l], S.fc[l].w, 2, S.fc[l].out, S.fc[l].in, 1);
+        for (int j = 0; j < S.n_up; ++j) stage(sm + m.w_up[j], S.up[j].w, 1, S.up[j].Cout, S.up[j].Cin, S.up[j].k * S.up[j].k);
     }
-    auto weights = [&](int off, const float* w, int n) -> const float* {
+    auto weights = [&](int off, const float* w, int kind, int Cout, int Cin, int KK) -> const float* {
         if (m.resident) return sm + off;
-        stage(wsm, w, n);
+        stage(wsm, w, kind, Cout, Cin, KK);
         __syncthreads();
         return wsm;
     };
@@ -276,24 +253,22 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
                 const ChanCoef kc = load_coef(a.x, c);
                 v = src_value(a.x, xbase + (long long)(n0 + s) * xv.sN + (long long)c * xv.sC + (long long)yy * xv.ld + xx, kc);
             }
-            sm[m.in0 + e] = v;
+            sm[m.in0 + stem_idx(s, r)] = v;
         }
         __syncthreads();
         // ---- encoder
         const float* cur = sm + m.in0;
-        int cur_pitch = in_elems;
         for (int l = 0; l < S.n_conv; ++l) {
             const CaeStemConv& L = S.conv[l];
-            const int op = L.Cout * L.Hout * L.Wout;
-            const float* w = weights(m.w_conv[l], L.w, L.Cout * L.Cin * L.k * L.k);
-            const float* in = cur + h * STEM_S * cur_pitch;
-            float* outp = sm + m.enc[l] + h * STEM_S * op;
-            if (L.k == 3) stem_conv_k<3>(L, w, in, outp, cur_pitch, op);
-            else if (L.k == 4) stem_conv_k<4>(L, w, in, outp, cur_pitch, op);
-            else stem_conv(L, w, in, outp, cur_pitch, op);
+            const float* w = weights(m.w_conv[l], L.w, 0, L.Cout, L.Cin, L.k * L.k);
+            float* outp = sm + m.enc[l];
+            const bool blk = L.Cout % STEM_COB == 0;
+            if (L.k == 3 && blk) stem_conv<3, STEM_COB>(L, w, cur, outp);
+            else if (L.k == 4 && blk) stem_conv<4, STEM_COB>(L, w, cur, outp);
+            else if (L.k == 3) stem_conv<3, 1>(L, w, cur, outp);
+            else stem_conv<0, 1>(L, w, cur, outp);
             __syncthreads();
-            cur = sm + m.enc[l];
-            cur_pitch = op;
+            cur = outp;
         }
         // ---- fc stack (ping-pong va / vb)
         float* va = sm + m.va;
@@ -301,11 +276,10 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
         for (int l = 0; l < S.n_fc; ++l) {
             const CaeStemFc& L = S.fc[l];
             float* dst = (l & 1) ? vb : va;
-            const float* w = weights(m.w_fc[l], L.w, L.in * L.out);
-            stem_fc(L, w, cur + h * STEM_S * cur_pitch, dst + h * STEM_S * L.out, cur_pitch, L.out);
+            const float* w = weights(m.w_fc[l], L.w, 2, L.out, L.in, 1);
+            stem_fc(L, w, cur, dst);
             __syncthreads();
             cur = dst;
-            cur_pitch = L.out;
         }
         // ---- decoder blocks
         for (int j = 0; j < S.n_up; ++j) {
@@ -313,21 +287,23 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
             const int C = L.Cout, HW = L.Hout * L.Wout, yp = C * HW, cp = 2 * yp;
             float* y = sm + m.y;
             float* cat = sm + m.cat;
-            const float* w = weights(m.w_up[j], L.w, L.Cin * L.Cout * L.k * L.k);
-            if (L.stride == 2 && L.k <= 4) stem_up_s2(L, w, cur + h * STEM_S * cur_pitch, y + h * STEM_S * yp, cur_pitch, yp);
-            else stem_up(L, w, cur + h * STEM_S * cur_pitch, y + h * STEM_S * yp, cur_pitch, yp);
+            const float* w = weights(m.w_up[j], L.w, 1, L.Cout, L.Cin, L.k * L.k);
+            const bool blk = L.Cout % STEM_COB == 0, s2 = L.stride == 2 && L.k <= 4;
+            if (s2 && blk) stem_up<true, STEM_COB>(L, w, cur, y);
+            else if (s2) stem_up<true, 1>(L, w, cur, y);
+            else stem_up<false, 1>(L, w, cur, y);
             __syncthreads();
             float* avg = sm + m.small;                     // [ST][C]
             float* mx = avg + STEM_ST * C;                 // [ST][C]
             float* hid = mx + STEM_ST * C;                 // [ST][2][Cr]
             float* att = hid + STEM_ST * 2 * L.Cr;         // [ST][C]
             for (int e = tid; e < STEM_ST * C; e += STEM_NT) {
-                const int s = e / C, c = e - s * C;
-                const float* q = y + s * yp + c * HW;
+                const int s = e % STEM_ST, c = e / STEM_ST;
+                const float* q = y + stem_idx(s, c * HW);
                 float sum = 0.f, mxx = -INFINITY;
-                for (int i = 0; i < HW; ++i) { sum += q[i]; mxx = fmaxf(mxx, q[i]); }
-                avg[e] = sum / (float)HW;
-                mx[e] = mxx;
+                for (int i = 0; i < HW; ++i) { const float t = q[i * STEM_ST]; sum += t; mxx = fmaxf(mxx, t); }
+                avg[s * C + c] = sum / (float)HW;
+                mx[s * C + c] = mxx;
             }
             __syncthreads();
             for (int e = tid; e < STEM_ST * 2 * L.Cr; e += STEM_NT) {
@@ -351,9 +327,9 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
             const bool last = j == S.n_up - 1;
             for (int e = tid; e < STEM_ST * cp; e += STEM_NT) {
                 const int s = e / cp, r = e - s * cp, c2 = r / HW, i = r - c2 * HW;
-                float v = c2 < C ? att[s * C + c2] * y[s * yp + r] : skip[s * yp + (r - yp)];
+                float v = c2 < C ? att[s * C + c2] * y[stem_idx(s, r)] : skip[stem_idx(s, r - yp)];
                 v = stem_bn_relu(v, L.scale, L.shift, c2);
-                cat[e] = v;
+                cat[stem_idx(s, r)] = v;
                 if (last && n0 + s < N) {
                     const int yy = i / L.Wout, xx = i - yy * L.Wout;
                     a.out.p[(long long)(n0 + s) * a.out.sN + (long long)c2 * a.out.sC + (long long)yy * a.out.ld + xx] = v;
@@ -361,7 +337,6 @@ __global__ void __launch_bounds__(STEM_NT) k_unet_stem_eval(const StemArgs a) {
             }
             __syncthreads();
             cur = cat;
-            cur_pitch = cp;
         }
     }
 }

@@ -118,6 +118,33 @@ class DPContext:
             dist.broadcast(t, src=src, group=self.group)
 
 
+def bind_to_local_numa(device_index):
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated
+    (cudaHostAlloc places the pages on the node of the calling thread).  With one process per GPU and every rank's staging
+    buffers on node 0, the host-fed step of 8 ranks shared one node's memory controllers (round 1: e2e scaling 0.51 at 8
+    GPUs).  Best effort: returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:       # no sysfs entry / no pci ids in this torch build / not permitted
+        return None
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from the torchrun environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR /
     MASTER_PORT): one process per GPU, NCCL when CUDA is present (gloo otherwise: CPU tests).  No-op outside torchrun or
@@ -135,6 +162,7 @@ def init_from_env(backend=None):
         if backend == "nccl":
             local = int(os.environ.get("LOCAL_RANK", "0"))
             torch.cuda.set_device(local)
+            bind_to_local_numa(local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
             dist.init_process_group(backend)

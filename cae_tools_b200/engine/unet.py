@@ -132,8 +132,8 @@ class UNetEngine(ConvAEEngine):
         return ops.make_epilogue(ops.EPI_PLAIN, bias=bias)
 
     # eval mode: every layer before the last one in ONE launch (unet_stem_eval.cu).  Measured (B200, shipped spec, whole score
-    # batch incl. the head, tools/eval_stem_probe.py): batch 256 - 90 us against 156 us for the 11-launch chain; 1024 - 144
-    # against 296; 4096 - 540 against 825.  (Round 1's version of the kernel lost to the chain at 4096 - 577 us for the stem
+    # batch incl. the head, tools/eval_stem_probe.py): batch 256 - 80 us against 155 us for the 11-launch chain; 1024 - 135
+    # against 294; 4096 - 492 against 820 (stem 190 + head 304).  (Round 1's version of the kernel lost to the chain at 4096 - 577 us for the stem
     # alone - and was capped at 2048 samples; its run-time tap loops were replaced by compile-time-K ones.)
     use_fused_stem = True
     fused_stem_max_batch = 1 << 30

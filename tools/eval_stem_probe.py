@@ -45,3 +45,5 @@ for B in a.batches:
         ms = e0.elapsed_time(e1) / a.reps
         print(f"batch {B} {'fused eval stem' if fused else 'per-layer chain'}: {ms * 1e3:.1f} us/batch, {B / ms * 1e3 / 1e6:.2f} M images/s, "
               f"launches {prog.n_launches}", flush=True)
+        if fused:
+            print("   " + ", ".join(f"{n} {t * 1e3:.1f} us" for n, t in prog.profile(reps=5)))

@@ -22,8 +22,13 @@ from .._lib import require_cuda
 
 class LinearEngine:
 
-    def __init__(self, module, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, device="cuda"):
+    def __init__(self, module, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, device="cuda", grad_hook=None,
+                 count_scale=1.0):
+        """grad_hook / count_scale: data parallelism (engine/dp.py) - every rank runs its share of each batch, the loss and
+        its gradient are scaled by count_scale = n_local / n_global, grad_hook SUM-all-reduces the flat gradient arena
+        before the optimiser step (so the summed gradients and the summed losses are those of the global batch)"""
         require_cuda()
+        self.grad_hook, self.count_scale = grad_hook, float(count_scale)
         self.device = torch.device(device)
         self.module = module.to(self.device)
         self.lin = module.linear[1]
@@ -81,12 +86,16 @@ class LinearEngine:
             yhat, dz = b["yhat"][:N], b["dz"][:N]
             self._forward(x, yhat)
             ops.mse(yhat, y, y.numel(), self._partials, self._ticket, data.losses[i:i + 1])
-            b["kp"].fill_(2.0 / y.numel())
-            b["kn"].fill_(-2.0 / y.numel())
+            if self.count_scale != 1.0:
+                data.losses[i:i + 1].mul_(self.count_scale)
+            b["kp"].fill_(2.0 * self.count_scale / y.numel())
+            b["kn"].fill_(-2.0 * self.count_scale / y.numel())
             ops.ew_epilogue(ops.make_src(yhat, t1=y.contiguous(), k0=b["kp"], k1=b["kn"]), ops.view4(dz),
                             ops.make_epilogue(ops.EPI_PLAIN))
             # dW[o][k] = sum_n dz[n][o] x[n][k] ; db[o] = sum_n dz[n][o]
             ops.gemm(O, K, N, dz, 1, O, x, K, 1, G[id(self.lin.weight)], K, 1, rowsum_A=G[id(self.lin.bias)])
+            if self.grad_hook is not None:
+                self.grad_hook(self.grads)
             ops.adam(self.arena, self.grads, self.adam_m, self.adam_v, self.n_params, self.lr, self.betas[0],
                      self.betas[1], self.eps, self.weight_decay, False, 1.0, self.step_count)
             ops.step_advance(self.step_count, None, 1)
@@ -97,6 +106,8 @@ class LinearEngine:
             yhat = self._buffers(x.shape[0])["yhat"][:x.shape[0]]
             self._forward(x, yhat)
             ops.mse(yhat, y, y.numel(), self._partials, self._ticket, data.losses[i:i + 1])
+            if self.count_scale != 1.0:
+                data.losses[i:i + 1].mul_(self.count_scale)
         return data.losses
 
     def score_batches(self, data, sink):

@@ -79,7 +79,8 @@ class LinearModel(ConvAEModel):
     def _make_engine(self, device, dp=None):
         from ..engine.linear import LinearEngine
         if dp is not None:
-            raise NotImplementedError("LinearModel: data-parallel training is not implemented")
+            return LinearEngine(self.weights, lr=self.lr, weight_decay=self.weight_decay, device=device,
+                                grad_hook=dp.allreduce_grads, count_scale=1.0 / dp.world)
         return LinearEngine(self.weights, lr=self.lr, weight_decay=self.weight_decay, device=device)
 
     def train(self, input_variables, output_variable, training_ds, testing_ds, model_path="", training_paths="",
@@ -102,20 +103,31 @@ class LinearModel(ConvAEModel):
         start = time.time()
         train_order = shuffled_order(len(train_ds), self.batch_size)
         test_order = shuffled_order(len(test_ds), self.batch_size)
-        self.engine = eng = self._make_engine(device)
+        # data parallel (torch.distributed initialised with > 1 rank): as ConvAEModel.train - every rank takes its contiguous
+        # share of every batch, one SUM all-reduce of the gradients per step, rank 0 saves / evaluates
+        from ..engine.dp import DPContext, shard_batches
+        dp = DPContext.from_env()
+        local_batch = self.batch_size
+        if dp is not None:
+            train_order, local_batch, _ = shard_batches(train_order, self.batch_size, dp.rank, dp.world)
+            test_order, _, _ = shard_batches(test_order, self.batch_size, dp.rank, dp.world)
+        self.engine = eng = self._make_engine(device, dp)
+        if dp is not None:
+            dp.broadcast_([eng.arena])
+        gather = (lambda t: dp.reduce_losses(t)) if dp is not None else (lambda t: t)
         train_data = eng.bind(torch.from_numpy(train_ds.input_array(train_order)),
-                              torch.from_numpy(train_ds.output_array(train_order)), self.batch_size)
+                              torch.from_numpy(train_ds.output_array(train_order)), local_batch)
         test_data = eng.bind(torch.from_numpy(test_ds.input_array(test_order)),
-                             torch.from_numpy(test_ds.output_array(test_order)), self.batch_size)
+                             torch.from_numpy(test_ds.output_array(test_order)), local_batch)
         train_loss = test_loss = 0.0
         last = self.nr_epochs - 1
         for epoch in range(self.nr_epochs):
             losses = eng.train_epoch(train_data)
             report = (epoch % self.test_interval == 0)
             if report or epoch == last:
-                train_loss = float(np.mean(losses.cpu().numpy()))
+                train_loss = float(np.mean(gather(losses).cpu().numpy()))
             if report:
-                test_loss = float(np.mean(eng.test_epoch(test_data).cpu().numpy()))
+                test_loss = float(np.mean(gather(eng.test_epoch(test_data)).cpu().numpy()))
                 self.history["train_loss"].append(train_loss)
                 self.history["test_loss"].append(test_loss)
                 if self.verbose:
@@ -125,12 +137,15 @@ class LinearModel(ConvAEModel):
         if self.verbose:
             print("elapsed:" + str(time.time() - start))
         self.weights.eval()
-        if self.db:
+        lead = dp is None or dp.rank == 0
+        if self.db and lead:
             self.db.add_training_result(self.get_model_id(), self.DB_TYPE, output_variable, input_variables,
                                         self.summary(), model_path, training_paths, train_loss, testing_paths,
                                         test_loss, self.get_parameters(), {})
-        if model_path:
+        if model_path and lead:
             self.save(model_path)
+        if not lead:
+            return
         metrics = {"test": self.evaluate(test_ds, device), "train": self.evaluate(train_ds, device)}
         if self.verbose:
             self.dump_metrics("Test Metrics", metrics["test"])

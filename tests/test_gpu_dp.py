@@ -144,3 +144,45 @@ def test_two_rank_unet_fused_stem_equals_single_gpu(tmp_path):
         if k.endswith("running_var") or a.dtype.kind != "f":
             continue
         assert np.abs(a - b).max() <= 2e-4 * max(np.abs(b).max(), 1e-3), k
+
+
+def _linear_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from cae_tools_b200.models.linear_model import LinearModel
+    from oracle import datagen
+    tr, te = datagen.circle_datasets(48, 16, output_size=(64, 64))
+    torch.manual_seed(77)
+    m = LinearModel(batch_size=16, nr_epochs=3, test_interval=1, lr=1e-3, weight_decay=1e-5)
+    m.verbose = False
+    m.train(["lowres"], "hires", tr, te)          # DPContext.from_env(): every batch of 16 is split 8 + 8
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "dpl.npz"), train=np.array(m.history["train_loss"]), test=np.array(m.history["test_loss"]),
+                 w=m.weights.linear[1].weight.detach().cpu().numpy(), b=m.weights.linear[1].bias.detach().cpu().numpy())
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_linear_model_equals_single_gpu(tmp_path):
+    """LinearModel.train under data parallelism: batches of 16 split 8 + 8 over two ranks, gradients
+    SUM-all-reduced - same loss history and weights as the single-process run"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_linear_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = dict(np.load(os.path.join(str(tmp_path), "dpl.npz")))
+    from cae_tools_b200.models.linear_model import LinearModel
+    from oracle import datagen
+    tr, te = datagen.circle_datasets(48, 16, output_size=(64, 64))
+    torch.manual_seed(77)
+    m = LinearModel(batch_size=16, nr_epochs=3, test_interval=1, lr=1e-3, weight_decay=1e-5)
+    m.verbose = False
+    m.train(["lowres"], "hires", tr, te)
+    np.testing.assert_allclose(got["train"], m.history["train_loss"], rtol=2e-5)
+    np.testing.assert_allclose(got["test"], m.history["test_loss"], rtol=2e-5)
+    w = m.weights.linear[1].weight.detach().cpu().numpy()
+    assert np.abs(got["w"] - w).max() <= 1e-4 * np.abs(w).max()
+    assert np.abs(got["b"] - m.weights.linear[1].bias.detach().cpu().numpy()).max() <= 1e-4 * np.abs(w).max()

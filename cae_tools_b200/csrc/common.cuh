@@ -58,6 +58,22 @@ __device__ __forceinline__ float cae_fast_sigmoid(float v) {
     return r;
 }
 
+// Operand split for the tensor-core paths: x = hi + lo with hi = x ROUNDED to TF32 (round-to-nearest, so |lo| <= 2^-12 |x|
+// instead of 2^-11 with truncation) and lo itself rounded to TF32 (the tensor core would otherwise truncate its low bits).
+// What the split drops is then <= 2^-24 |x| per operand; with the four products hi*hi + hi*lo + lo*hi + lo*lo a product is
+// accurate to ~1.2e-7 relative - within 2x of an fp32 FMA.  (Truncating hi and dropping lo*lo left ~7e-7 per product: on the
+// ill-conditioned sums of the config-4 backward pass the tensor-core layers' gradients sat 4.5e-3 from float64, 20x
+// torch fp32's own distance - tests/test_gpu_conv4.py::test_config4_full_batch_step_vs_float64_on_device.)
+__device__ __forceinline__ float tf32_rn(float v) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
+    hi = tf32_rn(v);
+    lo = tf32_rn(v - hi);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

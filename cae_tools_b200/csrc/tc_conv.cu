@@ -24,8 +24,7 @@ extern "C" int cae_tc_gemm(const CaeTcGemm* g, void* stream);
 namespace {
 
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    lo = v - hi;
+    tf32_split(v, hi, lo);
 }
 
 // ---- forward operand: NCHW source (with its on-load transform) -> [m, ci] hi / lo ------------------------------------

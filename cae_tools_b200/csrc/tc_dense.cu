@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(CAE_NT) k_td_split(const float* __restrict__ X
             v = fmaf(v, __ldg(k0 + c), __ldg(k2 + c));
         }
         if (relu) v = fmaxf(v, 0.f);
-        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        float h, l;
+        tf32_split(v, h, l);
         hi[o * ld + i] = h;
-        lo[o * ld + i] = v - h;
+        lo[o * ld + i] = l;
     }
 }
 

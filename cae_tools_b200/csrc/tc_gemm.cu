@@ -3,10 +3,17 @@
 //   C[m, n] = sum_k A[m, k] * B[n, k]           fp32 in, fp32 out, fp32 accumulation in tensor memory
 //
 // Precision: the tensor cores multiply TF32 (10-bit mantissa).  To keep the path's 1e-4 parity bar the operands arrive
-// PRE-SPLIT (cae_tc_split / the conv-specific producers in tc_conv.cu): x = hi + lo, hi = x with the low 13 mantissa
-// bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32; the hardware truncates it to TF32 again,
-// relative error 2^-11 * 2^-11).  Three MMAs per K step - hi*hi + hi*lo + lo*hi - give ~2^-21 relative error per product
-// ("3xTF32").  lo == NULL for both operands selects plain 1xTF32 (one MMA; ~1e-3 relative).
+// PRE-SPLIT (cae_tc_split / the conv-specific producers in tc_conv.cu): x = hi + lo, hi = x ROUNDED to TF32, lo = x - hi
+// rounded to TF32 (common.cuh: tf32_split; what the split drops is <= 2^-22 |x|, unbiased).  Three MMAs per K step -
+// lo*hi + hi*lo + hi*hi ("3xTF32"; the dropped lo*lo is <= 2^-24 of the product).  lo == NULL for both operands selects plain
+// 1xTF32 (one MMA; ~1e-3 relative).
+// Accumulation: the tensor core TRUNCATES its fp32 accumulator once per MMA.  Left to run over the whole K range that
+// is a bias growing linearly with K (3e-6 of the max-norm at K = 1000, ~10x an fp32 FMA chain) - harmless per element, but
+// BASELINE configs[3] at batch 128 amplifies rounding noise ~2000x on its way back through the decoder (torch's own
+// fp32 gradients sit 2e-4 from float64 there) and the tensor-core layers' gradients ended up 4.5e-3 away.  The TMEM
+// accumulator therefore only ever holds a CHUNK of KB_PER_CHUNK K blocks: two TMEM accumulators alternate, and while the
+// MMA issuer fills one, the epilogue warps drain the other into fp32 REGISTER accumulators with round-to-nearest adds
+// (the "promotion" scheme of fp8 GEMMs).  Truncation then happens at the magnitude of a 64-element partial sum only.
 //
 // Operands may be K-major (K contiguous: A[m*lda + k]) or MN-major (M or N contiguous: A[k*lda + m]); the weight
 // gradient of a transposed convolution contracts over positions, which is the LEADING dimension of both of its
@@ -15,7 +22,8 @@
 // Structure (one 128 x BN output tile per CTA, BK = 32 floats = one 128-byte swizzle row):
 //   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor.2d -> 128B-swizzled shared-memory stages, mbarrier expect_tx
 //   warp 1 (one lane)  MMA issuer:   tcgen05.mma.cta_group::1.kind::tf32, accumulator in TMEM, tcgen05.commit -> mbarriers
-//   warps 2-5          epilogue:     tcgen05.ld (32 lanes x 32 columns per instruction) -> registers -> global
+//   warps 2-9          epilogue:     per chunk tcgen05.ld (32 lanes x 32 columns per instruction) -> += registers; -> global
+//                                    (warp w owns TMEM lanes [32 (w % 4), +32) and one half of the BN columns)
 // Split-K (gridDim.z) writes partial tiles to C + z * split_stride; the caller reduces them in a fixed order.
 //
 // Replaces: the cuBLAS/cuDNN GEMMs behind torch.nn.ConvTranspose2d forward/backward for the fat decoder layers
@@ -29,7 +37,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;                      // floats per K block = 128 bytes = one swizzle row
 constexpr int TILE_A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
+constexpr int KB_PER_CHUNK = 2;             // K blocks accumulated in TMEM before promotion to registers
 
 struct TcParams {
     int M, N, K;
@@ -131,15 +140,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUte
           const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
     constexpr int TILE_B_BYTES = BN * BK * 4;
     constexpr int STAGE_BYTES = 2 * TILE_A_BYTES + 2 * TILE_B_BYTES;
+    constexpr int HALF = BN / 2;                                               // columns owned by one epilogue warp
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128B swizzle atoms need 1 KB alignment
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES);
-    // bars[0..STAGES) full, [STAGES..2*STAGES) empty, [2*STAGES] accumulator ready; then the TMEM base address
+    // bars[0..STAGES) full, [STAGES..2*STAGES) empty, then accumulator full [2], accumulator drained [2]; then the TMEM base
     const uint32_t bar_full = smem_base + STAGES * STAGE_BYTES;
     const uint32_t bar_empty = bar_full + 8 * STAGES;
-    const uint32_t bar_acc = bar_empty + 8 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    const uint32_t bar_accfull = bar_empty + 8 * STAGES;
+    const uint32_t bar_accfree = bar_accfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -147,6 +158,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUte
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
     const int nkb = kb_end - kb_begin;                                         // >= 1 by construction of the grid
+    const int nchunks = (nkb + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmAh) : "memory");
@@ -161,12 +173,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUte
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_acc, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_accfull + 8 * b, 1);                 // one tcgen05.commit
+            mbar_init(bar_accfree + 8 * b, 8);                 // lane 0 of each of the 8 epilogue warps
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        // TMEM: BN fp32 accumulator columns x 128 lanes (power of two >= 32); this warp also frees them at the end
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
+        // TMEM: TWO accumulators of BN fp32 columns x 128 lanes (chunk ping-pong); this warp also frees them at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -211,55 +226,81 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUte
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
+                const int chunk = i / KB_PER_CHUNK, in_chunk = i - chunk * KB_PER_CHUNK;
+                const int buf = chunk & 1;
+                if (in_chunk == 0 && chunk >= 2) {
+                    // the epilogue warps must have drained this accumulator's previous chunk (use (chunk >> 1) - 1)
+                    mbar_wait(bar_accfree + 8 * buf, (uint32_t)(((chunk >> 1) - 1) & 1));
+                    tc_fence_after();
+                }
                 mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
+                const uint32_t acc = tmem_acc + (uint32_t)(buf * BN);
                 const uint32_t st = smem_base + s * STAGE_BYTES;
                 const uint32_t a_hi = st, a_lo = st + TILE_A_BYTES;
                 const uint32_t b_hi = st + 2 * TILE_A_BYTES, b_lo = b_hi + TILE_B_BYTES;
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
+                    const uint32_t accumulate = (in_chunk | k) != 0 ? 1u : 0u;      // a chunk starts from zero
                     const uint64_t dah = make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
                     const uint64_t dbh = make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
                     if (p.three_pass) {
                         const uint64_t dal = make_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
                         const uint64_t dbl = make_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
                         // small terms first, so they are not absorbed by an already large accumulator
-                        umma_tf32(tmem_acc, dal, dbh, idesc, (i | k) != 0);
-                        umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
-                        umma_tf32(tmem_acc, dah, dbh, idesc, 1u);
+                        umma_tf32(acc, dal, dbh, idesc, accumulate);
+                        umma_tf32(acc, dah, dbl, idesc, 1u);
+                        umma_tf32(acc, dah, dbh, idesc, 1u);
                     } else {
-                        umma_tf32(tmem_acc, dah, dbh, idesc, (i | k) != 0);
+                        umma_tf32(acc, dah, dbh, idesc, accumulate);
                     }
                 }
                 umma_commit(bar_empty + 8 * s);          // frees the stage once these MMAs have read it
+                if (in_chunk == KB_PER_CHUNK - 1 || i == nkb - 1) umma_commit(bar_accfull + 8 * buf);   // chunk complete
             }
-            umma_commit(bar_acc);                        // accumulator complete
         }
     } else {
-        // ===== epilogue: warps 2..5; a warp may only touch the TMEM lanes [32 * (warp % 4), +32) =====
-        const int q = warp & 3;
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
+        // ===== epilogue: warps 2..9; a warp may only touch the TMEM lanes [32 * (warp % 4), +32); the two warps of a lane
+        // quarter split the BN columns.  Per chunk: TMEM -> registers, release the accumulator, add (round to nearest). =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        float racc[HALF];
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) racc[j] = 0.f;
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(bar_accfull + 8 * buf, (uint32_t)((chunk >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF);
+#pragma unroll
+            for (int c = 0; c < HALF; c += 32) {
+                uint32_t v[32];
+                TC_LD32(taddr + (uint32_t)c, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 32 == HALF) {
+                    // everything of this accumulator is in registers: hand it back to the MMA issuer before the adds
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_accfree + 8 * buf) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) racc[c + j] += __uint_as_float(v[j]);
+            }
+        }
         const int row = m0 + q * 32 + lane;
-        float* crow = p.C + (long long)blockIdx.z * p.split_stride + (long long)row * p.ldc + n0;
+        const int nb = n0 + half * HALF;
+        float* crow = p.C + (long long)blockIdx.z * p.split_stride + (long long)row * p.ldc + nb;
         const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.split_stride % 4 == 0);
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
-            TC_LD32(taddr, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < p.M) {
-                if (vec_ok && n0 + c + 32 <= p.N) {
+        if (row < p.M) {
+#pragma unroll
+            for (int c = 0; c < HALF; c += 32) {
+                if (vec_ok && nb + c + 32 <= p.N) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(crow + c + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                        __uint_as_float(v[j + 3]));
+                        *reinterpret_cast<float4*>(crow + c + j) = make_float4(racc[c + j], racc[c + j + 1], racc[c + j + 2], racc[c + j + 3]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (n0 + c + j < p.N) crow[c + j] = __uint_as_float(v[j]);
+                        if (nb + c + j < p.N) crow[c + j] = racc[c + j];
                 }
             }
         }
@@ -268,7 +309,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUte
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)(2 * BN)) : "memory");
     }
 }
 
@@ -370,9 +411,10 @@ __global__ void k_tc_split(const float* __restrict__ x, float* __restrict__ hi, 
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const float v = x[i];
-        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        float h, l;
+        tf32_split(v, h, l);
         hi[i] = h;
-        lo[i] = v - h;
+        lo[i] = l;
     }
 }
 

@@ -440,7 +440,7 @@ typedef struct CaeTcGemm {
     int tile_n;
 } CaeTcGemm;
 int cae_tc_gemm(const CaeTcGemm* g, void* stream);
-/* hi = x with the low 13 mantissa bits cleared, lo = x - hi */
+/* hi = x rounded to TF32 (round to nearest), lo = x - hi rounded to TF32 */
 int cae_tc_split(const float* x, float* hi, float* lo, long long n, void* stream);
 
 /* ---- ConvTranspose2d on the tensor cores (tc_conv.cu) --------------------------------------------------------------

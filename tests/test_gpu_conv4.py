@@ -119,3 +119,68 @@ def test_config4_geometry_vs_oracle(tc, monkeypatch):
                 # above; the loss of both steps to 2e-5.)
                 assert np.median(dev) <= 1e-4 * max(np.abs(ref).max(), 1e-3) + 5e-5, k
                 assert dev.max() <= 2.0 * 1e-3 * 2 + 1e-4 * np.abs(ref).max(), k
+
+
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("batch", [128])
+def test_config4_full_batch_step_vs_float64_on_device(batch, tc, monkeypatch):
+    """BASELINE configs[3] at its FULL size (4x64x64 -> 4x1024x1024, batch 128): one optimiser step of the production schedule -
+    tcgen05 layers, tile-resident weight gradients, cp.async tile pipelines - against the oracle port evaluated in float64
+    on the same GPU (torch ops; test infrastructure only).  At this batch the BatchNorm planes hold 10^3 ... 10^8 elements and
+    the float64 evaluation is the reference: loss to 1e-5; every gradient to 1e-4 of its tensor's max-norm (north_star's bar) or
+    to twice the distance at which torch's own fp32 evaluation (cuDNN / cuBLAS, TF32 off) of the same step sits from float64."""
+    from cae_tools_b200.engine.convae import ConvAEEngine
+    from cae_tools_b200.models.decoder import Decoder
+    from cae_tools_b200.models.encoder import Encoder
+    from cae_tools_b200.models.model_sizer import create_model_spec
+    from oracle.torch_port import OracleModel
+    if not tc:
+        monkeypatch.setattr(ConvAEEngine, "TC_MIN_CIN", 1 << 30)
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * 2 ** 30:
+        pytest.skip("needs ~100 GB of free device memory for the float64 evaluation")
+    dev = torch.device("cuda")
+    spec = create_model_spec(input_size=(64, 64), input_channels=4, output_size=(1024, 1024), output_channels=4)
+    torch.manual_seed(3)
+    enc, dec = Encoder(spec.get_input_layers(), 4, 16), Decoder(spec.get_output_layers(), 4, 16)
+    esd = {k: v.detach().clone().to(dev) for k, v in enc.state_dict().items()}
+    dsd = {k: v.detach().clone().to(dev) for k, v in dec.state_dict().items()}
+    gen = torch.Generator(device=dev).manual_seed(5)
+    x = torch.rand(batch, 4, 64, 64, device=dev, generator=gen)
+    y = torch.rand(batch, 4, 1024, 1024, device=dev, generator=gen)
+    eng = ConvAEEngine(enc, dec, lr=1e-3, weight_decay=1e-5)
+    data = eng.bind(x, y, batch)
+    names = [n for n, _ in eng._program("train", data, batch).sched]
+    assert ("fwd.convT0.tc" in names) == tc and ("fwd.convT4.tc" in names) == tc and "fwd.convT5" in names
+    got_loss = float(eng.train_epoch(data).cpu()[0])
+    grads = {("enc." + k): p.grad.detach().double().cpu() for k, p in enc.named_parameters()}
+    grads.update({("dec." + k): p.grad.detach().double().cpu() for k, p in dec.named_parameters()})
+    del eng, data
+    torch.cuda.empty_cache()
+    exact = OracleModel(esd, dsd, spec.save(), zero_dead_bias_grads=True, dtype=torch.float64)
+    want_loss = float(exact.train_step(x.double(), y.double()))
+    ref64 = {(pre + k): v.grad.detach().cpu() for pre, sd in (("enc.", exact.enc), ("dec.", exact.dec)) for k, v in sd.items()
+             if v.grad is not None}
+    del exact
+    torch.cuda.empty_cache()
+    # the same step in plain fp32 torch (cuDNN / cuBLAS with TF32 off): how far does an fp32 evaluation sit from float64?
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        plain = OracleModel(esd, dsd, spec.save(), zero_dead_bias_grads=True)
+        plain_loss = float(plain.train_step(x, y))
+        ref32 = {(pre + k): v.grad.detach().double().cpu() for pre, sd in (("enc.", plain.enc), ("dec.", plain.dec))
+                 for k, v in sd.items() if v.grad is not None}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert abs(got_loss - want_loss) <= 1e-5 * want_loss, (got_loss, want_loss, plain_loss)
+    table = []
+    for k, ref in ref64.items():
+        scale = max(float(ref.abs().max()), 1e-12)
+        table.append((float((grads[k] - ref).abs().max()) / scale, float((ref32[k] - ref).abs().max()) / scale, k))
+    table.sort(reverse=True)
+    print("config 4, batch", batch, ": loss", got_loss, "float64", want_loss, "torch fp32", plain_loss)
+    for e_gpu, e_32, k in table[:12]:
+        print(f"   {k:34s} this path vs float64 {e_gpu:.2e}   torch fp32 vs float64 {e_32:.2e}")
+    for e_gpu, e_32, k in table:
+        assert e_gpu <= max(1e-4, 2.0 * e_32), (k, e_gpu, e_32)

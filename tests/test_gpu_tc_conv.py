@@ -17,6 +17,8 @@ CASES = [
     (2, 64, 8, 4, 2, 0, 6, 6),
     (2, 48, 16, 3, 2, 1, 5, 5),        # output_padding
     (5, 160, 136, 3, 2, 0, 9, 9),      # several M / N tiles, split-K weight gradient
+    (128, 1024, 512, 3, 2, 0, 3, 3),   # BASELINE configs[3], first decoder layer at the full batch
+    (128, 64, 32, 3, 2, 0, 63, 63),    # ... and the last tensor-core layer (508 k positions: 248 split-K slices)
 ]
 
 

@@ -28,7 +28,7 @@ def split(x):
 def check():
     gen = torch.Generator(device="cuda").manual_seed(1)
     for (M, N, K, splits, tn) in [(128, 128, 32, 1, 128), (128, 128, 64, 1, 128), (200, 136, 100, 1, 128), (384, 520, 1000, 3, 128),
-                                  (130, 300, 264, 2, 256)]:
+                                  (130, 300, 264, 2, 256), (256, 512, 4608, 1, 256), (256, 256, 4608, 1, 128), (256, 512, 8192, 4, 256)]:
         for a_mn, b_mn in [(0, 0), (1, 1), (0, 1), (1, 0)]:
             A, lda, Ad = operand(M, K, a_mn, gen)
             B, ldb, Bd = operand(N, K, b_mn, gen)
@@ -41,7 +41,16 @@ def check():
             got = Cb[:, :, :N].double().sum(0)
             want = Ad @ Bd.t()
             err = float((got - want).abs().max() / want.abs().max())
-            print(f"M{M} N{N} K{K} splits{splits} tile_n{tn} a_mn{a_mn} b_mn{b_mn}: err {err:.2e}", flush=True)
+            # the same product as a plain fp32 GEMM (cuBLAS, TF32 off): the accuracy the tensor-core route has to match
+            tf = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            plain = (Ad.float() @ Bd.float().t()).double()
+            torch.backends.cuda.matmul.allow_tf32 = tf
+            e32 = float((plain - want).abs().max() / want.abs().max())
+            rms = float((got - want).pow(2).mean().sqrt() / want.pow(2).mean().sqrt())
+            rms32 = float((plain - want).pow(2).mean().sqrt() / want.pow(2).mean().sqrt())
+            print(f"M{M} N{N} K{K} splits{splits} tile_n{tn} a_mn{a_mn} b_mn{b_mn}: err {err:.2e} (fp32 GEMM {e32:.2e})  "
+                  f"rms {rms:.2e} (fp32 GEMM {rms32:.2e})", flush=True)
 
 
 def bench():

@@ -569,24 +569,36 @@ __global__ void __launch_bounds__(CAE_NT, 1) k_ph_bwd(const PhArgs a) {
     }
 }
 
-// grad_w[e] = sum_rows partials[row][e] (fixed order); CTA = 64 float4 columns x 4 row groups.  CTA 0 also sums the bias rows.
+// grad_w[e] = sum_rows partials[row][e] (fixed order); CTA = 32 float4 columns x 8 row groups, 8 row loads in flight per
+// thread (the rows were just written and sit in L2: the kernel is pure latency - with 64 columns x 4 groups, 4 loads in
+// flight and the bias rows summed by ONE thread per channel it took 12 us, 9.6 of them CTA 0's serial bias loop).
+// One extra CTA sums the bias rows: a warp per channel, lanes over the rows, fixed-order butterfly in float64.
 __global__ void __launch_bounds__(CAE_NT) k_ph_wgrad_reduce(const PhArgs a, long long nelem4) {
-    __shared__ float4 s_p[4][64];
-    const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
-    const long long e4 = (long long)blockIdx.x * 64 + col;
+    __shared__ float4 s_p[8][32];
+    if (blockIdx.x == gridDim.x - 1) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int co = warp; a.grad_b && co < a.Cout; co += CAE_NWARP) {
+            double t = 0.0;
+            for (int r = lane; r < a.rows; r += 32) t += (double)__ldcg(a.dbpart + (size_t)r * a.Cout + co);
+            t = warp_sum_d(t);
+            if (lane == 0) a.grad_b[co] = (float)t;
+        }
+        return;
+    }
+    const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const long long e4 = (long long)blockIdx.x * 32 + col;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e4 < nelem4) {
         const float4* base = reinterpret_cast<const float4*>(a.partials) + e4;
         int r = grp;
-        for (; r + 12 < a.rows; r += 16) {
-            const float4 v0 = __ldcg(base + (size_t)r * nelem4), v1 = __ldcg(base + (size_t)(r + 4) * nelem4);
-            const float4 v2 = __ldcg(base + (size_t)(r + 8) * nelem4), v3 = __ldcg(base + (size_t)(r + 12) * nelem4);
-            s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
-            s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
-            s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
-            s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+        for (; r + 56 < a.rows; r += 64) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcg(base + (size_t)(r + 8 * j) * nelem4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
         }
-        for (; r < a.rows; r += 4) {
+        for (; r < a.rows; r += 8) {
             const float4 v = __ldcg(base + (size_t)r * nelem4);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
@@ -596,13 +608,8 @@ __global__ void __launch_bounds__(CAE_NT) k_ph_wgrad_reduce(const PhArgs a, long
     if (grp == 0 && e4 < nelem4) {
         float4 t = s_p[0][col];
 #pragma unroll
-        for (int g = 1; g < 4; ++g) { t.x += s_p[g][col].x; t.y += s_p[g][col].y; t.z += s_p[g][col].z; t.w += s_p[g][col].w; }
+        for (int g = 1; g < 8; ++g) { t.x += s_p[g][col].x; t.y += s_p[g][col].y; t.z += s_p[g][col].z; t.w += s_p[g][col].w; }
         reinterpret_cast<float4*>(a.grad_w)[e4] = t;
-    }
-    if (blockIdx.x == 0 && a.grad_b && threadIdx.x < a.Cout) {
-        double t = 0.0;
-        for (int r = 0; r < a.rows; ++r) t += (double)a.dbpart[(size_t)r * a.Cout + threadIdx.x];
-        a.grad_b[threadIdx.x] = (float)t;
     }
 }
 
@@ -771,6 +778,6 @@ extern "C" int cae_patch_head_wgrad_reduce(const CaePatchHead* h, float* grad_w,
     a.partials = const_cast<float*>(partials);
     a.dbpart = a.partials + (long long)CAE_NUM_SMS * slots * nelem;
     a.grad_w = grad_w; a.grad_b = grad_b;
-    k_ph_wgrad_reduce<<<ceil_div(nelem / 4, 64), CAE_NT, 0, (cudaStream_t)stream>>>(a, nelem / 4);
+    k_ph_wgrad_reduce<<<ceil_div(nelem / 4, 32) + 1, CAE_NT, 0, (cudaStream_t)stream>>>(a, nelem / 4);
     return cae_check_launch("cae_patch_head_wgrad_reduce");
 }

@@ -17,7 +17,9 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef ST_NT
 #define ST_NT 256
+#endif
 #define ST_NW (ST_NT / 32)
 #define ST_MAX_SPC 4
 #define ST_CMAX 64            // channels per BatchNorm layer

@@ -58,12 +58,11 @@ __device__ __forceinline__ float cae_fast_sigmoid(float v) {
     return r;
 }
 
-// Operand split for the tensor-core paths: x = hi + lo with hi = x ROUNDED to TF32 (round-to-nearest, so |lo| <= 2^-12 |x|
-// instead of 2^-11 with truncation) and lo itself rounded to TF32 (the tensor core would otherwise truncate its low bits).
-// What the split drops is then <= 2^-24 |x| per operand; with the four products hi*hi + hi*lo + lo*hi + lo*lo a product is
-// accurate to ~1.2e-7 relative - within 2x of an fp32 FMA.  (Truncating hi and dropping lo*lo left ~7e-7 per product: on the
-// ill-conditioned sums of the config-4 backward pass the tensor-core layers' gradients sat 4.5e-3 from float64, 20x
-// torch fp32's own distance - tests/test_gpu_conv4.py::test_config4_full_batch_step_vs_float64_on_device.)
+// Operand split for the tensor-core paths: x = hi + lo with hi = x ROUNDED to TF32 (round-to-nearest, so |x - hi| <= 2^-11 |x|
+// instead of 2^-10 with truncation) and lo = (x - hi) itself rounded to TF32 (the tensor core would otherwise truncate its low
+// bits).  What the pair drops is then <= 2^-22 |x|, unbiased; the three products hi*hi + hi*lo + lo*hi (tc_gemm.cu) leave out
+// lo*lo <= 2^-22 of the product.  Measured: a 3xTF32 GEMM with chunked accumulation sits 4 - 7e-7 of the max-norm from
+// float64, flat in K (profiles/r02_tc_precision.md).
 __device__ __forceinline__ float tf32_rn(float v) {
     unsigned r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -72,6 +71,23 @@ __device__ __forceinline__ float tf32_rn(float v) {
 __device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
     hi = tf32_rn(v);
     lo = tf32_rn(v - hi);
+}
+
+// packed fp32 pairs: one FFMA2 (fma.rn.f32x2) issues two IEEE FMAs.  The tile kernels of the wide thin layers
+// (conv_wgrad_tile / conv_up_tile / conv_down_tile) pair two adjacent channels, which arrive as one 8-byte shared-memory
+// load, and so halve the FMA issue slots of their inner loops (bit-identical to scalar fmaf).
+__device__ __forceinline__ unsigned long long wgt_pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void wgt_upk(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long wgt_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

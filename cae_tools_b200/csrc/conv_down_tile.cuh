@@ -86,11 +86,11 @@ __global__ void __launch_bounds__(CAE_NT, 2) k_down_tile(const ConvArgs a, const
         const int n = tile / per_sample, tr = tile - n * per_sample;
         const int tyi = tr / p.tiles_x, txi = tr - tyi * p.tiles_x;
         const int oy = tyi * DT_ROWS + ty, ox0 = (txi * DT_STRIPS + tx) * 4;
-        float acc[COT][4];
+        unsigned long long acc2[COT / 2][4];             // channel pairs (j, j + 1): one FFMA2 per pair (wgt_fma2, bit-identical to fmaf)
 #pragma unroll
-        for (int j = 0; j < COT; ++j)
+        for (int j = 0; j < COT / 2; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+            for (int e = 0; e < 4; ++e) acc2[j][e] = 0ull;
         for (int ci = 0; ci < a.Cin; ++ci) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();                 // stage `buf` landed; everyone finished reading the other stage (and, the first time, s_w / s_coef are visible)
@@ -123,22 +123,30 @@ __global__ void __launch_bounds__(CAE_NT, 2) k_down_tile(const ConvArgs a, const
 #pragma unroll
                     for (int i = 0; i < NVV; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
+                unsigned long long v2[NVV];
+#pragma unroll
+                for (int i = 0; i < NVV; ++i) v2[i] = wgt_pk(v[i], v[i]);
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    float wv[COT];
+                    unsigned long long wv[COT / 2];
 #pragma unroll
                     for (int j = 0; j < COT; j += 4) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(wp + (ky * K + kx) * COT + j);
-                        wv[j] = w4.x; wv[j + 1] = w4.y; wv[j + 2] = w4.z; wv[j + 3] = w4.w;
+                        const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wp + (ky * K + kx) * COT + j);
+                        wv[j / 2] = w4.x; wv[j / 2 + 1] = w4.y;
                     }
 #pragma unroll
                     for (int cx = 0; cx < 4; ++cx)
 #pragma unroll
-                        for (int j = 0; j < COT; ++j) acc[j][cx] = fmaf(v[2 * cx + kx], wv[j], acc[j][cx]);
+                        for (int j = 0; j < COT / 2; ++j) acc2[j][cx] = wgt_fma2(v2[2 * cx + kx], wv[j], acc2[j][cx]);
                 }
             }
             buf ^= 1;
         }
+        float acc[COT][4];
+#pragma unroll
+        for (int j = 0; j < COT / 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) wgt_upk(acc2[j][e], acc[2 * j][e], acc[2 * j + 1][e]);
         if (oy < OH && ox0 < OW) {
 #pragma unroll
             for (int j = 0; j < COT; ++j)

@@ -156,6 +156,78 @@ __global__ void __launch_bounds__(CAE_NT) k_tc_col2im(const float* __restrict__ 
     if (epi_reduces(a.epi.mode)) epi_reduce_tail<COT>(a.epi, a.out, co0, s1, s2);
 }
 
+// ---- the same tail for wide planes (Wout >= 48): a CTA walks tiles of one output row x 64 pixels x 32 channels.  Gather with
+// lane = channel (every tap of a pixel is ONE coalesced 128-byte line of cols; the thread-per-pixel kernel above fetches
+// 32-byte pieces scattered ldn floats apart), transpose through shared memory, epilogue + store with 8 consecutive pixels
+// per channel and warp instruction.  Same tap order per pixel as above, so y is bit-identical; the BatchNorm sums are
+// partitioned differently (8 threads per channel, fixed-order butterfly, one partial row per CTA).
+__global__ void __launch_bounds__(CAE_NT) k_tc_col2im_tile(const float* __restrict__ cols, long long ldn, const ConvArgs a, int Hin,
+                                                            int Win, int xtiles, int ntiles) {
+    __shared__ float so[32][65];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cm = threadIdx.x >> 3, xl = threadIdx.x & 7;          // epilogue role: channel co0 + cm, pixels xl + 8 i
+    const int co0 = blockIdx.y * 32;
+    const int Hout = a.out.H, Wout = a.out.W, Cout = a.Cout;
+    const bool cvalid = co0 + cm < Cout;
+    const EpiCh ech = epi_load_channel(a.epi, co0 + cm, cvalid);
+    float s1 = 0.f, s2 = 0.f;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int xt = tile % xtiles, row = tile / xtiles;
+        const int oy = row % Hout, n = row / Hout;
+        const int ox0 = xt * 64, npx = min(64, Wout - ox0);
+        // a warp owns pixels warp + 8 u: all <= 2 x 2 taps of all eight pixels are requested before the first add (32
+        // independent 128-byte lines in flight per warp; with the taps fetched one after the other behind their bounds
+        // checks a tile cost 23 us of exposed latency).  Missing taps contribute +0.f: same sums as the pixel kernel.
+        float v[8][4];
+        const bool cok = co0 + lane < Cout;
+        const int ky0 = oy % a.s, iy0 = oy / a.s;                    // taps ky0 + s jy hit input rows iy0 - jy
+        const float* cbase = cols + (long long)n * Hin * Win * ldn + co0 + lane;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int ox = ox0 + warp + 8 * u;
+            const int kx0 = ox % a.s, ix0 = ox / a.s;
+#pragma unroll
+            for (int jy = 0; jy < 2; ++jy)
+#pragma unroll
+                for (int jx = 0; jx < 2; ++jx) {
+                    const int ky = ky0 + a.s * jy, kx = kx0 + a.s * jx, iy = iy0 - jy, ix = ix0 - jx;
+                    const bool ok = cok && warp + 8 * u < npx && ky < a.kh && kx < a.kw && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+                    v[u][jy * 2 + jx] = ok ? __ldg(cbase + (long long)(iy * Win + ix) * ldn + (long long)(ky * a.kw + kx) * Cout) : 0.f;
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (warp + 8 * u < npx) so[lane][warp + 8 * u] = ((v[u][0] + v[u][1]) + v[u][2]) + v[u][3];
+        __syncthreads();
+        if (cvalid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int px = xl + 8 * i;
+                if (px < npx) epi_element(a.epi, a.out, ech, n, co0 + cm, oy, ox0 + px, so[cm][px], 0ll, a.inv_count, s1, s2);
+            }
+        }
+        __syncthreads();
+    }
+    if (epi_reduces(a.epi.mode)) {
+        double d1 = (double)s1, d2 = (double)s2;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        }
+        if (xl == 0 && cvalid) {
+            double* dst = a.epi.partials + ((size_t)blockIdx.x * Cout + co0 + cm) * 2;
+            dst[0] = d1;
+            dst[1] = d2;
+        }
+        if (cae_last_block(a.epi.ticket)) {
+            const double count = (double)a.out.N * Hout * Wout;
+            if (a.epi.mode == CAE_EPI_STATS) finalize_bn_forward(a.epi.bn, a.epi.partials, gridDim.x, count);
+            else if (a.epi.mode == CAE_EPI_MASKSTATS) finalize_bn_backward(a.epi.bn, a.epi.partials, gridDim.x, count);
+        }
+    }
+}
+
 // ---- backward operand: dcols[m, (t,co)] = transform(dy)[n, co, s*iy + ky, s*ix + kx] -> hi / lo ------------------------
 template <int COT>
 __global__ void __launch_bounds__(CAE_NT) k_tc_im2col(const CaeSrc dy, float* __restrict__ hi, float* __restrict__ lo,
@@ -198,6 +270,52 @@ __global__ void __launch_bounds__(CAE_NT) k_tc_im2col(const CaeSrc dy, float* __
                         }
                 }
             }
+    }
+}
+
+// ---- the same operand for the layers with wide planes (Win >= 24): a CTA owns 32 consecutive positions of one input row
+// and 32 channels.  The dy rows they touch (kh rows x (31 s + kw) columns per channel) are read ONCE, coalesced, transformed
+// and parked in shared memory; the (position, tap) rows of dcols then leave as full 128-byte lines (lane = channel).  The
+// thread-per-position kernel above reads dy with stride s and scatters 32-byte pieces ldn floats apart: 1.5 TB/s of
+// traffic at the 64 -> 32 layer of BASELINE configs[3] (1.12 ms); this one is bit-identical and HBM-bound.
+__global__ void __launch_bounds__(CAE_NT) k_tc_im2col_tile(const CaeSrc dy, float* __restrict__ hi, float* __restrict__ lo,
+                                                            long long ldn, int kh, int kw, int s, int Hin, int Win, int xtiles,
+                                                            int WT, int cpitch) {
+    extern __shared__ float sv[];                               // [32 channels][cpitch >= kh * WT, odd]
+    const CaeView& dv = dy.t0;
+    const int Cout = dv.C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co0 = blockIdx.y * 32;
+    int b = blockIdx.x;
+    const int xt = b % xtiles;
+    b /= xtiles;
+    const int iy = b % Hin, n = b / Hin;
+    const int ix0 = xt * 32;
+    const int npos = min(32, Win - ix0);
+    const int wt = (npos - 1) * s + kw;                         // columns of dy this tile touches
+    const long long base = src_cursor_offset(dy) + (long long)n * dv.sN + (long long)(iy * s) * dv.ld + ix0 * s;
+    // rows (channel, ky): a warp per row, lanes over the columns
+    for (int r = warp; r < 32 * kh; r += CAE_NWARP) {
+        const int c = r / kh, ky = r - c * kh;
+        if (co0 + c >= Cout) continue;
+        const ChanCoef kc = load_coef(dy, co0 + c);
+        const long long roff = base + (long long)(co0 + c) * dv.sC + (long long)ky * dv.ld;
+        float* dst = sv + c * cpitch + ky * WT;
+        for (int x = lane; x < wt; x += 32) dst[x] = src_value(dy, roff + x, kc);
+    }
+    __syncthreads();
+    if (co0 + lane >= Cout) return;
+    const int T = kh * kw;
+    const long long m0 = ((long long)n * Hin + iy) * Win + ix0;
+    const float* src = sv + lane * cpitch;
+    for (int e = warp; e < npos * T; e += CAE_NWARP) {
+        const int pos = e / T, t = e - pos * T;
+        const int ky = t / kw, kx = t - ky * kw;
+        float h, l;
+        split_tf32(src[ky * WT + pos * s + kx], h, l);
+        const long long o = (m0 + pos) * ldn + (long long)t * Cout + co0 + lane;
+        hi[o] = h;
+        lo[o] = l;
     }
 }
 
@@ -353,6 +471,12 @@ extern "C" int cae_tc_convt_fwd(const CaeTcConv* c, const CaeSrc* in, const floa
     a.total = c->N * c->Hout * c->Wout;
     a.inv_count = 1.f;
     if (epi_reduces(a.epi.mode)) CAE_REQUIRE(a.epi.partials && a.epi.ticket, "tc_convT_fwd: reducing epilogue needs partials + ticket");
+    const long long ntiles = (long long)c->N * c->Hout * ceil_div(c->Wout, 64);
+    if (c->Wout >= 48 && ntiles < (1ll << 31) && c->kh <= 2 * c->stride && c->kw <= 2 * c->stride) {
+        dim3 grid((unsigned)min(ntiles, (long long)CAE_MAX_GRID_X), ceil_div(c->Cout, 32));
+        k_tc_col2im_tile<<<grid, CAE_NT, 0, st>>>(c->cols, c->ldn, a, c->Hin, c->Win, ceil_div(c->Wout, 64), (int)ntiles);
+        return cae_check_launch("k_tc_col2im_tile");
+    }
     dim3 grid(min(ceil_div(a.total, CAE_NT), CAE_MAX_GRID_X), ceil_div(c->Cout, 8));
     k_tc_col2im<8><<<grid, CAE_NT, 0, st>>>(c->cols, c->ldn, a, c->Hin, c->Win);
     return cae_check_launch("k_tc_col2im");
@@ -365,6 +489,16 @@ extern "C" int cae_tc_convt_im2col(const CaeTcConv* c, const CaeSrc* dy, void* s
     CAE_REQUIRE(dy->t0.N == c->N && dy->t0.C == c->Cout && dy->t0.H == c->Hout && dy->t0.W == c->Wout,
                 "tc_convT_im2col: dy view does not match the descriptor");
     const int M = c->N * c->Hin * c->Win;
+    const int WT = 31 * c->stride + c->kw, cpitch = (c->kh * WT) | 1;
+    const size_t smem = (size_t)32 * cpitch * sizeof(float);
+    const long long tiles = (long long)c->N * c->Hin * ceil_div(c->Win, 32);
+    if (c->Win >= 24 && smem <= 96 * 1024 && tiles < (1ll << 31)) {
+        ensure_smem_limit(k_tc_im2col_tile, 96 * 1024);
+        dim3 grid((unsigned)tiles, ceil_div(c->Cout, 32));
+        k_tc_im2col_tile<<<grid, CAE_NT, smem, (cudaStream_t)stream>>>(*dy, c->dcols_hi, c->dcols_lo, c->ldn, c->kh, c->kw, c->stride,
+                                                                     c->Hin, c->Win, ceil_div(c->Win, 32), WT, cpitch);
+        return cae_check_launch("k_tc_im2col_tile");
+    }
     dim3 grid(min(ceil_div(M, CAE_NT), CAE_MAX_GRID_X * 4), ceil_div(c->Cout, 8));
     k_tc_im2col<8><<<grid, CAE_NT, 0, (cudaStream_t)stream>>>(*dy, c->dcols_hi, c->dcols_lo, c->ldn, c->kh, c->kw, c->stride,
                                                              c->Hin, c->Win, M);

@@ -59,7 +59,7 @@ class CaePatchHead(C.Structure):
     _fields_ = [("inp", CaeSrc), ("weight", C.c_void_p), ("bias", C.c_void_p), ("K", C.c_int), ("Cout", C.c_int),
                 ("target", CaeSrc), ("mask", CaeSrc), ("mask_channels", C.c_int), ("lambda_pearson", C.c_float),
                 ("count_scale", C.c_float), ("moments", C.c_void_p), ("coef", C.c_void_p), ("scalars", C.c_void_p),
-                ("loss_out", C.c_void_p), ("pearson_out", C.c_void_p), ("ticket", C.c_void_p)]
+                ("loss_out", C.c_void_p), ("pearson_out", C.c_void_p), ("ticket", C.c_void_p), ("mse_scale", C.c_void_p)]
 
 
 class CaeFcStack(C.Structure):
@@ -177,7 +177,7 @@ EXPORTS = {
     "cae_sum_over_n": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cae_masked_pearson_loss": (C.c_int, [C.POINTER(CaeView), C.POINTER(CaeSrc), C.POINTER(CaeSrc), C.c_int, C.c_float,
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.POINTER(CaeView), C.c_void_p, C.c_void_p]),
+                                          C.POINTER(CaeView), C.c_void_p, C.c_void_p, C.c_void_p]),
     "cae_attention_block_supported": (C.c_int, [C.c_int] * 4),
     "cae_attention_block_partials_len": (C.c_longlong, [C.c_int, C.c_int]),
     "cae_attention_block_fwd": (C.c_int, [C.POINTER(CaeView), C.POINTER(CaeSrc), C.c_void_p, C.c_void_p, C.c_int,

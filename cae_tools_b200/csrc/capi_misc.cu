@@ -170,7 +170,7 @@ extern "C" int cae_sum_over_n(const float* in, int N, int C, float* out, void* s
 extern "C" int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target, const CaeSrc* mask, int mask_channels,
                                        float lambda_pearson, float count_scale, double* moments, float* coef,
                                        float* scalars, float* loss_out, float* pearson_out, const CaeView* dz,
-                                       float* plane_sum, void* stream) {
+                                       float* plane_sum, const float* mse_scale, void* stream) {
     CAE_REQUIRE(pred && target && moments && coef && scalars, "masked_pearson_loss: null argument");
     int rc = check_view(*pred, "masked_pearson_loss pred");
     if (rc) return rc;
@@ -193,6 +193,7 @@ extern "C" int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target
     a.moments = moments; a.coef = coef; a.scalars = scalars;
     a.loss_out = loss_out; a.pearson_out = pearson_out;
     a.lambda_pearson = lambda_pearson; a.count_scale = count_scale;
+    a.mse_scale = mse_scale;
     cudaStream_t st = (cudaStream_t)stream;
     const int planes = pred->N * pred->C;
     k_mp_moments<<<planes, CAE_NT, 0, st>>>(a);

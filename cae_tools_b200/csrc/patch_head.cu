@@ -41,6 +41,7 @@ struct PhArgs {
     float* pearson_out;
     unsigned int* ticket;
     float lambda_pearson, count_scale;
+    const float* mse_scale;    // per-batch factor of the masked-MSE term (replaces count_scale there), may be NULL
     int pixels_per_plane;
     // backward
     CaeView dout;              // [N, Cin, Hin, Win]
@@ -208,11 +209,13 @@ __device__ __forceinline__ void ph_finalize(const PhArgs& a, int rows_per_plane)
     if (threadIdx.x == 0) {
         const double cs = a.count_scale > 0.f ? (double)a.count_scale : 1.0;
         const double mse = SQ / CNT;
-        a.scalars[0] = (float)(2.0 / CNT * cs);
+        const int slot = a.target.cursor ? __ldg(a.target.cursor) : 0;
+        // data parallelism with masks: this share's valid pixels / the global batch's (see cae_b200.h)
+        const double cm = a.mse_scale ? (double)__ldg(a.mse_scale + slot) : cs;
+        a.scalars[0] = (float)(2.0 / CNT * cm);
         a.scalars[1] = (float)mse;
         a.scalars[2] = (float)(1.0 - CS / NC);
-        const int slot = a.target.cursor ? __ldg(a.target.cursor) : 0;
-        if (a.loss_out) a.loss_out[slot] = (float)(mse * cs);
+        if (a.loss_out) a.loss_out[slot] = (float)(mse * cm);
         if (a.pearson_out) a.pearson_out[slot] = (float)((1.0 - CS / NC) * cs);
     }
 }
@@ -634,6 +637,7 @@ static int ph_fill(PhArgs& a, const CaePatchHead* h) {
     a.moments = h->moments; a.coef = h->coef; a.scalars = h->scalars;
     a.loss_out = h->loss_out; a.pearson_out = h->pearson_out; a.ticket = h->ticket;
     a.lambda_pearson = h->lambda_pearson; a.count_scale = h->count_scale;
+    a.mse_scale = h->mse_scale;
     const int Ho = h->K * a.Hin, Wo = h->K * a.Win;
     a.pixels_per_plane = Ho * Wo;
     if (a.target.t0.p) {

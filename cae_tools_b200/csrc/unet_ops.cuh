@@ -229,6 +229,7 @@ struct MaskedPearsonArgs {
     float* pearson_out;      // pearson_out[slot] = 1 - mean corr
     float lambda_pearson;
     float count_scale;
+    const float* mse_scale;  // per-batch factor of the masked-MSE term (replaces count_scale there), may be NULL
 };
 
 __device__ __forceinline__ float mp_mask(const MaskedPearsonArgs& a, long long mbase, int n, int c, int r, int x) {
@@ -296,11 +297,13 @@ static __global__ void __launch_bounds__(CAE_NT) k_mp_finalize(const MaskedPears
     if (threadIdx.x == 0) {
         const double cs = a.count_scale > 0.f ? (double)a.count_scale : 1.0;
         const double mse = SQ / CNT;
-        a.scalars[0] = (float)(2.0 / CNT * cs);
+        const int slot = a.target.cursor ? __ldg(a.target.cursor) : 0;
+        // data parallelism with masks: this share's valid pixels / the global batch's (see cae_b200.h)
+        const double cm = a.mse_scale ? (double)__ldg(a.mse_scale + slot) : cs;
+        a.scalars[0] = (float)(2.0 / CNT * cm);
         a.scalars[1] = (float)mse;
         a.scalars[2] = (float)(1.0 - CS / NC);
-        const int slot = a.target.cursor ? __ldg(a.target.cursor) : 0;
-        if (a.loss_out) a.loss_out[slot] = (float)(mse * cs);
+        if (a.loss_out) a.loss_out[slot] = (float)(mse * cm);
         if (a.pearson_out) a.pearson_out[slot] = (float)((1.0 - CS / NC) * cs);
     }
 }

@@ -582,7 +582,8 @@ class ConvAEEngine:
                 X2 = torch.empty(2 * B, *xh.shape[1:], dtype=torch.float32, device=self.device)
                 Y2 = torch.empty(2 * B, *yh.shape[1:], dtype=torch.float32, device=self.device)
                 if mh is not None:
-                    st["data"] = self.bind(X2, Y2, B, mask=torch.empty(2 * B, *mh.shape[1:], dtype=torch.float32, device=self.device))
+                    st["data"] = self.bind(X2, Y2, B, mask=torch.zeros(2 * B, *mh.shape[1:], dtype=torch.float32, device=self.device))
+                    st["data"].mse_scale = None      # streamed masks are not known at bind time: constant count_scale
                 else:
                     st["data"] = self.bind(X2, Y2, B)
                 st["prog"] = self._program("train", st["data"], B)

@@ -7,10 +7,10 @@ decoder + fc gradients are SUM-all-reduced asynchronously while the encoder back
 right after it; the optimiser waits for both (engine/convae.py:_BucketedProgram).  Each rank computes on its contiguous share of
 every global batch; the loss epilogue divides by the GLOBAL element count (count_scale =
 n_local/n_global), so the summed gradients - and the summed per-batch losses - are exactly those of
-the global batch for the plain MSE.  The UNET's masked MSE divides by the mask count: with count_scale = 1/world the
-sum over ranks equals the global masked MSE only when every rank's share of a batch has the same number of valid
-pixels; with land/sea masks it is the mean of the per-share masked MSEs instead (a different weighting of the same
-pixels, exact again for mask-free data).  BatchNorm uses the statistics of the local share ("local BN").  `apply` shards the
+the global batch for the plain MSE.  The UNET's masked MSE divides by the mask count: there the constant is replaced by
+a per-batch factor, valid pixels of the share / valid pixels of the global batch (`DPContext.mask_scales`, all-reduced
+once at bind time, read by the loss kernels at the batch cursor: `mse_scale` in cae_b200.h), so the sum over ranks is the
+global sum((d-t)^2 m^2) / sum(m) for any land / sea split (host-streamed batches, `train_stream`, keep the constant).  BatchNorm uses the statistics of the local share ("local BN").  `apply` shards the
 samples over ranks with no collective at all.
 """
 
@@ -64,6 +64,18 @@ class DPContext:
         """the per-step exchange: in-place SUM over ranks of the flat gradient arena"""
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         return flat
+
+    def mask_scales(self, mask, batch_size):
+        """mask [n_local, c, H, W] of this rank's shares in batch order -> float32 [n_batches]: valid pixels of the share /
+        valid pixels of the global batch (one SUM all-reduce; every rank holds the same number of batches).  The factor the
+        masked-MSE term of a share is multiplied with so that the shares' losses and gradients ADD UP to the global
+        batch's sum((d-t)^2 m^2) / sum(m), whatever the split of valid pixels between the ranks."""
+        n = int(mask.shape[0])
+        per_sample = mask.sum(dim=(1, 2, 3), dtype=torch.float64)
+        local = torch.stack([per_sample[lo:lo + batch_size].sum() for lo in range(0, n, batch_size)])
+        total = local.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        return (local / total.clamp_min(1e-300)).to(torch.float32).contiguous()
 
     def allreduce_grads_async(self, bucket):
         """one gradient bucket (a contiguous slice of the flat arena): SUM over ranks, asynchronous; the caller keeps

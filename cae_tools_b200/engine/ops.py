@@ -241,11 +241,11 @@ def sum_over_n(inp, N, Cn, out):
 
 
 def masked_pearson_loss(pred: CaeView, target: CaeSrc, mask, mask_channels, lambda_pearson, count_scale, moments, coef,
-                        scalars, loss_out, pearson_out, dz=None, plane_sum=None):
+                        scalars, loss_out, pearson_out, dz=None, plane_sum=None, mse_scale=None):
     check(lib().cae_masked_pearson_loss(C.byref(pred), C.byref(target), C.byref(mask) if mask is not None else None,
                                         int(mask_channels), float(lambda_pearson), float(count_scale), _ptr(moments),
                                         _ptr(coef), _ptr(scalars), _ptr(loss_out), _ptr(pearson_out),
-                                        C.byref(dz) if dz is not None else None, _ptr(plane_sum), _stream()),
+                                        C.byref(dz) if dz is not None else None, _ptr(plane_sum), _ptr(mse_scale), _stream()),
           "cae_masked_pearson_loss")
 
 
@@ -256,7 +256,7 @@ def patch_head_supported(K, stride, pad, Cin, Win) -> bool:
 
 def make_patch_head(src: CaeSrc, weight, bias, K, Cout, target=None, mask=None, mask_channels=0, lambda_pearson=0.0,
                     count_scale=1.0, moments=None, coef=None, scalars=None, loss_out=None, pearson_out=None,
-                    ticket=None) -> CaePatchHead:
+                    ticket=None, mse_scale=None) -> CaePatchHead:
     h = CaePatchHead()
     h.inp = src
     h.weight = _ptr(weight)
@@ -273,7 +273,8 @@ def make_patch_head(src: CaeSrc, weight, bias, K, Cout, target=None, mask=None, 
     h.moments, h.coef, h.scalars = _ptr(moments), _ptr(coef), _ptr(scalars)
     h.loss_out, h.pearson_out = _ptr(loss_out), _ptr(pearson_out)
     h.ticket = _ptr(ticket)
-    h._keep = (src, weight, bias, target, mask, moments, coef, scalars, loss_out, pearson_out, ticket)
+    h.mse_scale = _ptr(mse_scale)
+    h._keep = (src, weight, bias, target, mask, moments, coef, scalars, loss_out, pearson_out, ticket, mse_scale)
     return h
 
 

@@ -51,9 +51,20 @@ class UNetEngine(ConvAEEngine):
     def bind(self, X, Y, batch_size, mask=None):
         data = super().bind(X, Y, batch_size)
         data.M = mask.to(self.device, torch.float32).contiguous() if mask is not None else None
+        data.mse_scale = self._mse_scale(data)
         data.pearson = torch.zeros(data.n_batches, dtype=torch.float32, device=self.device)
         data.extra_state = [data.pearson]
         return data
+
+    def _mse_scale(self, data):
+        """Data parallelism with a mask: per batch, the valid pixels of this rank's share over those of the global batch (one
+        all-reduce at bind time - masks are data).  With it the masked-MSE term each rank forms, SQ_local / CNT_local, is
+        weighted so that the SUM over ranks is SQ_global / CNT_global exactly, whatever the land / sea split between the
+        shares; without a mask (or without ranks) the constant count_scale = 1 / world is already exact -> None."""
+        dp = getattr(self, "dp", None)
+        if dp is None or data.M is None:
+            return None
+        return dp.mask_scales(data.M, data.batch_size)
 
     def batch_losses(self, data):
         return data.losses                        # the reference's history records the masked MSE term only
@@ -160,7 +171,7 @@ class UNetEngine(ConvAEEngine):
         return ops.make_patch_head(src, conv.weight, conv.bias, k, co, target=tgt, mask=msk, mask_channels=mch,
                                    lambda_pearson=self.lambda_pearson, count_scale=self.count_scale,
                                    moments=b["ph_moments"], coef=b["coef"], scalars=b["scalars"], loss_out=data.losses,
-                                   pearson_out=data.pearson, ticket=self._ticket())
+                                   pearson_out=data.pearson, ticket=self._ticket(), mse_scale=data.mse_scale)
 
     def _last_layer_ops(self, S, b, N, data, src, conv, sp, j, final):
         """last transposed conv + sigmoid (+ loss): the fused patch head when the geometry allows it, else generic"""
@@ -183,7 +194,8 @@ class UNetEngine(ConvAEEngine):
             dz = ops.view4(b["dzL"], N) if final == "loss_grad" else None
             S.append(("loss.masked_mse+pearson", lambda tgt=tgt, msk=msk, mch=mch, dz=dz: ops.masked_pearson_loss(
                 ops.view4(b["yhat"], N), tgt, msk, mch, self.lambda_pearson, self.count_scale, b["moments"], b["coef"],
-                b["scalars"], data.losses, data.pearson, dz, b["psL"] if dz is not None else None)))
+                b["scalars"], data.losses, data.pearson, dz, b["psL"] if dz is not None else None,
+                mse_scale=data.mse_scale)))
 
     def _eval_stem(self):
         """descriptor of the fused eval-mode stem (cached), or None when the geometry does not fit the kernel"""

@@ -220,10 +220,15 @@ int cae_sum_over_n(const float* in, int N, int C, float* out, void* stream);
 /* masked MSE + lambda * (1 - mean Pearson) (unet.py:314-320,635-678): pred = sigmoid output; mask may be absent
  * (mask->t0.p NULL = ones) and has 1 or C channels.  Writes loss_out[slot] = masked MSE, pearson_out[slot] =
  * 1 - mean corr; with dz != NULL also dL/d(pre-sigmoid) and its plane sums (bias gradient pieces).
- * moments: N*C*7 doubles, coef: N*C*3 floats, scalars: 3 floats of workspace. */
+ * moments: N*C*7 doubles, coef: N*C*3 floats, scalars: 3 floats of workspace.
+ * mse_scale (device, may be NULL): per-batch factor of the masked-MSE term, read at the target's cursor slot, used INSTEAD of
+ * count_scale for that term - data parallelism with masks: valid pixels of this rank's share / valid pixels of the
+ * global batch, so that the SUM over ranks is sum((d-t)^2 m^2) / sum(m) of the global batch exactly (the Pearson term is a
+ * mean over samples and keeps count_scale). */
 int cae_masked_pearson_loss(const CaeView* pred, const CaeSrc* target, const CaeSrc* mask, int mask_channels,
                             float lambda_pearson, float count_scale, double* moments, float* coef, float* scalars,
-                            float* loss_out, float* pearson_out, const CaeView* dz, float* plane_sum, void* stream);
+                            float* loss_out, float* pearson_out, const CaeView* dz, float* plane_sum,
+                            const float* mse_scale, void* stream);
 
 /* ---- fc bottleneck in one launch per direction (replaces the cae_gemm / cae_ew_epilogue chain when it fits one CTA) --
  * ConvAEModel (encoder.py:52-58, decoder.py:29-35):  Linear ReLU Linear | Linear ReLU Linear           (bn*.C == 0, relu_mid 0)
@@ -388,6 +393,7 @@ typedef struct CaePatchHead {
     float*        loss_out;
     float*        pearson_out;
     unsigned int* ticket;         /* 1 x u32, zero before first use (loss only) */
+    const float*  mse_scale;      /* device, may be NULL: as cae_masked_pearson_loss.mse_scale */
 } CaePatchHead;
 int       cae_patch_head_supported(int K, int stride, int pad, int Cin, int Win);
 int       cae_patch_head_fwd(const CaePatchHead* h, const CaeView* yhat, void* stream);

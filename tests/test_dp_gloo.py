@@ -105,6 +105,22 @@ def _worker(rank, world, port, out_dir):
         if dead:
             continue    # zero true gradient; autograd's rounding noise is amplified differently by Adam
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5), k
+    # masked MSE under data parallelism (DPContext.mask_scales): with the per-batch factor CNT_share / CNT_global the shares'
+    # masked-MSE terms add up to the global batch's sum((d-t)^2 m^2) / sum(m) although the ranks see very different masks
+    gm = torch.Generator().manual_seed(9)
+    d, t = torch.rand(2 * world, 1, 8, 8, generator=gm), torch.rand(2 * world, 1, 8, 8, generator=gm)
+    keep = torch.linspace(0.9, 0.1, 2 * world).view(-1, 1, 1, 1)
+    msk = (torch.rand(2 * world, 1, 8, 8, generator=gm) < keep).float()
+    mine = slice(2 * rank, 2 * rank + 2)                      # two batches of one sample per rank: global batches (0,2), (1,3)
+    scales = dp.mask_scales(msk[mine], 1)
+    assert scales.dtype == torch.float32 and scales.shape == (2,)
+    for b in range(2):
+        idx = [b + 2 * r for r in range(world)]
+        want = float(((d[idx] - t[idx]) ** 2 * msk[idx] ** 2).sum() / msk[idx].sum())
+        i = 2 * rank + b
+        part = ((d[i] - t[i]) ** 2 * msk[i] ** 2).sum() / msk[i].sum() * scales[b]
+        got = float(dp.reduce_losses(part.reshape(1))[0])
+        assert abs(got - want) <= 1e-6 * want, (b, got, want)
     if rank == 0:
         open(os.path.join(out_dir, "ok"), "w").write("ok")
     dist.destroy_process_group()

@@ -450,3 +450,63 @@ def test_unet_loss_curve_50_epochs_vs_reference():
     lo, hi = m.normalisation_parameters[2], m.normalisation_parameters[3]
     pred = (np.asarray(te["est"].data)[:4] - lo) / (hi - lo)
     assert np.max(np.abs(pred[:, :, ::8, ::8] - g["pred_sub"])) < 1e-4
+
+
+def test_masked_loss_per_batch_scale_makes_rank_shares_sum_to_the_global_batch():
+    """Data parallelism with a land / sea mask: a rank forms SQ_local / CNT_local; with the constant
+    count_scale = 1 / world the sum over ranks is the MEAN of the per-share masked MSEs, not the global masked MSE.  The
+    per-batch `mse_scale` = CNT_local / CNT_global (engine/unet.py:_mse_scale, all-reduced at bind time) makes loss and
+    gradient of the shares add up to those of the global batch exactly.  Here: two "ranks" evaluated one after the other on
+    one GPU - (a) the generic loss kernel with its gradient, (b) the fused patch head through an eval-mode engine."""
+    from cae_tools_b200.engine import ops
+    from cae_tools_b200.engine.unet import UNetEngine
+    from cae_tools_b200.models.unet_modules import UNetDecoder, UNetEncoder
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(11)
+    N, H = 4, 32
+    pred = (0.05 + 0.9 * torch.rand(N, 1, H, H, generator=gen)).to(dev)
+    tgt = torch.rand(N, 1, H, H, generator=gen).to(dev)
+    keep = torch.tensor([0.9, 0.8, 0.3, 0.1]).view(N, 1, 1, 1)
+    mask = (torch.rand(N, 1, H, H, generator=gen) < keep).float().to(dev)
+
+    def run(lo, hi, count_scale, mse_scale):
+        n = hi - lo
+        p, t, m = pred[lo:hi].contiguous(), tgt[lo:hi].contiguous(), mask[lo:hi].contiguous()
+        moments = torch.zeros(n * 7, dtype=torch.float64, device=dev)
+        coef, scalars = torch.zeros(n * 3, device=dev), torch.zeros(3, device=dev)
+        loss, pl = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+        dz, ps = torch.zeros_like(p), torch.zeros(n, device=dev)
+        ops.masked_pearson_loss(ops.view4(p), ops.make_src(t), ops.make_src(m), 1, 0.7, count_scale, moments, coef, scalars,
+                                loss, pl, ops.view4(dz), ps, mse_scale=mse_scale)
+        torch.cuda.synchronize()
+        return float(loss), float(pl), dz.cpu()
+
+    L, P, DZ = run(0, N, 1.0, None)
+    total = float(mask.sum())
+    sc = [torch.tensor([float(mask[lo:hi].sum()) / total], device=dev) for lo, hi in ((0, 2), (2, 4))]
+    parts = [run(lo, hi, 0.5, s) for (lo, hi), s in zip(((0, 2), (2, 4)), sc)]
+    assert abs(parts[0][0] + parts[1][0] - L) <= 1e-6 * L
+    assert abs(parts[0][1] + parts[1][1] - P) <= 1e-5 * abs(P)
+    dz = torch.cat([parts[0][2], parts[1][2]])
+    assert float((dz - DZ).abs().max()) <= 2e-6 * float(DZ.abs().max())
+    # the constant scale alone does NOT reproduce the global batch for these unequal shares (the test has teeth)
+    plain = [run(lo, hi, 0.5, None) for lo, hi in ((0, 2), (2, 4))]
+    assert abs(plain[0][0] + plain[1][0] - L) > 1e-3 * L
+
+    # (b) fused patch head, eval-mode engine (running statistics: no coupling between the samples of a batch)
+    spec, _ = _shipped_spec()
+    torch.manual_seed(3)
+    enc, dec = UNetEncoder(spec.get_input_layers(), 8, 32, 0.0), UNetDecoder(spec.get_output_layers(), 8, 32, 0.0)
+    x, y = torch.rand(N, 1, 16, 16, generator=gen), torch.rand(N, 1, 256, 256, generator=gen)
+    m = (torch.rand(N, 1, 256, 256, generator=gen) < keep).float()
+    full = UNetEngine(enc, dec, lambda_pearson=0.7, dropout_rate=0.0)
+    want = float(full.test_epoch(full.bind(x, y, N, mask=m)).cpu()[0])
+    share = UNetEngine(enc, dec, lambda_pearson=0.7, dropout_rate=0.0, count_scale=0.5)
+    got = 0.0
+    for lo, hi in ((0, 2), (2, 4)):
+        data = share.bind(x[lo:hi], y[lo:hi], 2, mask=m[lo:hi])
+        data.mse_scale = torch.tensor([float(m[lo:hi].sum() / m.sum())], device=dev)
+        names = [n for n, _ in share._program("test", data, 2).sched]
+        assert any("head" in n for n in names), names
+        got += float(share.test_epoch(data).cpu()[0])
+    assert abs(got - want) <= 2e-6 * want, (got, want)

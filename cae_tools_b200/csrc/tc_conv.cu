@@ -432,8 +432,10 @@ extern "C" long long cae_tc_convt_wgrad_splits(const CaeTcConv* c) {
     const long long tiles = (long long)((c->Cin + 127) / 128) * ((TC + bn - 1) / bn);
     const long long nkb = (P + 31) / 32;
     long long splits = (2 * CAE_NUM_SMS + tiles - 1) / tiles;
-    // the tensor core truncates its fp32 accumulation once per MMA: keep a slice's chain at <= 64 K blocks (2048
-    // positions) so the error stays ~5e-6 of the max-norm however many positions the layer has
+    // at most 64 K blocks (2048 positions) per slice.  Introduced when one TMEM accumulator ran over a slice's whole K range
+    // (truncation error linear in K); the GEMM now promotes every 2 K blocks into round-to-nearest register sums, so the
+    // cap is no longer needed for accuracy - it is kept because the extra slices cost < 20 MB of partial tiles and the
+    // parity fixtures were recorded with it
     if (splits < (nkb + 63) / 64) splits = (nkb + 63) / 64;
     if (splits > nkb / 8) splits = nkb / 8;
     if (splits < 1) splits = 1;

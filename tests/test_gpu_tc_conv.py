@@ -19,6 +19,10 @@ CASES = [
     (5, 160, 136, 3, 2, 0, 9, 9),      # several M / N tiles, split-K weight gradient
     (128, 1024, 512, 3, 2, 0, 3, 3),   # BASELINE configs[3], first decoder layer at the full batch
     (128, 64, 32, 3, 2, 0, 63, 63),    # ... and the last tensor-core layer (508 k positions: 248 split-K slices)
+    # wide planes -> the tile kernels of the pack passes (k_tc_im2col_tile: Win >= 24, k_tc_col2im_tile: Wout >= 48):
+    (3, 64, 40, 3, 2, 1, 9, 30),       # partial channel chunk (32 + 8), output_padding, one ragged 30-position tile per row
+    (2, 32, 8, 4, 2, 0, 6, 40),        # 4-wide kernel (every output pixel has 2 x 2 taps), two position tiles per row (32 + 8)
+    (2, 96, 36, (3, 4), 2, 0, 5, 33),  # tuple kernel, channel chunks 32 + 4, tiles 32 + 1
 ]
 
 

@@ -405,7 +405,7 @@ extern "C" int cae_tc_gemm(const CaeTcGemm* g, void* stream) {
     return launch<128, 3>(g, maps, p, grid, st);
 }
 
-// ---- operand split: hi = x with the low 13 mantissa bits cleared, lo = x - hi ---------------------------------------------
+// ---- operand split: hi = x rounded to TF32, lo = x - hi rounded to TF32 (common.cuh: tf32_split) -------------------------
 __global__ void k_tc_split(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;

@@ -391,7 +391,7 @@ def fc_stack_bwd(p: CaeFcStack):
 
 # ---- tensor-core GEMM (tcgen05 / TMEM / TMA) ---------------------------------------------------------------------------
 def tc_split(x, hi, lo):
-    """hi = x with the low 13 mantissa bits cleared, lo = x - hi (operands of the 3xTF32 GEMM)"""
+    """hi = x rounded to TF32, lo = x - hi rounded to TF32 (operands of the 3xTF32 GEMM; the pair drops <= 2^-22 |x|)"""
     check(lib().cae_tc_split(_ptr(x), _ptr(hi), _ptr(lo), int(x.numel()), _stream()), "cae_tc_split")
 
 
